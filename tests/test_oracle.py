@@ -1,0 +1,190 @@
+"""
+CPU tests of the oracle (the C++ restatement of the reference) against every pin
+the reference's own tests hold for the hot path.  No GPU needed.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+# ---------------------------------------------------------------- .NET Random
+def test_dotnet_random_known_answers(oracle):
+    gold = json.load(open(GOLD / "dotnet_random.json"))["next"]
+    for seed, vals in gold.items():
+        got = oracle.dotnet_next(int(seed), len(vals))
+        assert list(got) == vals
+
+
+def test_dotnet_next_single_range_and_determinism(oracle):
+    a = oracle.dotnet_next_single(65537, 4096)
+    b = oracle.dotnet_next_single(65537, 4096)
+    assert np.array_equal(a, b)
+    assert a.min() >= 0.0 and a.max() < 1.0
+    assert abs(a.mean() - 0.5) < 0.02
+
+
+def test_level_distribution(oracle):
+    # GraphData.cs:211-219 with the default rate 1/ln16: P(level >= 1) = 1/16
+    lv = oracle.draw_levels(31337, 1.0 / np.log(16.0), 200000)
+    assert lv.min() == 0
+    assert abs((lv >= 1).mean() - 1 / 16) < 0.003
+    assert abs((lv >= 2).mean() - 1 / 256) < 0.001
+
+
+# ---------------------------------------------------------------- metrics
+@pytest.mark.parametrize("dim", [96, 100, 127, 128, 960])
+def test_metric_scalar_equals_avx_bitwise(oracle, dim):
+    if not oracle.lib().orc_have_avx():
+        pytest.skip("oracle built without AVX")
+    g = np.load(GOLD / "metric_float64.npz")
+    for name, a, b in (("sq_euclid", g[f"a_{dim}"], g[f"b_{dim}"]), ("cosine", g[f"a_{dim}"], g[f"b_{dim}"]),
+                       ("ucosine", g[f"an_{dim}"], g[f"bn_{dim}"])):
+        s = oracle.metric_many(name, a, b, impl=0)
+        v = oracle.metric_many(name, a, b, impl=1)
+        assert np.array_equal(s.view(np.uint32), v.view(np.uint32)), name
+
+
+@pytest.mark.parametrize("dim", [96, 100, 127, 128, 960])
+def test_metric_against_float64_golden(oracle, dim):
+    # bindings/__tests__/metric_test.py:51,72,95 -- atol 1e-5 against float64 numpy
+    g = np.load(GOLD / "metric_float64.npz")
+    sq = oracle.metric_many("sq_euclid", g[f"a_{dim}"], g[f"b_{dim}"])
+    assert np.allclose(sq, g[f"sq_{dim}"], rtol=1e-5, atol=1e-5)
+    cos = oracle.metric_many("cosine", g[f"a_{dim}"], g[f"b_{dim}"])
+    assert np.allclose(cos, g[f"cos_{dim}"], rtol=0, atol=1e-5)
+    uc = oracle.metric_many("ucosine", g[f"an_{dim}"], g[f"bn_{dim}"])
+    assert np.allclose(uc, g[f"ucos_{dim}"], rtol=0, atol=1e-5)
+
+
+def test_metric_symmetry_bitwise(oracle):
+    # GraphData.Distance(int, TVector) passes (item, query); operand order must not matter
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((200, 127)).astype(np.float32)
+    b = rng.standard_normal((200, 127)).astype(np.float32)
+    for name in ("sq_euclid", "cosine", "ucosine"):
+        x = oracle.metric_many(name, a, b)
+        y = oracle.metric_many(name, b, a)
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
+def test_cosine_zero_vector(oracle):
+    # CosineMetric.cs:89-90: denom < 1e-30 -> 1
+    z = np.zeros(128, dtype=np.float32)
+    o = np.ones(128, dtype=np.float32)
+    assert oracle.metric("cosine", z, o) == 1.0
+    assert oracle.metric("sq_euclid", z, z) == 0.0
+
+
+# ---------------------------------------------------------------- reference windows
+def _fixture(oracle, name):
+    n = {"v2000": 2000, "v1000": 1000, "v5000": 5000}[name]
+    return oracle.normalize_rows_like_reference(oracle.random_vectors(128, n))
+
+
+@pytest.mark.parametrize("case", json.load(open(GOLD / "reference_windows.json")), ids=lambda c: c["name"])
+def test_reference_recall_windows(oracle, case):
+    v = _fixture(oracle, case["fixture"])
+    ix = oracle.OracleIndex(case["metric"], **case["params"])
+    ids = ix.add(v)
+    r = oracle.self_recall(ix, v, ids)
+    assert case["lo"] < r < case["hi"], (case["cite"], r)
+    # regression pin of the restatement itself (deterministic: seeded, serial)
+    assert abs(r - case["oracle_value"]) < 1e-9
+
+
+def test_parameter_allow_removals_false(oracle):
+    # ParametersTests.cs:69-88: AllowRemovals=false, Add(List), sq_euclid, un-normalised
+    v = oracle.random_vectors(128, 1000)
+    ix = oracle.OracleIndex("sq_euclid", allow_removals=False)
+    ids = ix.add(v, threads=4)
+    assert oracle.self_recall(ix, v, ids) > 0.9
+    assert all(ix.row(i, 0, which=1) is None for i in range(0, 1000, 97))  # MaxInEdges == 0
+
+
+def test_query_determinism_serial_vs_parallel(oracle):
+    # GraphTests.cs:83-120
+    v = _fixture(oracle, "v2000")
+    ix = oracle.OracleIndex("ucosine")
+    ix.add(v)
+    a, _ = ix.knn_query(v, 10, threads=1)
+    b, _ = ix.knn_query(v, 10, threads=8)
+    assert np.array_equal(a, b)
+
+
+def _in_out_balanced(ix, n):
+    tot_out = tot_in = 0
+    for i in range(n):
+        for layer in range(ix.node_level(i) + 1):
+            tot_out += len(ix.row(i, layer, 0))
+            tot_in += len(ix.row(i, layer, 1))
+    return tot_out, tot_in
+
+
+def test_build_multithread_recall_and_balance(oracle):
+    # GraphTests.cs:40-80: Parallel.For build, recall > 0.85, AvgOutEdges == AvgInEdges
+    v = _fixture(oracle, "v2000")
+    ix = oracle.OracleIndex("ucosine")
+    ids = ix.add(v, threads=8)
+    assert sorted(ids) == list(range(2000))
+    r = oracle.self_recall(ix, v[np.argsort(ids)], None)
+    assert r > 0.85
+    o, i = _in_out_balanced(ix, 2000)
+    assert o == i
+
+
+def test_readme_example_config1(oracle):
+    # README.md:80-96 / BASELINE config[0]: 2000 x 128 rand, sq_euclid, MaxEdges 16, k=1
+    rng = np.random.default_rng(1234)
+    v = rng.random((2000, 128), dtype=np.float32)
+    ix = oracle.OracleIndex("sq_euclid", collection_size=2000, max_edges=16)
+    ids = ix.add(v)
+    assert oracle.self_recall(ix, v, ids) > 0.85  # recall_test.py:15
+
+
+# ---------------------------------------------------------------- snapshot
+@pytest.mark.parametrize("packed", [False, True])
+def test_encode_decode_roundtrip(oracle, tmp_path, packed):
+    # GraphSerializationTests.cs:17-48: identical Id and Distance (exact) for k=5 on all queries
+    v = oracle.random_vectors(128, 2000)
+    ix = oracle.OracleIndex("sq_euclid")
+    ix.add(v)
+    path = tmp_path / "snap.bin"
+    ix.serialize(path, packed=packed)
+    ix2 = oracle.OracleIndex.deserialize("sq_euclid", path)
+    assert ix2.count == 2000 and ix2.dim == 128 and ix2.entry_point == ix.entry_point
+    assert ix2.params() == ix.params()
+    a_ids, a_d = ix.knn_query(v, 5)
+    b_ids, b_d = ix2.knn_query(v, 5)
+    assert np.array_equal(a_ids, b_ids)
+    assert np.array_equal(a_d.view(np.uint32), b_d.view(np.uint32))
+    assert np.array_equal(ix.items(), ix2.items())
+
+
+def test_snapshot_quirks(oracle, tmp_path):
+    # AllowRemovals=false is omitted on write (zero default) and must be inferred on read
+    v = oracle.random_vectors(16, 50)
+    ix = oracle.OracleIndex("sq_euclid", allow_removals=False, random_seed=7, min_nn=3)
+    ix.add(v)
+    p = tmp_path / "s.bin"
+    ix.serialize(p)
+    ix2 = oracle.OracleIndex.deserialize("sq_euclid", p)
+    assert ix2.params()["allow_removals"] == 0
+    assert ix2.params()["random_seed"] == 7 and ix2.params()["min_nn"] == 3
+
+
+# ---------------------------------------------------------------- batching design aid
+def test_frozen_batch_insertion_recall(oracle):
+    # The GPU engine inserts in batches against a frozen graph; bound the recall cost on CPU.
+    v = oracle.random_vectors(128, 4000)
+    base = oracle.OracleIndex("sq_euclid")
+    ids = base.add(v)
+    r0 = oracle.self_recall(base, v, ids)
+    fb = oracle.OracleIndex("sq_euclid")
+    ids2 = fb.add_frozen_batches(v, ratio=4, bmax=4096)
+    assert np.array_equal(ids, ids2)
+    r1 = oracle.self_recall(fb, v, ids2)
+    assert r1 > r0 - 0.02, (r0, r1)
