@@ -1,0 +1,308 @@
+// beam.cuh -- warp-level HNSW traversal primitives (one warp = one query / one insert).
+//
+// Replaces, for TVector=float[] / TDistance=float:
+//   GraphNavigator.FindEntryAtLayer     GraphNavigator.cs:51-82   (greedy descent)
+//   GraphNavigator.SearchLayer(Query)   GraphNavigator.cs:123-256 (ef beam search)
+//   BinaryHeap / DistanceComparer       BinaryHeap.cs, DistanceComparer.cs
+//   VisitedList / VisitedListPool       VisitedListPool.cs
+//
+// The reference keeps a max-heap `top` (cap ef) and a min-heap `cand`.  Everything
+// ever pushed to `cand` was pushed to `top` at the same time, and whatever `top`
+// evicts is >= far for the rest of the search, so it can never be expanded before
+// the break at GraphNavigator.cs:218.  Hence the two heaps are equivalent (up to
+// exact fp32 ties) to ONE sorted list of the best <= ef entries carrying an
+// "expanded" bit: expand the closest unexpanded entry until none is left.
+// The list lives in shared memory as 64-bit keys (ordered distance | id | flag).
+//
+// Visited set: the reference stamps a short[capacity] per search.  Here a small
+// 2-way bucketed table of recently seen ids in shared memory filters most repeats.
+// It may forget (never invents): a forgotten node is re-evaluated, then either
+// rejected again (its distance is >= far, which only shrinks) or recognised as a
+// duplicate of a list entry (same distance bits, same id) -- results are identical
+// to an exact visited set, only the number of distance evaluations can grow.
+#pragma once
+#include "common.cuh"
+#include "metric.cuh"
+
+namespace hnsw {
+
+constexpr int kUnroll = 8;  // float4 loads in flight per lane in the distance loop
+
+struct WarpScratch {
+    float* q;          // [pitch] query / inserted vector (16 B aligned)
+    u64* list;         // [cap] sorted candidate keys
+    uint32_t* vis;     // [vis_size] recently visited ids (+1), 2-way buckets
+    int* cand_id;      // [cand_cap] fresh neighbour ids of the current expansion
+    float* cand_dist;  // [cand_cap]
+    int vis_size;      // power of two >= 64
+    int vis_shift;     // 32 - log2(vis_size / 2)
+    int cap;           // list capacity (>= ef)
+};
+
+struct WarpCounters {
+    unsigned ndist = 0, nexp = 0, row_words = 0;
+};
+
+__host__ __device__ inline size_t warp_scratch_bytes(int pitch, int cap, int vis_size, int cand_cap) {
+    size_t b = 0;
+    b += (size_t)((pitch + 3) & ~3) * 4;
+    b += (size_t)cap * 8;
+    b += (size_t)vis_size * 4;
+    b += (size_t)cand_cap * 8;
+    return (b + 15) & ~(size_t)15;
+}
+__device__ __forceinline__ WarpScratch carve_scratch(unsigned char* base, int pitch, int cap, int vis_size, int cand_cap) {
+    WarpScratch s;
+    s.q = reinterpret_cast<float*>(base);
+    base += (size_t)((pitch + 3) & ~3) * 4;
+    s.list = reinterpret_cast<u64*>(base);
+    base += (size_t)cap * 8;
+    s.vis = reinterpret_cast<uint32_t*>(base);
+    base += (size_t)vis_size * 4;
+    s.cand_id = reinterpret_cast<int*>(base);
+    base += (size_t)cand_cap * 4;
+    s.cand_dist = reinterpret_cast<float*>(base);
+    s.vis_size = vis_size;
+    s.vis_shift = 32 - (31 - __clz(vis_size >> 1));
+    s.cap = cap;
+    return s;
+}
+
+__device__ __forceinline__ const int* row_ptr(const GraphView& g, int id, int layer, int& stride) {
+    if (layer == 0) {
+        stride = g.stride0;
+        return g.adj0 + (size_t)id * g.stride0;
+    }
+    stride = g.strideU;
+    return g.adjU + ((size_t)__ldg(g.upper_off + id) + (size_t)(layer - 1)) * g.strideU;
+}
+
+// ----------------------------------------------------------------------------
+// distances of cand_id[0..m) to the vector in s.q -> cand_dist[0..m)
+// (16 vectors per pass, one lane pair each)
+// ----------------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ void batch_dist_to(const GraphView& g, const float* q, double q_norm_sqrt, const int* ids, float* out, int m,
+                                              int lane) {
+    const int h = lane & 1, grp = lane >> 1;
+    for (int base = 0; base < m; base += 16) {
+        const int j = base + grp;
+        const bool active = j < m;
+        const int id = active ? ids[j] : 0;
+        double an = 0.0;
+        if (METRIC == COSINE && active) an = __ldg(g.norm_sqrt + id);
+        const float* vec = g.vectors + (size_t)id * g.pitch;
+        const float d = pair_distance<METRIC, kUnroll>(vec, q, g.dim, h, active, an, q_norm_sqrt);
+        if (active && h == 0) out[j] = d;
+    }
+    __syncwarp();
+}
+template <int METRIC>
+__device__ __forceinline__ void batch_dist(const GraphView& g, const WarpScratch& s, double q_norm_sqrt, int m, int lane) {
+    batch_dist_to<METRIC>(g, s.q, q_norm_sqrt, s.cand_id, s.cand_dist, m, lane);
+}
+
+template <int METRIC>
+__device__ __forceinline__ float single_dist(const GraphView& g, const WarpScratch& s, double q_norm_sqrt, int id, int lane) {
+    __syncwarp();
+    if (lane == 0) s.cand_id[0] = id;
+    __syncwarp();
+    batch_dist<METRIC>(g, s, q_norm_sqrt, 1, lane);
+    const float d = s.cand_dist[0];
+    __syncwarp();
+    return d;
+}
+
+// ----------------------------------------------------------------------------
+// sorted list in shared memory
+// ----------------------------------------------------------------------------
+struct BeamState {
+    int n;             // entries in list
+    int ef;            // capacity in use
+    uint32_t far_ord;  // ordered distance of list[ef-1] when full, else 0xFFFFFFFF
+    int cursor;        // every entry below cursor is expanded
+};
+
+__device__ __forceinline__ int list_lower_bound(const u64* list, int n, u64 key, int lane) {
+    if (n <= 256) {
+        int pos = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + lane;
+            const bool lt = idx < n && list[idx] < key;
+            const unsigned mk = __ballot_sync(FULL, lt);
+            pos += __popc(mk);
+            if (mk != FULL) break;  // sorted: nothing smaller beyond this chunk
+        }
+        return pos;
+    }
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (list[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Insert `key` (flag bit clear) keeping the list sorted, dropping the last entry when
+// full.  Returns false when the id is already present (duplicate) or falls off the end.
+__device__ __forceinline__ bool list_insert(u64* list, BeamState& st, u64 key, int lane) {
+    const int n = st.n;
+    const int pos = list_lower_bound(list, n, key, lane);
+    if (pos < n && (list[pos] >> 1) == (key >> 1)) return false;  // same distance bits + id
+    if (pos >= st.ef) return false;
+    const int last = (n == st.ef) ? n - 1 : n;  // entries [pos, last) move up by one
+    __syncwarp();
+    for (int hi = last; hi > pos; hi -= 32) {
+        const int idx = hi - 1 - lane;
+        u64 v = 0;
+        if (idx >= pos) v = list[idx];
+        __syncwarp();
+        if (idx >= pos) list[idx + 1] = v;
+        __syncwarp();
+    }
+    if (lane == 0) list[pos] = key;
+    __syncwarp();
+    if (n < st.ef) st.n = n + 1;
+    st.far_ord = (st.n == st.ef) ? key_ord(list[st.ef - 1]) : 0xFFFFFFFFu;
+    if (pos < st.cursor) st.cursor = pos;
+    return true;
+}
+
+__device__ __forceinline__ void vis_clear(const WarpScratch& s, int lane) {
+    for (int i = lane; i < s.vis_size; i += 32) s.vis[i] = 0u;
+    __syncwarp();
+}
+// true if `id` was not in the table (and records it)
+__device__ __forceinline__ bool vis_test_and_set(const WarpScratch& s, int id) {
+    const uint32_t tag = (uint32_t)id + 1u;
+    const uint32_t b = (tag * 0x9E3779B1u) >> s.vis_shift;  // multiplicative hash, top bits
+    const uint32_t v0 = s.vis[2 * b], v1 = s.vis[2 * b + 1];
+    if (v0 == tag || v1 == tag) return false;
+    s.vis[2 * b + 1] = v0;
+    s.vis[2 * b] = tag;
+    return true;
+}
+
+// ----------------------------------------------------------------------------
+// Greedy descent on one upper layer (GraphNavigator.cs:51-82): scan the whole
+// row of the current node in stored order, move to the strict minimum (first
+// occurrence on ties), repeat until a scan brings no improvement.
+// ----------------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ void greedy_layer(const GraphView& g, const WarpScratch& s, double qn, int layer, int& cur, float& cur_d,
+                                             int lane, WarpCounters& wc) {
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        int stride;
+        const int* row = row_ptr(g, cur, layer, stride);
+        int m = 0;
+        for (int rb = 0; rb < stride; rb += 32) {
+            const int slot = rb + lane;
+            const int nb = slot < stride ? row[slot] : -1;
+            const unsigned mk = __ballot_sync(FULL, nb >= 0);
+            if (nb >= 0) s.cand_id[m + __popc(mk & ((1u << lane) - 1u))] = nb;
+            m += __popc(mk);
+        }
+        __syncwarp();
+        wc.nexp++;
+        wc.row_words += m + 1;
+        if (m == 0) break;
+        wc.ndist += m;
+        batch_dist<METRIC>(g, s, qn, m, lane);
+        u64 best = ~0ull;
+        for (int j = lane; j < m; j += 32) {
+            const u64 k = ((u64)f2ord(s.cand_dist[j]) << 32) | (u64)(uint32_t)j;
+            best = k < best ? k : best;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const u64 other = __shfl_xor_sync(FULL, best, o);
+            best = other < best ? other : best;
+        }
+        const int bj = (int)(uint32_t)best;
+        const float bd = s.cand_dist[bj];
+        const int bid = s.cand_id[bj];
+        __syncwarp();
+        if (bd < cur_d) {
+            cur_d = bd;
+            cur = bid;
+            changed = true;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Beam search of width ef on one layer (GraphNavigator.cs:194-256).  On return
+// s.list[0..st.n) holds the result sorted ascending by (distance, id).
+// ----------------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ void beam_search(const GraphView& g, const WarpScratch& s, double qn, int layer, int entry, float entry_d,
+                                            int ef, BeamState& st, int lane, WarpCounters& wc) {
+    st.n = 0;
+    st.ef = ef;
+    st.far_ord = 0xFFFFFFFFu;
+    st.cursor = 0;
+    vis_clear(s, lane);
+    list_insert(s.list, st, make_key(entry_d, entry), lane);
+    if (lane == 0) vis_test_and_set(s, entry);
+    __syncwarp();
+
+    for (;;) {
+        // closest unexpanded entry
+        int sel = -1;
+        for (int base = st.cursor & ~31; base < st.n; base += 32) {
+            const int idx = base + lane;
+            const bool un = idx < st.n && !(s.list[idx] & 1ull);
+            const unsigned mk = __ballot_sync(FULL, un);
+            if (mk) { sel = base + __ffs(mk) - 1; break; }
+        }
+        if (sel < 0) break;
+        const u64 e = s.list[sel];
+        const int c = key_id(e);
+        __syncwarp();
+        if (lane == 0) s.list[sel] = e | 1ull;
+        __syncwarp();
+        st.cursor = sel + 1;
+
+        // row of c: keep the neighbours not seen recently, in stored order
+        int stride;
+        const int* row = row_ptr(g, c, layer, stride);
+        int m = 0, deg = 0;
+        for (int rb = 0; rb < stride; rb += 32) {
+            const int slot = rb + lane;
+            const int nb = slot < stride ? row[slot] : -1;
+            deg += __popc(__ballot_sync(FULL, nb >= 0));
+            bool fresh = false;
+            if (nb >= 0) fresh = vis_test_and_set(s, nb);
+            const unsigned mk = __ballot_sync(FULL, fresh);
+            if (fresh) s.cand_id[m + __popc(mk & ((1u << lane) - 1u))] = nb;
+            m += __popc(mk);
+        }
+        __syncwarp();
+        wc.nexp++;
+        wc.row_words += deg + 1;
+        if (m == 0) continue;
+        wc.ndist += m;
+        batch_dist<METRIC>(g, s, qn, m, lane);
+
+        // insert in stored order; a candidate is accepted iff |top| < ef or d < far (strict)
+        for (int jb = 0; jb < m; jb += 32) {
+            const int j = jb + lane;
+            const bool have = j < m;
+            const u64 mykey = have ? make_key(s.cand_dist[j], s.cand_id[j]) : ~0ull;
+            bool pending = have;
+            for (;;) {
+                const bool want = pending && (st.n < st.ef || key_ord(mykey) < st.far_ord);
+                const unsigned mk = __ballot_sync(FULL, want);
+                if (!mk) break;
+                const int src = __ffs(mk) - 1;
+                const u64 kn = __shfl_sync(FULL, mykey, src);
+                if (lane == src) pending = false;
+                list_insert(s.list, st, kn, lane);
+            }
+        }
+    }
+}
+
+}  // namespace hnsw

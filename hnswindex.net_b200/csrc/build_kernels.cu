@@ -1,0 +1,283 @@
+// build_kernels.cu -- K4/K5/K6: batched insertion on sm_100a, one warp per new node.
+//
+// Replaces the linking half of HNSWIndex.Add (HNSWIndex.cs:55-78):
+//   GraphConnector.AddNewConnections   GraphConnector.cs:172-181  (descent, then per layer top..0)
+//   GraphConnector.ConnectAtLayer      GraphConnector.cs:187-217  (SearchLayer with ef = MaxCandidates,
+//                                                                  heuristic, own row, reverse links)
+//   Heuristic.RelativeNeighborPruning  Heuristic.cs:11-46
+//   GraphConnector.PruneOverflow       GraphConnector.cs:222-262
+// The reference inserts with Parallel.For under per-node Monitor locks.  Here a batch of new
+// nodes is handled by two kernels:
+//   select_kernel : every new node searches the graph as it stood before the batch (nodes of the
+//                   same batch are unreachable, exactly like nodes still being linked in the
+//                   reference), runs the heuristic and writes its own rows;
+//   link_kernel   : for every selected neighbour n, under a per-node spin lock (atomicCAS on
+//                   locks[n]), append the new id to n's row, re-running the heuristic on
+//                   overflow so MaxEdges(layer) is honoured.
+#include <algorithm>
+
+#include "beam.cuh"
+#include "kernels.hpp"
+
+namespace hnsw {
+
+struct BuildScratch {
+    WarpScratch s;
+    float* cvec;  // [pitch] second vector buffer (heuristic: the candidate under test)
+    int* sel;     // [sel_cap] selected neighbour ids
+};
+
+__host__ __device__ inline size_t build_scratch_bytes(int pitch, int cap, int vis_size, int cand_cap, int sel_cap) {
+    return warp_scratch_bytes(pitch, cap, vis_size, cand_cap) + (size_t)((pitch + 3) & ~3) * 4 + (((size_t)sel_cap * 4 + 15) & ~(size_t)15);
+}
+__device__ __forceinline__ BuildScratch carve_build(unsigned char* base, int pitch, int cap, int vis_size, int cand_cap, int sel_cap) {
+    BuildScratch b;
+    b.s = carve_scratch(base, pitch, cap, vis_size, cand_cap);
+    base += warp_scratch_bytes(pitch, cap, vis_size, cand_cap);
+    b.cvec = reinterpret_cast<float*>(base);
+    base += (size_t)((pitch + 3) & ~3) * 4;
+    b.sel = reinterpret_cast<int*>(base);
+    return b;
+}
+
+__device__ __forceinline__ void load_vector(const GraphView& g, int id, float* dst, int lane) {
+    const float4* src = reinterpret_cast<const float4*>(g.vectors + (size_t)id * g.pitch);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = lane; i < (g.pitch >> 2); i += 32) d4[i] = __ldg(src + i);
+    __syncwarp();
+}
+
+// Heuristic.cs:11-46 on the sorted list[0..n): returns the number selected (ids in b.sel, ascending
+// by distance).  Caller handles the n < maxE early-return case.
+template <int METRIC>
+__device__ __forceinline__ int select_neighbors(const GraphView& g, const BuildScratch& b, const u64* list, int n, int maxE, int lane,
+                                                WarpCounters& wc) {
+    int nsel = 0;
+    for (int i = 0; i < n && nsel < maxE; ++i) {
+        const u64 e = list[i];
+        const int c = key_id(e);
+        const float cd = key_dist(e);
+        bool ok = true;
+        if (nsel > 0) {
+            load_vector(g, c, b.cvec, lane);
+            double cn = 0.0;
+            if (METRIC == COSINE) cn = __ldg(g.norm_sqrt + c);
+            batch_dist_to<METRIC>(g, b.cvec, cn, b.sel, b.s.cand_dist, nsel, lane);
+            wc.ndist += nsel;
+            bool rej = false;
+            for (int j = lane; j < nsel; j += 32) rej |= b.s.cand_dist[j] < cd;  // strict, Heuristic.cs:34
+            ok = !__any_sync(FULL, rej);
+            __syncwarp();
+        }
+        if (ok) {
+            if (lane == 0) b.sel[nsel] = c;
+            ++nsel;
+            __syncwarp();
+        }
+    }
+    return nsel;
+}
+
+__device__ __forceinline__ int* row_ptr_mut(const GraphView& g, int id, int layer, int& stride) {
+    if (layer == 0) {
+        stride = g.stride0;
+        return g.adj0 + (size_t)id * g.stride0;
+    }
+    stride = g.strideU;
+    return g.adjU + ((size_t)__ldg(g.upper_off + id) + (size_t)(layer - 1)) * g.strideU;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads)
+build_select_kernel(GraphView g, const int* __restrict__ levels, int first, int count, int efc, int list_cap, int vis_size, int cand_cap,
+                    int sel_cap, unsigned* work_counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, vis_size, cand_cap, sel_cap);
+    const BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, vis_size, cand_cap, sel_cap);
+    const WarpScratch& s = b.s;
+
+    for (;;) {
+        unsigned wi = 0;
+        if (lane == 0) wi = atomicAdd(work_counter, 1u);
+        wi = __shfl_sync(FULL, wi, 0);
+        if (wi >= (unsigned)count) break;
+        const int v = first + (int)wi;
+        const int level = __ldg(levels + v);
+
+        load_vector(g, v, s.q, lane);
+        double qn = 0.0;
+        if (METRIC == COSINE) qn = __ldg(g.norm_sqrt + v);
+
+        WarpCounters wc;
+        int cur = g.entry;
+        float cur_d = single_dist<METRIC>(g, s, qn, cur, lane);
+        for (int layer = g.top_layer; layer > level; --layer) greedy_layer<METRIC>(g, s, qn, layer, cur, cur_d, lane, wc);
+
+        for (int layer = min(level, g.top_layer); layer >= 0; --layer) {
+            BeamState st;
+            beam_search<METRIC>(g, s, qn, layer, cur, cur_d, efc, st, lane, wc);
+            const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
+            int nsel;
+            int next;
+            float next_d;
+            if (st.n < maxE) {
+                // Heuristic.cs:13-18 returns the candidates unsorted; ConnectAtLayer then continues from
+                // element [0] of that array, the root of the max-heap = the FARTHEST candidate.
+                nsel = st.n;
+                for (int j = lane; j < nsel; j += 32) b.sel[j] = key_id(s.list[j]);
+                next = key_id(s.list[st.n - 1]);
+                next_d = key_dist(s.list[st.n - 1]);
+                __syncwarp();
+            } else {
+                nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, wc);
+                next = key_id(s.list[0]);  // the closest candidate is always selected first
+                next_d = key_dist(s.list[0]);
+            }
+            int stride;
+            int* row = row_ptr_mut(g, v, layer, stride);
+            for (int j = lane; j < stride; j += 32) row[j] = j < nsel ? b.sel[j] : -1;
+            __syncwarp();
+            cur = next;
+            cur_d = next_d;
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ bool lock_node(int* locks, int n, int lane, int* error_flag) {
+    int ok = 1;
+    if (lane == 0) {
+        unsigned spins = 0;
+        while (atomicCAS(locks + n, 0, 1) != 0) {
+            __nanosleep(128);
+            if (++spins > (1u << 22)) { ok = 0; atomicExch(error_flag, 1); break; }  // never hang the GPU
+        }
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    __threadfence();
+    return ok != 0;
+}
+__device__ __forceinline__ void unlock_node(int* locks, int n, int lane) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(locks + n, 0);
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads)
+build_link_kernel(GraphView g, const int* __restrict__ levels, int first, int count, int list_cap, int cand_cap, int sel_cap,
+                  unsigned* work_counter, int* error_flag) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, 64, cand_cap, sel_cap);
+    const BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, 64, cand_cap, sel_cap);
+    const WarpScratch& s = b.s;
+
+    for (;;) {
+        unsigned wi = 0;
+        if (lane == 0) wi = atomicAdd(work_counter, 1u);
+        wi = __shfl_sync(FULL, wi, 0);
+        if (wi >= (unsigned)count) break;
+        const int v = first + (int)wi;
+        const int level = __ldg(levels + v);
+        WarpCounters wc;
+
+        for (int layer = min(level, g.top_layer); layer >= 0; --layer) {
+            const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
+            int vstride;
+            const int* vrow = row_ptr_mut(g, v, layer, vstride);
+            for (int t = 0; t < vstride; ++t) {
+                const int n = __ldcg(vrow + t);
+                if (n < 0) break;
+                if (!lock_node(g.locks, n, lane, error_flag)) continue;
+                int stride;
+                int* row = row_ptr_mut(g, n, layer, stride);
+                // current row of n, read past L1 (other SMs update it under the same lock)
+                int cnt = 0;
+                for (int rb = 0; rb < stride; rb += 32) {
+                    const int slot = rb + lane;
+                    const int nb = slot < stride ? __ldcg(row + slot) : -1;
+                    if (nb >= 0) s.cand_id[slot] = nb;
+                    cnt += __popc(__ballot_sync(FULL, nb >= 0));
+                }
+                __syncwarp();
+                if (cnt < maxE) {
+                    if (lane == 0) row[cnt] = v;  // EdgeList.Add, GraphConnector.cs:207
+                } else {
+                    // PruneOverflow (GraphConnector.cs:222-262): heuristic over the row plus the new link
+                    if (lane == 0) s.cand_id[cnt] = v;
+                    const int m = cnt + 1;
+                    load_vector(g, n, s.q, lane);
+                    double nn = 0.0;
+                    if (METRIC == COSINE) nn = __ldg(g.norm_sqrt + n);
+                    batch_dist<METRIC>(g, s, nn, m, lane);
+                    wc.ndist += m;
+                    BeamState st;
+                    st.n = 0; st.ef = list_cap; st.far_ord = 0xFFFFFFFFu; st.cursor = 0;
+                    for (int j = 0; j < m; ++j) list_insert(s.list, st, make_key(s.cand_dist[j], s.cand_id[j]), lane);
+                    const int nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, wc);
+                    for (int j = lane; j < stride; j += 32) row[j] = j < nsel ? b.sel[j] : -1;
+                }
+                unlock_node(g.locks, n, lane);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int pow2_ge(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <typename Kern>
+static int persistent_grid(Kern kern, size_t smem, const Tuning& t, int work_items) {
+    int dev = 0, max_optin = 0, sms = 0, per_sm = 0;
+    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (smem > (size_t)max_optin)
+        throw std::runtime_error("MaxCandidates / MaxEdges too large for shared memory: need " + std::to_string(smem) + " B per block");
+    HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);
+    const int need = (work_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    return std::max(1, std::min(need, sms * per_sm));
+}
+
+// d_work_counter: three consecutive words -- [0] select work, [1] link work, [2] error flag
+void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int first, int count, int efc, unsigned* d_work_counter,
+                        const Tuning& t, cudaStream_t stream) {
+    if (count <= 0) return;
+    const int maxE0 = 2 * g.max_edges;
+    const int list_cap_sel = std::max(efc, 1);
+    const int list_cap_link = maxE0 + 1;
+    const int cand_cap = ((std::max(g.stride0, g.strideU) + 1 + 31) / 32) * 32;
+    const int sel_cap = std::max(maxE0, list_cap_sel < maxE0 ? list_cap_sel : maxE0);
+    int vis = t.vis_size_build > 0 ? std::max(64, pow2_ge(t.vis_size_build)) : std::min(8192, std::max(256, pow2_ge(8 * efc)));
+    const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap) * kWarpsPerBlock;
+    const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap) * kWarpsPerBlock;
+    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, 2 * sizeof(unsigned), stream));
+    int* err = reinterpret_cast<int*>(d_work_counter + 2);
+#define HNSW_LAUNCH_BUILD(M)                                                                                                    \
+    {                                                                                                                           \
+        const int g1 = persistent_grid(build_select_kernel<M>, smem_sel, t, count);                                            \
+        build_select_kernel<M><<<g1, kThreads, smem_sel, stream>>>(g, d_levels, first, count, efc, list_cap_sel, vis, cand_cap, \
+                                                                   sel_cap, d_work_counter);                                   \
+        const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, count);                                             \
+        build_link_kernel<M><<<g2, kThreads, smem_link, stream>>>(g, d_levels, first, count, list_cap_link, cand_cap, sel_cap, \
+                                                                  d_work_counter + 1, err);                                    \
+    }
+    switch (metric) {
+        case SQ_EUCLID: HNSW_LAUNCH_BUILD(SQ_EUCLID) break;
+        case COSINE: HNSW_LAUNCH_BUILD(COSINE) break;
+        default: HNSW_LAUNCH_BUILD(UCOSINE) break;
+    }
+#undef HNSW_LAUNCH_BUILD
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace hnsw

@@ -1,0 +1,267 @@
+// capi.cu -- the C ABI (include/hnsw_b200.h) over hnsw::Index.
+// Mirrors bindings/HNSWIndex.Native/HNSWIndexExports.cs: process-global pending parameters that the
+// next hnsw_create consumes and resets (:16,50-61), process-global last error (:11-12), -1 / NULL on error.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/hnsw_b200.h"
+#include "engine.hpp"
+
+using namespace hnsw;
+
+namespace {
+std::mutex g_mu;
+std::string g_last_error;
+Parameters g_pending;
+
+void set_error(const std::string& what) {
+    std::lock_guard<std::mutex> l(g_mu);
+    g_last_error = what;
+}
+MetricKind parse_metric(const char* m) {
+    const std::string s(m ? m : "");
+    if (s == "sq_euclid") return SQ_EUCLID;
+    if (s == "cosine") return COSINE;
+    if (s == "ucosine") return UCOSINE;
+    throw std::invalid_argument("Unsupported distance metric: " + s);  // HNSWIndexExports.cs:59
+}
+Index* get(hnsw_handle h) {
+    if (!h) throw std::invalid_argument("Invalid handle");  // HNSWIndexExports.cs:20
+    return reinterpret_cast<Index*>(h);
+}
+}  // namespace
+
+#define HNSW_TRY try {
+#define HNSW_CATCH(ret)                                          \
+    }                                                            \
+    catch (const std::exception& e) { set_error(e.what()); return ret; } \
+    catch (...) { set_error("unknown error"); return ret; }
+
+extern "C" {
+
+int hnsw_get_last_error_utf8(char* buf, int bufLen) {
+    std::lock_guard<std::mutex> l(g_mu);
+    const int need = (int)g_last_error.size();
+    if (bufLen > 0 && buf != nullptr) {
+        const int n = std::min(need, std::max(0, bufLen - 1));
+        std::memcpy(buf, g_last_error.data(), (size_t)n);
+        buf[n] = 0;
+    }
+    return need;
+}
+
+hnsw_handle hnsw_create(const char* distanceMetric) {
+    HNSW_TRY
+    const MetricKind m = parse_metric(distanceMetric);
+    Parameters p;
+    {
+        std::lock_guard<std::mutex> l(g_mu);
+        p = g_pending;
+    }
+    Index* ix = new Index(m, p);
+    {
+        std::lock_guard<std::mutex> l(g_mu);
+        g_pending = Parameters();  // reset parameters for next instance (HNSWIndexExports.cs:61)
+    }
+    return ix;
+    HNSW_CATCH(nullptr)
+}
+
+void hnsw_free(hnsw_handle handle) {
+    if (!handle) return;
+    try { delete reinterpret_cast<Index*>(handle); } catch (const std::exception& e) { set_error(e.what()); }
+}
+
+int hnsw_add(hnsw_handle handle, const float* vectors, int count, int dim, int* outIds) {
+    if (!handle) return 0;
+    HNSW_TRY
+    if (vectors == nullptr || count <= 0 || dim <= 0) return 0;
+    return get(handle)->add(vectors, count, dim, outIds);
+    HNSW_CATCH(-1)
+}
+
+int hnsw_remove(hnsw_handle handle, const int* ids, int count) {
+    if (!handle) return 0;
+    HNSW_TRY
+    if (ids == nullptr || count <= 0) return 0;
+    if (!get(handle)->params().AllowRemovals) throw std::runtime_error("Removals are disabled in this index instance.");  // HNSWIndex.cs:85-86
+    throw std::runtime_error("Remove is outside the GPU-accelerated path of this engine (Add / KnnQuery / Serialize); not supported.");
+    HNSW_CATCH(-1)
+}
+
+int hnsw_knn_query(hnsw_handle handle, const float* vectors, int count, int dim, int k, int* outIds, float* outDists) {
+    if (!handle) return 0;
+    HNSW_TRY
+    if (count > 0 && (vectors == nullptr || outIds == nullptr || outDists == nullptr)) throw std::invalid_argument("null buffer");
+    get(handle)->knn_query(vectors, count, dim, k, outIds, outDists);
+    return 0;
+    HNSW_CATCH(-1)
+}
+
+int hnsw_range_query(hnsw_handle handle, const float* vectors, int count, int dim, float range, void** outIds, void** outDists, int* counts) {
+    if (!handle) return 0;
+    HNSW_TRY
+    (void)vectors; (void)dim; (void)range;
+    for (int i = 0; i < count; ++i) {
+        if (outIds) outIds[i] = nullptr;
+        if (outDists) outDists[i] = nullptr;
+        if (counts) counts[i] = 0;
+    }
+    throw std::runtime_error("RangeQuery is not yet accelerated by this engine (next tier after KnnQuery / Add).");
+    HNSW_CATCH(-1)
+}
+
+void hnsw_free_results(void** idsArray, void** distsArray, int count) {
+    if (idsArray == nullptr && distsArray == nullptr) return;
+    for (int i = 0; i < count; ++i) {
+        if (idsArray && idsArray[i]) { std::free(idsArray[i]); idsArray[i] = nullptr; }
+        if (distsArray && distsArray[i]) { std::free(distsArray[i]); distsArray[i] = nullptr; }
+    }
+}
+
+int hnsw_set_collection_size(int v) { std::lock_guard<std::mutex> l(g_mu); g_pending.CollectionSize = v; return 0; }
+int hnsw_set_max_edges(int v) { std::lock_guard<std::mutex> l(g_mu); g_pending.MaxEdges = v; return 0; }
+int hnsw_set_max_candidates(int v) { std::lock_guard<std::mutex> l(g_mu); g_pending.MaxCandidates = v; return 0; }
+int hnsw_set_remove_max_candidates(int v) { std::lock_guard<std::mutex> l(g_mu); g_pending.RemoveMaxCandidates = v; return 0; }
+int hnsw_set_distribution_rate(float v) { std::lock_guard<std::mutex> l(g_mu); g_pending.DistributionRate = (double)v; return 0; }
+int hnsw_set_random_seed(int v) { std::lock_guard<std::mutex> l(g_mu); g_pending.RandomSeed = v; return 0; }
+int hnsw_set_min_nn(int v) { std::lock_guard<std::mutex> l(g_mu); g_pending.MinNN = v; return 0; }
+int hnsw_set_allow_removals(bool v) { std::lock_guard<std::mutex> l(g_mu); g_pending.AllowRemovals = v; return 0; }
+
+// ------------------------------------------------------------------------------------ additions
+int hnsw_count(hnsw_handle handle) { return handle ? reinterpret_cast<Index*>(handle)->count() : -1; }
+int hnsw_dim(hnsw_handle handle) { return handle ? reinterpret_cast<Index*>(handle)->dim() : -1; }
+
+int hnsw_serialize(hnsw_handle handle, const char* path, int packed) {
+    HNSW_TRY
+    if (!path) throw std::invalid_argument("null path");
+    get(handle)->serialize(path, packed != 0);
+    return 0;
+    HNSW_CATCH(-1)
+}
+hnsw_handle hnsw_deserialize(const char* distanceMetric, const char* path) {
+    HNSW_TRY
+    if (!path) throw std::invalid_argument("null path");
+    return Index::from_snapshot(parse_metric(distanceMetric), path);
+    HNSW_CATCH(nullptr)
+}
+int hnsw_index_set_min_nn(hnsw_handle handle, int minNN) {
+    HNSW_TRY
+    if (minNN < 1) throw std::invalid_argument("MinNN must be at least 1");
+    get(handle)->set_min_nn(minNN);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_index_get_params(hnsw_handle handle, int* ints7, double* rate) {
+    HNSW_TRY
+    const Parameters& p = get(handle)->params();
+    if (ints7) {
+        ints7[0] = p.MaxEdges; ints7[1] = p.MinNN; ints7[2] = p.MaxCandidates; ints7[3] = p.RemoveMaxCandidates;
+        ints7[4] = p.CollectionSize; ints7[5] = p.RandomSeed; ints7[6] = p.AllowRemovals ? 1 : 0;
+    }
+    if (rate) *rate = p.DistributionRate;
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_set_device(int device) {
+    HNSW_TRY
+    HNSW_CUDA_CHECK(cudaSetDevice(device));
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int hnsw_knn_query_device(hnsw_handle handle, const float* dQueries, int count, int dim, int k, int* dOutIds, float* dOutDists) {
+    HNSW_TRY
+    get(handle)->knn_query_device(dQueries, count, dim, k, dOutIds, dOutDists);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_set_stream(hnsw_handle handle, void* cudaStream) {
+    HNSW_TRY
+    get(handle)->set_stream(reinterpret_cast<cudaStream_t>(cudaStream));
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_exact_knn(hnsw_handle handle, const float* queries, int count, int dim, int k, int* outIds, float* outDists) {
+    HNSW_TRY
+    get(handle)->exact_knn(queries, count, dim, k, outIds, outDists);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_merge_topk_device(const int* dInIds, const float* dInDists, int parts, int count, int k, int* dOutIds, float* dOutDists, void* cudaStream) {
+    HNSW_TRY
+    if (parts < 1 || k < 1) throw std::invalid_argument("parts and k must be positive");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cudaStream);
+    launch_merge_topk(dInIds, dInDists, parts, count, k, dOutIds, dOutDists, s);
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_enable_stats(hnsw_handle handle, int on) {
+    HNSW_TRY
+    get(handle)->enable_stats(on != 0);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_get_stats(hnsw_handle handle, hnsw_stats* out) {
+    HNSW_TRY
+    if (!out) throw std::invalid_argument("null stats");
+    const IndexStats s = get(handle)->stats();
+    out->last_search_ms = s.last_search_ms; out->last_build_ms = s.last_build_ms;
+    out->ndist = s.ndist; out->nexp = s.nexp; out->row_words = s.row_words;
+    out->search_launches = s.search_launches; out->build_launches = s.build_launches;
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_set_tuning(hnsw_handle handle, const char* key, int value) {
+    HNSW_TRY
+    get(handle)->set_tuning(key ? key : "", value);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_export_layer0(hnsw_handle handle, int* levels, int* rows0, int* stride0, int* entryPoint) {
+    HNSW_TRY
+    Index* ix = get(handle);
+    HostGraph g;
+    ix->export_graph(g);
+    if (stride0) *stride0 = g.stride0;
+    if (entryPoint) *entryPoint = g.entry;
+    if (levels) std::memcpy(levels, g.levels.data(), g.levels.size() * sizeof(int));
+    if (rows0) std::memcpy(rows0, g.adj0.data(), g.adj0.size() * sizeof(int));
+    return g.length;
+    HNSW_CATCH(-1)
+}
+int hnsw_export_layer(hnsw_handle handle, int layer, int* rows, int* stride) {
+    HNSW_TRY
+    if (layer < 1) throw std::invalid_argument("use hnsw_export_layer0 for layer 0");
+    Index* ix = get(handle);
+    HostGraph g;
+    ix->export_graph(g);
+    if (stride) *stride = g.strideU;
+    if (rows)
+        for (int i = 0; i < g.length; ++i) {
+            int* dst = rows + (size_t)i * g.strideU;
+            if (g.levels[i] >= layer) std::memcpy(dst, g.adjU.data() + ((size_t)g.upper_off[i] + (layer - 1)) * g.strideU, (size_t)g.strideU * sizeof(int));
+            else for (int j = 0; j < g.strideU; ++j) dst[j] = -1;
+        }
+    return g.length;
+    HNSW_CATCH(-1)
+}
+int hnsw_snapshot_transcode(const char* inPath, const char* outPath, int packed) {
+    HNSW_TRY
+    if (!inPath || !outPath) throw std::invalid_argument("null path");
+    HostGraph g;
+    read_snapshot(inPath, g);
+    write_snapshot(g, outPath, packed != 0);
+    return g.length;
+    HNSW_CATCH(-1)
+}
+const char* hnsw_version(void) { return "hnsw-b200 0.1.0 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,467 @@
+// engine.cu -- host side of the B200 HNSW engine (see engine.hpp).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <random>
+
+namespace hnsw {
+
+// ---------------------------------------------------------------------------------------------
+// .NET System.Random(seed): Knuth subtractive generator as published in dotnet/runtime
+// (Random.CompatPrng).  NextSingle() = (float)(InternalSample() * (1.0 / int.MaxValue)),
+// redrawn when it rounds to 1.0f.
+// ---------------------------------------------------------------------------------------------
+DotNetRandom::DotNetRandom(int seed) {
+    const int kMax = std::numeric_limits<int>::max();
+    const int sub = seed == std::numeric_limits<int>::min() ? kMax : std::abs(seed);
+    int mj = 161803398 - sub;
+    std::memset(seed_array_, 0, sizeof(seed_array_));
+    seed_array_[55] = mj;
+    int mk = 1, ii = 0;
+    for (int i = 1; i < 55; ++i) {
+        ii += 21;
+        if (ii >= 55) ii -= 55;
+        seed_array_[ii] = mk;
+        mk = mj - mk;
+        if (mk < 0) mk += kMax;
+        mj = seed_array_[ii];
+    }
+    for (int round = 0; round < 4; ++round)
+        for (int i = 1; i < 56; ++i) {
+            int n = i + 30;
+            if (n >= 55) n -= 55;
+            seed_array_[i] = (int)((unsigned)seed_array_[i] - (unsigned)seed_array_[1 + n]);
+            if (seed_array_[i] < 0) seed_array_[i] += kMax;
+        }
+    inext_ = 0;
+    inextp_ = 21;
+}
+int DotNetRandom::InternalSample() {
+    const int kMax = std::numeric_limits<int>::max();
+    if (++inext_ >= 56) inext_ = 1;
+    if (++inextp_ >= 56) inextp_ = 1;
+    int r = (int)((unsigned)seed_array_[inext_] - (unsigned)seed_array_[inextp_]);
+    if (r == kMax) r--;
+    if (r < 0) r += kMax;
+    seed_array_[inext_] = r;
+    return r;
+}
+float DotNetRandom::NextSingle() {
+    for (;;) {
+        const float f = (float)(InternalSample() * (1.0 / std::numeric_limits<int>::max()));
+        if (f < 1.0f) return f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static void grow_device(T*& p, size_t old_n, size_t new_n, int fill_byte, cudaStream_t s) {
+    T* np = nullptr;
+    HNSW_CUDA_CHECK(cudaMalloc(&np, std::max<size_t>(new_n, 1) * sizeof(T)));
+    if (fill_byte >= 0) HNSW_CUDA_CHECK(cudaMemsetAsync(np, fill_byte, std::max<size_t>(new_n, 1) * sizeof(T), s));
+    if (p && old_n) HNSW_CUDA_CHECK(cudaMemcpyAsync(np, p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (p) {
+        HNSW_CUDA_CHECK(cudaStreamSynchronize(s));
+        HNSW_CUDA_CHECK(cudaFree(p));
+    }
+    p = np;
+}
+
+static int seed_or_random(int seed) {
+    if (seed >= 0) return seed;  // GraphData.cs:42 -- negative = unseeded
+    std::random_device rd;
+    return (int)(rd() & 0x7fffffff);
+}
+
+Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), params_(params), rng_(seed_or_random(params.RandomSeed)) {
+    if (params_.MaxEdges < 1) throw std::invalid_argument("MaxEdges must be at least 1");
+    if (params_.MaxEdges > 256) throw std::invalid_argument("MaxEdges above 256 is not supported by the B200 engine");
+    if (params_.MaxCandidates < 1) throw std::invalid_argument("MaxCandidates must be at least 1");
+    if (params_.MinNN < 1) params_.MinNN = 1;
+    HNSW_CUDA_CHECK(cudaGetDevice(&device_));
+    HNSW_CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    stream_ = own_stream_;
+    HNSW_CUDA_CHECK(cudaEventCreate(&ev0_));
+    HNSW_CUDA_CHECK(cudaEventCreate(&ev1_));
+    HNSW_CUDA_CHECK(cudaMalloc(&d_counters_, 8 * sizeof(unsigned)));
+    HNSW_CUDA_CHECK(cudaMemset(d_counters_, 0, 8 * sizeof(unsigned)));
+    stride0_ = stride_for(2 * params_.MaxEdges);
+    strideU_ = stride_for(params_.MaxEdges);
+    capacity_ = std::max(1, params_.CollectionSize);
+}
+
+Index::~Index() {
+    cudaSetDevice(device_);
+    cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
+    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_);
+    cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+}
+
+void Index::set_tuning(const std::string& key, int value) {
+    if (key == "vis_size_search") tuning_.vis_size_search = value;
+    else if (key == "vis_size_build") tuning_.vis_size_build = value;
+    else if (key == "blocks_per_sm") tuning_.blocks_per_sm = value;
+    else if (key == "build_batch_max") build_batch_max_ = std::max(1, value);
+    else if (key == "build_batch_ratio") build_batch_ratio_ = std::max(1, value);
+    else throw std::invalid_argument("unknown tuning key: " + key);
+}
+
+GraphView Index::view() const {
+    GraphView g;
+    g.vectors = d_vectors_;
+    g.norm_sqrt = d_norms_;
+    g.adj0 = d_adj0_;
+    g.adjU = d_adjU_;
+    g.upper_off = d_upper_off_;
+    g.locks = d_locks_;
+    g.dim = dim_;
+    g.pitch = pitch_;
+    g.stride0 = stride0_;
+    g.strideU = strideU_;
+    g.max_edges = params_.MaxEdges;
+    g.entry = entry_;
+    g.top_layer = top_;
+    g.count = length_;
+    return g;
+}
+
+void Index::ensure_dim(int dim) {
+    if (dim_ < 0) {
+        dim_ = dim;
+        pitch_ = (dim + 3) & ~3;
+    } else if (dim != dim_) {
+        throw std::invalid_argument("vector dimension " + std::to_string(dim) + " does not match the index dimension " + std::to_string(dim_));
+    }
+}
+
+// GraphData.cs:98-111: Capacity doubles whenever Length exceeds it
+void Index::ensure_capacity(int needed) {
+    while (needed > capacity_) capacity_ *= 2;
+    if (capacity_ <= dev_capacity_) return;
+    const size_t o = (size_t)dev_capacity_, n = (size_t)capacity_;
+    grow_device(d_vectors_, o * pitch_, n * pitch_, 0, stream_);
+    if (metric_ == COSINE) grow_device(d_norms_, o, n, 0, stream_);
+    grow_device(d_adj0_, o * stride0_, n * stride0_, 0xFF, stream_);
+    grow_device(d_upper_off_, o, n, 0xFF, stream_);
+    grow_device(d_locks_, o, n, 0, stream_);
+    grow_device(d_levels_, o, n, 0, stream_);
+    dev_capacity_ = capacity_;
+}
+
+void Index::ensure_upper_rows(int needed) {
+    if (needed <= upper_rows_cap_) return;
+    int cap = std::max(1024, upper_rows_cap_);
+    while (cap < needed) cap *= 2;
+    grow_device(d_adjU_, (size_t)upper_rows_cap_ * strideU_, (size_t)cap * strideU_, 0xFF, stream_);
+    upper_rows_cap_ = cap;
+}
+
+void Index::ensure_query_scratch(int count, int k) {
+    const size_t qn = (size_t)count * dim_, on = (size_t)count * k;
+    if (qn > q_cap_) { cudaFree(d_q_); d_q_ = nullptr; HNSW_CUDA_CHECK(cudaMalloc(&d_q_, qn * sizeof(float))); q_cap_ = qn; }
+    if (on > out_cap_) {
+        cudaFree(d_ids_); cudaFree(d_dists_); d_ids_ = nullptr; d_dists_ = nullptr;
+        HNSW_CUDA_CHECK(cudaMalloc(&d_ids_, on * sizeof(int)));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_dists_, on * sizeof(float)));
+        out_cap_ = on;
+    }
+}
+
+void Index::ensure_stats(int count) {
+    if ((size_t)count > stats_cap_) {
+        cudaFree(d_stats_); d_stats_ = nullptr;
+        HNSW_CUDA_CHECK(cudaMalloc(&d_stats_, (size_t)count * sizeof(QueryStats)));
+        stats_cap_ = count;
+    }
+}
+
+void Index::set_stream(cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(mu_);
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    stream_ = s ? s : own_stream_;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Add (HNSWIndex.cs:70-78).  Levels and slots are assigned in input order, i.e. the ids equal the
+// ones the reference hands out when items are added one after another.
+// ---------------------------------------------------------------------------------------------
+int Index::add(const float* vectors, int count, int dim, int* out_ids) {
+    std::lock_guard<std::mutex> lock(mu_);
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    std::vector<int> lv;
+    lv.reserve(count);
+    int nnew = 0;
+    bool all = true;
+    for (int i = 0; i < count; ++i) {
+        // GraphData.GetRandomLayer, GraphData.cs:211-219
+        const float r = rng_.NextSingle();
+        const double x = -std::log((double)r) * params_.DistributionRate;
+        if (!(x < 2147483648.0) || x < 0.0) {  // r == 0: the reference's cast goes negative and the item is dropped (:81-82)
+            out_ids[i] = -1;
+            all = false;
+            continue;
+        }
+        int level = (int)x;
+        if (level > 30) level = 30;
+        out_ids[i] = length_ + nnew++;
+        lv.push_back(level);
+    }
+    if (nnew == 0) return count;
+    const int first = length_;
+    ensure_capacity(first + nnew);
+
+    // vectors -> slab rows [first, first+nnew)
+    if (all) {
+        HNSW_CUDA_CHECK(cudaMemcpy2DAsync(d_vectors_ + (size_t)first * pitch_, (size_t)pitch_ * 4, vectors, (size_t)dim * 4, (size_t)dim * 4,
+                                          (size_t)nnew, cudaMemcpyHostToDevice, stream_));
+    } else {
+        int j = 0;
+        for (int i = 0; i < count; ++i)
+            if (out_ids[i] >= 0) {
+                HNSW_CUDA_CHECK(cudaMemcpyAsync(d_vectors_ + (size_t)(first + j) * pitch_, vectors + (size_t)i * dim, (size_t)dim * 4,
+                                                cudaMemcpyHostToDevice, stream_));
+                ++j;
+            }
+    }
+    // NewNode (GraphData.cs:224-242): rows for layers 0..level
+    levels_.resize(first + nnew);
+    upper_off_.resize(first + nnew);
+    for (int j = 0; j < nnew; ++j) {
+        levels_[first + j] = lv[j];
+        upper_off_[first + j] = lv[j] > 0 ? upper_rows_ : -1;
+        upper_rows_ += lv[j];
+    }
+    ensure_upper_rows(upper_rows_);
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_levels_ + first, levels_.data() + first, (size_t)nnew * 4, cudaMemcpyHostToDevice, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_ + first, upper_off_.data() + first, (size_t)nnew * 4, cudaMemcpyHostToDevice, stream_));
+    if (metric_ == COSINE) launch_item_norms(d_vectors_, pitch_, dim_, first, nnew, d_norms_, stream_);
+
+    HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    int done = 0;
+    while (done < nnew) {
+        const int v = first + done;
+        if (entry_ < 0) {  // GraphConnector.cs:28-33: the first node becomes the entry point, no links
+            entry_ = v;
+            top_ = levels_[v];
+            length_ = v + 1;
+            ++done;
+            continue;
+        }
+        int batch = 1;
+        const bool new_top = levels_[v] > top_;
+        if (!new_top) {
+            const int b = std::max(1, std::min(build_batch_max_, v / build_batch_ratio_));
+            while (done + batch < nnew && batch < b && levels_[v + batch] <= top_) ++batch;
+        }
+        length_ = v;  // nodes visible to this batch
+        launch_build_batch((int)metric_, view(), d_levels_, v, batch, params_.MaxCandidates, d_counters_, tuning_, stream_);
+        stats_.build_launches += 2;
+        if (new_top) {  // GraphConnector.cs:36-41
+            entry_ = v;
+            top_ = levels_[v];
+        }
+        done += batch;
+        length_ = v + batch;
+    }
+    length_ = first + nnew;
+    HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    int err = 0;
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(&err, d_counters_ + 2, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    float ms = 0.f;
+    HNSW_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    stats_.last_build_ms = ms;
+    if (err != 0) {
+        HNSW_CUDA_CHECK(cudaMemset(d_counters_ + 2, 0, sizeof(int)));
+        throw std::runtime_error("build: a node lock could not be acquired (index may be inconsistent)");
+    }
+    return count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchKnnQuery (HNSWIndex.cs:129-137) + result marshalling of HNSWIndexExports.cs:135-145
+// ---------------------------------------------------------------------------------------------
+static void fill_empty(int* ids, float* dists, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        ids[i] = -1;
+        dists[i] = std::numeric_limits<float>::quiet_NaN();
+    }
+}
+
+void Index::fetch_query_stats(int count) {
+    std::vector<QueryStats> h(count);
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(h.data(), d_stats_, (size_t)count * sizeof(QueryStats), cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    stats_.ndist = stats_.nexp = stats_.row_words = 0;
+    for (auto& q : h) { stats_.ndist += q.ndist; stats_.nexp += q.nexp; stats_.row_words += q.row_words; }
+}
+
+void Index::knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (count <= 0 || k < 1) return;
+    if (length_ <= 0) {  // HNSWIndex.cs:109
+        fill_empty(out_ids, out_dists, (size_t)count * k);
+        return;
+    }
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    ensure_query_scratch(count, k);
+    if (collect_stats_) ensure_stats(count);
+    const int ef = std::max(params_.MinNN, k);  // HNSWIndex.cs:115
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
+    HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    launch_knn_search((int)metric_, view(), d_q_, count, k, ef, d_ids_, d_dists_, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr, tuning_,
+                      stream_);
+    HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    stats_.search_launches += 1;
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists, d_dists_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    float ms = 0.f;
+    HNSW_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    stats_.last_search_ms = ms;
+    if (collect_stats_) fetch_query_stats(count);
+}
+
+void Index::knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (count <= 0 || k < 1) return;
+    if (length_ <= 0) throw std::runtime_error("knn_query_device on an empty index");
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    if (collect_stats_) ensure_stats(count);
+    const int ef = std::max(params_.MinNN, k);
+    HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    launch_knn_search((int)metric_, view(), d_queries, count, k, ef, d_ids, d_dists, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr, tuning_,
+                      stream_);
+    HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    stats_.search_launches += 1;
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    float ms = 0.f;
+    HNSW_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    stats_.last_search_ms = ms;
+    if (collect_stats_) fetch_query_stats(count);
+}
+
+void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (count <= 0 || k < 1) return;
+    if (length_ <= 0) {
+        fill_empty(out_ids, out_dists, (size_t)count * k);
+        return;
+    }
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    // bound the scratch: process the batch in slabs
+    const int slab = std::max(8, std::min(count, (int)((size_t)(1u << 30) / ((size_t)32 * k * 8))));
+    void* scratch = nullptr;
+    const size_t sbytes = exact_knn_scratch_bytes(slab, k, length_);
+    HNSW_CUDA_CHECK(cudaMalloc(&scratch, sbytes));
+    try {
+        for (int q0 = 0; q0 < count; q0 += slab) {
+            const int n = std::min(slab, count - q0);
+            ensure_query_scratch(n, k);
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries + (size_t)q0 * dim, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream_));
+            launch_exact_knn((int)metric_, view(), d_q_, n, k, d_ids_, d_dists_, scratch, sbytes, stream_);
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids + (size_t)q0 * k, d_ids_, (size_t)n * k * 4, cudaMemcpyDeviceToHost, stream_));
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists + (size_t)q0 * k, d_dists_, (size_t)n * k * 4, cudaMemcpyDeviceToHost, stream_));
+            HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        }
+    } catch (...) {
+        cudaFree(scratch);
+        throw;
+    }
+    cudaFree(scratch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Serialize / Deserialize (HNSWIndex.cs:210-229)
+// ---------------------------------------------------------------------------------------------
+void Index::export_graph(HostGraph& g) {
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    g = HostGraph();
+    g.params = params_;
+    g.dim = std::max(dim_, 0);
+    g.length = length_;
+    g.capacity = capacity_;
+    g.entry = entry_;
+    g.stride0 = stride0_;
+    g.strideU = strideU_;
+    g.levels.assign(levels_.begin(), levels_.begin() + length_);
+    g.upper_off.assign(upper_off_.begin(), upper_off_.begin() + length_);
+    g.vectors.resize((size_t)length_ * g.dim);
+    g.adj0.resize((size_t)length_ * stride0_);
+    g.adjU.resize((size_t)upper_rows_ * strideU_);
+    if (length_ > 0) {
+        HNSW_CUDA_CHECK(cudaMemcpy2DAsync(g.vectors.data(), (size_t)g.dim * 4, d_vectors_, (size_t)pitch_ * 4, (size_t)g.dim * 4, (size_t)length_,
+                                          cudaMemcpyDeviceToHost, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(g.adj0.data(), d_adj0_, g.adj0.size() * 4, cudaMemcpyDeviceToHost, stream_));
+        if (!g.adjU.empty()) HNSW_CUDA_CHECK(cudaMemcpyAsync(g.adjU.data(), d_adjU_, g.adjU.size() * 4, cudaMemcpyDeviceToHost, stream_));
+        HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+}
+
+void Index::serialize(const std::string& path, bool packed) {
+    std::lock_guard<std::mutex> lock(mu_);
+    HostGraph g;
+    export_graph(g);
+    write_snapshot(g, path, packed);
+}
+
+void Index::upload_graph(const HostGraph& g) {
+    const int n = g.length;
+    if (n == 0) return;
+    ensure_dim(g.dim);
+    capacity_ = std::max(capacity_, std::max(g.capacity, 1));
+    ensure_capacity(n);
+    levels_ = g.levels;
+    upper_off_ = g.upper_off;
+    upper_rows_ = (int)(g.adjU.size() / (size_t)strideU_);
+    for (int i = 0; i < n; ++i) {
+        if (levels_[i] > 30) throw std::runtime_error("snapshot: node level above 30 is not supported");
+        const int rows = levels_[i];
+        if (rows > 0 && (upper_off_[i] < 0 || upper_off_[i] + rows > upper_rows_)) throw std::runtime_error("snapshot: inconsistent upper-layer rows");
+    }
+    // every link at layer l must point at a node that exists on layer l
+    for (int i = 0; i < n; ++i)
+        for (int l = 1; l <= levels_[i]; ++l) {
+            const int* row = g.adjU.data() + ((size_t)upper_off_[i] + (l - 1)) * strideU_;
+            for (int j = 0; j < strideU_ && row[j] >= 0; ++j)
+                if (levels_[row[j]] < l) throw std::runtime_error("snapshot: upper-layer link to a node that is not on that layer");
+        }
+    ensure_upper_rows(upper_rows_);
+    HNSW_CUDA_CHECK(cudaMemcpy2DAsync(d_vectors_, (size_t)pitch_ * 4, g.vectors.data(), (size_t)dim_ * 4, (size_t)dim_ * 4, (size_t)n,
+                                      cudaMemcpyHostToDevice, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_adj0_, g.adj0.data(), g.adj0.size() * 4, cudaMemcpyHostToDevice, stream_));
+    if (!g.adjU.empty()) HNSW_CUDA_CHECK(cudaMemcpyAsync(d_adjU_, g.adjU.data(), g.adjU.size() * 4, cudaMemcpyHostToDevice, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_levels_, levels_.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_, upper_off_.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+    if (metric_ == COSINE) launch_item_norms(d_vectors_, pitch_, dim_, 0, n, d_norms_, stream_);
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    length_ = n;
+    entry_ = g.entry;
+    top_ = levels_[entry_];
+}
+
+Index* Index::from_snapshot(MetricKind metric, const std::string& path) {
+    HostGraph g;
+    read_snapshot(path, g);
+    Index* ix = new Index(metric, g.params);
+    try {
+        if (g.stride0 != ix->stride0_ || g.strideU != ix->strideU_) throw std::runtime_error("snapshot: stride mismatch");
+        ix->upload_graph(g);
+    } catch (...) {
+        delete ix;
+        throw;
+    }
+    return ix;
+}
+
+}  // namespace hnsw

@@ -1,0 +1,122 @@
+// engine.hpp -- host side of the B200 HNSW engine: the object behind an hnsw_* handle.
+//
+// Mirrors HNSWIndex<float[], float> (HNSWIndex.cs) for the accelerated path:
+//   ctor(parameters)            HNSWIndex.cs:20-30     -> Index(metric, params)
+//   Add(List<float[]>)          HNSWIndex.cs:70-78     -> add()
+//   BatchKnnQuery               HNSWIndex.cs:129-137   -> knn_query()
+//   Serialize / Deserialize     HNSWIndex.cs:210-229   -> serialize() / from_snapshot()
+//   Count                       HNSWIndex.cs:250       -> count()
+// GraphData's arrays of objects (GraphData.cs:17-25) become flat device arrays
+// (common.cuh GraphView); AddItem's slot allocation, level draw and x2 growth
+// (GraphData.cs:79-118, 211-219) stay on the host because they are sequential
+// scalar bookkeeping.  All distance work runs on the GPU; there is no CPU fallback.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.hpp"
+#include "snapshot.hpp"
+
+namespace hnsw {
+
+// System.Random(seed) of the .NET BCL (seeded legacy algorithm), needed so that levels drawn by
+// GraphData.GetRandomLayer (GraphData.cs:211-219) come out identical for a given RandomSeed.
+class DotNetRandom {
+public:
+    explicit DotNetRandom(int seed);
+    float NextSingle();
+private:
+    int InternalSample();
+    int seed_array_[56];
+    int inext_, inextp_;
+};
+
+struct IndexStats {
+    double last_search_ms = 0.0;    // device time of the last search kernel (CUDA events)
+    double last_build_ms = 0.0;     // device time of the last add() (all batches)
+    unsigned long long ndist = 0;   // distance evaluations of the last search (if stats enabled)
+    unsigned long long nexp = 0;
+    unsigned long long row_words = 0;
+    unsigned long long search_launches = 0, build_launches = 0;  // kernels launched since creation
+};
+
+class Index {
+public:
+    Index(MetricKind metric, const Parameters& params);
+    ~Index();
+    Index(const Index&) = delete;
+    Index& operator=(const Index&) = delete;
+
+    static Index* from_snapshot(MetricKind metric, const std::string& path);
+
+    int add(const float* vectors, int count, int dim, int* out_ids);
+    void knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists);
+    // queries / outputs already resident in device memory of this index's GPU
+    void knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists);
+    void exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists);
+    void serialize(const std::string& path, bool packed);
+
+    int count() const { return length_; }
+    int dim() const { return dim_; }
+    const Parameters& params() const { return params_; }
+    void set_min_nn(int v) { params_.MinNN = v; }
+    void set_tuning(const std::string& key, int value);
+    // run on a caller-owned CUDA stream (e.g. torch's current stream) instead of the index's own
+    void set_stream(cudaStream_t s);
+    void enable_stats(bool on) { collect_stats_ = on; }
+    IndexStats stats() const { return stats_; }
+    void export_graph(HostGraph& g);  // device -> host copy of the whole index
+    int device() const { return device_; }
+
+private:
+    void ensure_dim(int dim);
+    void ensure_capacity(int needed);
+    void ensure_upper_rows(int needed);
+    void ensure_query_scratch(int count, int k);
+    void ensure_stats(int count);
+    void upload_graph(const HostGraph& g);
+    GraphView view() const;
+    void fetch_query_stats(int count);
+
+    MetricKind metric_;
+    Parameters params_;
+    Tuning tuning_;
+    DotNetRandom rng_;
+    int device_ = 0;
+    int dim_ = -1, pitch_ = 0;
+    int stride0_, strideU_;
+    int length_ = 0, capacity_ = 0, dev_capacity_ = 0;
+    int entry_ = -1, top_ = -1;
+    bool collect_stats_ = false;
+    IndexStats stats_;
+    int build_batch_max_ = 4096;   // new nodes per build launch (upper bound)
+    int build_batch_ratio_ = 32;   // ... and at most 1/ratio of the nodes already linked
+
+    std::vector<int> levels_, upper_off_;
+    int upper_rows_ = 0, upper_rows_cap_ = 0;
+
+    float* d_vectors_ = nullptr;
+    double* d_norms_ = nullptr;
+    int* d_adj0_ = nullptr;
+    int* d_upper_off_ = nullptr;
+    int* d_adjU_ = nullptr;
+    int* d_locks_ = nullptr;
+    int* d_levels_ = nullptr;
+    unsigned* d_counters_ = nullptr;  // [0..2] build, [3] search
+
+    float* d_q_ = nullptr;
+    int* d_ids_ = nullptr;
+    float* d_dists_ = nullptr;
+    QueryStats* d_stats_ = nullptr;
+    size_t q_cap_ = 0, out_cap_ = 0, stats_cap_ = 0;
+
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    std::mutex mu_;
+};
+
+}  // namespace hnsw

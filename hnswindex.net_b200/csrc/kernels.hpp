@@ -1,0 +1,46 @@
+// kernels.hpp -- host-callable launchers of the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace hnsw {
+
+struct Tuning {
+    int vis_size_search = 0;  // 0 = derive from ef
+    int vis_size_build = 0;
+    int blocks_per_sm = 0;    // 0 = occupancy query
+};
+
+// per-query counters written by the search kernel when requested
+struct QueryStats {
+    unsigned ndist, nexp, row_words;
+};
+
+int device_sm_count();
+
+// K2: batched KnnQuery (HNSWIndex.cs:107-137).  queries: device [nq][dim] dense fp32;
+// out_ids/out_dists: device [nq][k], rows ascending, padded with -1 / NaN.
+void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int* d_ids, float* d_dists,
+                       unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream);
+
+// per-item sqrt((double)normA) in the cosine metric's accumulation order
+void launch_item_norms(const float* d_vectors, int pitch, int dim, int first, int count, double* d_norm_sqrt, cudaStream_t stream);
+
+// K4+K5: for new nodes [first, first+count): descent, per-layer beam search (ef = MaxCandidates) against the
+// graph as it stands, relative-neighbour selection, write the node's own rows.
+// K6: reverse links with per-node locks and overflow pruning.
+void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int first, int count, int ef_construction,
+                        unsigned* d_work_counter, const Tuning& t, cudaStream_t stream);
+
+// K3: exact brute-force top-k (recall ground truth), same metric arithmetic.
+void launch_exact_knn(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists,
+                      void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t exact_knn_scratch_bytes(int nq, int k, int count);
+
+// K7: merge `parts` sorted top-k lists per query: in_* are [parts][nq][k], out_* [nq][k]
+void launch_merge_topk(const int* d_in_ids, const float* d_in_dists, int parts, int nq, int k, int* d_out_ids, float* d_out_dists,
+                       cudaStream_t stream);
+
+}  // namespace hnsw

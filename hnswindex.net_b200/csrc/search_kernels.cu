@@ -1,0 +1,146 @@
+// search_kernels.cu -- K2: batched KnnQuery on sm_100a, one warp per query.
+//
+// Replaces HNSWIndex.BatchKnnQuery / KnnQuery (HNSWIndex.cs:107-137):
+//   ef = max(MinNN, k); greedy descent over layers top..1 (GraphNavigator.cs:39-82);
+//   layer-0 beam search of width ef (GraphNavigator.cs:194-256); ascending by distance,
+//   first k (HNSWIndex.cs:119-123); rows padded with -1 / NaN (HNSWIndexExports.cs:135-145).
+// Persistent grid: every warp pulls the next query index from a global counter, so
+// long and short searches balance across the 148 SMs.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "beam.cuh"
+#include "kernels.hpp"
+
+namespace hnsw {
+
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads)
+knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int vis_size, int cand_cap,
+                  int* __restrict__ out_ids, float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis_size, cand_cap);
+    const WarpScratch s = carve_scratch(smem + warp * per_warp, g.pitch, ef, vis_size, cand_cap);
+
+    for (;;) {
+        unsigned qi = 0;
+        if (lane == 0) qi = atomicAdd(work_counter, 1u);
+        qi = __shfl_sync(FULL, qi, 0);
+        if (qi >= (unsigned)nq) break;
+
+        const float* qsrc = queries + (size_t)qi * g.dim;
+        for (int i = lane; i < g.pitch; i += 32) s.q[i] = i < g.dim ? __ldg(qsrc + i) : 0.f;
+        __syncwarp();
+        double qn = 0.0;
+        if (METRIC == COSINE) qn = pair_norm_sqrt(s.q, g.dim, lane & 1);
+
+        WarpCounters wc;
+        int cur = g.entry;
+        float cur_d = single_dist<METRIC>(g, s, qn, cur, lane);
+        wc.ndist++;
+        for (int layer = g.top_layer; layer > 0; --layer) greedy_layer<METRIC>(g, s, qn, layer, cur, cur_d, lane, wc);
+
+        BeamState st;
+        beam_search<METRIC>(g, s, qn, 0, cur, cur_d, ef, st, lane, wc);
+
+        for (int j = lane; j < k; j += 32) {
+            int id = -1;
+            float d = CUDART_NAN_F;
+            if (j < st.n) {
+                const u64 e = s.list[j];
+                id = key_id(e);
+                d = key_dist(e);
+            }
+            out_ids[(size_t)qi * k + j] = id;
+            out_dists[(size_t)qi * k + j] = d;
+        }
+        if (stats != nullptr && lane == 0) {
+            QueryStats qs;
+            qs.ndist = wc.ndist; qs.nexp = wc.nexp; qs.row_words = wc.row_words;
+            stats[qi] = qs;
+        }
+        __syncwarp();
+    }
+}
+
+// one lane pair per item; 16 items per warp
+__global__ void item_norms_kernel(const float* __restrict__ vectors, int pitch, int dim, int first, int count, double* __restrict__ norm_sqrt) {
+    const int lane = threadIdx.x & 31;
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const bool active = pair < count;
+    const int id = first + (active ? pair : 0);
+    const double r = pair_norm_sqrt(vectors + (size_t)id * pitch, dim, lane & 1);
+    if (active && (lane & 1) == 0) norm_sqrt[id] = r;
+}
+
+int device_sm_count() {
+    int dev = 0, sms = 0;
+    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return sms;
+}
+
+static int pow2_at_least(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int pick_vis_size(int requested, int ef) {
+    if (requested > 0) return std::max(64, pow2_at_least(requested));
+    // ~25 distance evaluations per unit of ef are typical; 16*ef slots keep most of them
+    return std::min(8192, std::max(256, pow2_at_least(16 * ef)));
+}
+
+template <typename Kern>
+static int configure_persistent(Kern kern, size_t smem, const Tuning& t, int work_items, int items_per_block) {
+    int dev = 0, max_optin = 0;
+    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)max_optin)
+        throw std::runtime_error("search width too large for shared memory: need " + std::to_string(smem) + " B per block, have " +
+                                 std::to_string(max_optin));
+    HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);
+    const int sms = device_sm_count();
+    const int need = (work_items + items_per_block - 1) / items_per_block;
+    return std::max(1, std::min(need, sms * per_sm));  // persistent: at most one resident wave
+}
+
+void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int* d_ids, float* d_dists,
+                       unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream) {
+    if (nq <= 0) return;
+    const int vis = pick_vis_size(t.vis_size_search, ef);
+    const int cand_cap = ((std::max(g.stride0, g.strideU) + 31) / 32) * 32;
+    const size_t smem = warp_scratch_bytes(g.pitch, ef, vis, cand_cap) * kWarpsPerBlock;
+    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
+#define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
+    {                                                                                                                           \
+        const int grid = configure_persistent(knn_search_kernel<M>, smem, t, nq, kWarpsPerBlock);                               \
+        knn_search_kernel<M><<<grid, kThreads, smem, stream>>>(g, d_queries, nq, k, ef, vis, cand_cap, d_ids, d_dists,         \
+                                                               d_work_counter, d_stats);                                       \
+    }
+    switch (metric) {
+        case SQ_EUCLID: HNSW_LAUNCH_SEARCH(SQ_EUCLID) break;
+        case COSINE: HNSW_LAUNCH_SEARCH(COSINE) break;
+        default: HNSW_LAUNCH_SEARCH(UCOSINE) break;
+    }
+#undef HNSW_LAUNCH_SEARCH
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_item_norms(const float* d_vectors, int pitch, int dim, int first, int count, double* d_norm_sqrt, cudaStream_t stream) {
+    if (count <= 0) return;
+    const int threads = 256;
+    const int blocks = (count * 2 + threads - 1) / threads;
+    item_norms_kernel<<<blocks, threads, 0, stream>>>(d_vectors, pitch, dim, first, count, d_norm_sqrt);
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace hnsw

@@ -1,0 +1,155 @@
+/*
+ * hnsw_b200.h -- C ABI of the B200-native HNSW engine.
+ *
+ * Drop-in boundary: the library exports exactly the cdecl symbols that the reference's NativeAOT
+ * shim `bindings/HNSWIndex.Native/HNSWIndexExports.cs` exports (and that `bindings/bindings.py`
+ * binds with ctypes, lines 46-119), with the same argument meaning, return codes and error
+ * behaviour, so the reference's Python package and any P/Invoke host work unchanged when the
+ * shared object is installed as  <package>/artifacts/native/linux-x64/HNSWIndex.Native.so.
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Part 1 = the reference's 16 exports.  Part 2 = additions the C# surface has but the reference's
+ * native shim lacks (Serialize/Deserialize/Count), plus device selection, resident-buffer entry
+ * points and measurement hooks.  All citations are relative to /root/reference.
+ *
+ * Errors never cross the ABI as exceptions: functions return -1 (or a null handle) and the text
+ * is available from hnsw_get_last_error_utf8, as in HNSWIndexExports.cs:11-12,27-39.
+ * Threading: as the reference (README.md:64-65) -- operations of one type may run concurrently
+ * with each other; this implementation additionally serialises calls on one handle internally.
+ */
+#ifndef HNSW_B200_H
+#define HNSW_B200_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define HNSW_API __declspec(dllexport)
+#else
+#define HNSW_API __attribute__((visibility("default")))
+#endif
+
+typedef void* hnsw_handle;
+
+/* ------------------------------------------------------------------ Part 1: reference exports */
+
+/* HNSWIndexExports.cs:27-39.  Returns the UTF-8 byte length of the last error (excluding NUL);
+ * if buf != NULL and bufLen > 0, writes at most bufLen-1 bytes and a terminating NUL. */
+HNSW_API int hnsw_get_last_error_utf8(char* buf, int bufLen);
+
+/* HNSWIndexExports.cs:41-65.  metric: "sq_euclid" | "cosine" | "ucosine".  Consumes the pending
+ * process-global parameters (hnsw_set_*) and resets them to defaults.  NULL on error. */
+HNSW_API hnsw_handle hnsw_create(const char* distanceMetric);
+
+/* HNSWIndexExports.cs:67-73.  No-op on NULL. */
+HNSW_API void hnsw_free(hnsw_handle handle);
+
+/* HNSWIndexExports.cs:75-100 -> HNSWIndex.Add(List) (HNSWIndex.cs:70-78).  vectors: row-major
+ * [count][dim] fp32, caller-owned (copied before return).  Writes `count` ids (slot numbers; -1 for
+ * a rejected item).  Returns the number written, 0 if handle/vectors is NULL or count/dim <= 0,
+ * -1 on error.  The dimension is fixed by the first call. */
+HNSW_API int hnsw_add(hnsw_handle handle, const float* vectors, int count, int dim, int* outIds);
+
+/* HNSWIndexExports.cs:102-117 -> HNSWIndex.Remove (HNSWIndex.cs:83-100).  Removal is outside the
+ * accelerated path: returns 0 for NULL handle / NULL ids / count <= 0 like the
+ * reference, otherwise -1 with an explanatory error. */
+HNSW_API int hnsw_remove(hnsw_handle handle, const int* ids, int count);
+
+/* HNSWIndexExports.cs:119-149 -> HNSWIndex.BatchKnnQuery (HNSWIndex.cs:129-137).  outIds/outDists:
+ * caller-owned row-major [count][k]; each row ascending by distance, padded with id -1 / NaN when
+ * fewer than k results exist.  Returns 0, or -1 on error; returns 0 without writing if handle is NULL. */
+HNSW_API int hnsw_knn_query(hnsw_handle handle, const float* vectors, int count, int dim, int k, int* outIds, float* outDists);
+
+/* HNSWIndexExports.cs:151-197 -> HNSWIndex.BatchRangeQuery (HNSWIndex.cs:160-168).  The callee
+ * allocates outIds[i]/outDists[i] (malloc) and sets counts[i]; release with hnsw_free_results. */
+HNSW_API int hnsw_range_query(hnsw_handle handle, const float* vectors, int count, int dim, float range, void** outIds, void** outDists,
+                              int* counts);
+
+/* HNSWIndexExports.cs:199-217. */
+HNSW_API void hnsw_free_results(void** idsArray, void** distsArray, int count);
+
+/* HNSWIndexExports.cs:219-273: mutate the pending parameters used by the NEXT hnsw_create
+ * (HNSWParameters.cs:13-55).  Return 0, or -1 on error. */
+HNSW_API int hnsw_set_collection_size(int collectionSize);
+HNSW_API int hnsw_set_max_edges(int maxEdges);
+HNSW_API int hnsw_set_max_candidates(int maxCandidates);
+HNSW_API int hnsw_set_remove_max_candidates(int maxCandidates);
+HNSW_API int hnsw_set_distribution_rate(float distRate);
+HNSW_API int hnsw_set_random_seed(int seed);
+HNSW_API int hnsw_set_min_nn(int minNN);
+HNSW_API int hnsw_set_allow_removals(bool allowRemovals);
+
+/* ------------------------------------------------------------------ Part 2: additions */
+
+/* HNSWIndex.Count (HNSWIndex.cs:250). -1 on NULL handle. */
+HNSW_API int hnsw_count(hnsw_handle handle);
+/* dimension fixed by the first add / by the snapshot, -1 if none yet */
+HNSW_API int hnsw_dim(hnsw_handle handle);
+
+/* HNSWIndex.Serialize (HNSWIndex.cs:210-217): writes the protobuf-net snapshot layout.
+ * packed != 0 writes repeated scalars packed (smaller/faster; both forms are accepted on read). */
+HNSW_API int hnsw_serialize(hnsw_handle handle, const char* path, int packed);
+/* HNSWIndex.Deserialize (HNSWIndex.cs:222-229).  NULL on error. */
+HNSW_API hnsw_handle hnsw_deserialize(const char* distanceMetric, const char* path);
+
+/* HNSWParameters is a live object in the C# API (KnnQuery reads parameters.MinNN on every call,
+ * HNSWIndex.cs:115): change MinNN (= ef) of an existing index. */
+HNSW_API int hnsw_index_set_min_nn(hnsw_handle handle, int minNN);
+/* read back the parameters of an index: ints = {MaxEdges, MinNN, MaxCandidates, RemoveMaxCandidates,
+ * CollectionSize, RandomSeed, AllowRemovals}, rate = DistributionRate */
+HNSW_API int hnsw_index_get_params(hnsw_handle handle, int* ints7, double* rate);
+
+/* One process per GPU: select the CUDA device used by indexes created afterwards on this thread. */
+HNSW_API int hnsw_set_device(int device);
+HNSW_API int hnsw_device_count(void);
+
+/* Same as hnsw_knn_query with queries/outputs already resident in the index's GPU memory
+ * (dense [count][dim] fp32 -> [count][k]).  Synchronises before returning. */
+HNSW_API int hnsw_knn_query_device(hnsw_handle handle, const float* dQueries, int count, int dim, int k, int* dOutIds, float* dOutDists);
+/* Run the index's work on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream. */
+HNSW_API int hnsw_set_stream(hnsw_handle handle, void* cudaStream);
+
+/* Exact brute-force top-k over the indexed vectors with the index's metric (recall ground truth). */
+HNSW_API int hnsw_exact_knn(hnsw_handle handle, const float* queries, int count, int dim, int k, int* outIds, float* outDists);
+
+/* Merge `parts` per-partition top-k results (device memory, [parts][count][k], rows ascending,
+ * -1 padded) into [count][k] on the current device. */
+HNSW_API int hnsw_merge_topk_device(const int* dInIds, const float* dInDists, int parts, int count, int k, int* dOutIds, float* dOutDists,
+                                    void* cudaStream);
+
+/* Measurement hooks. */
+typedef struct hnsw_stats {
+    double last_search_ms;              /* CUDA-event time of the last search kernel */
+    double last_build_ms;               /* CUDA-event time of the last hnsw_add (all batches) */
+    unsigned long long ndist;           /* last search: distance evaluations (needs stats enabled) */
+    unsigned long long nexp;            /* last search: rows expanded */
+    unsigned long long row_words;       /* last search: sum of (degree + 1) over expansions */
+    unsigned long long search_launches; /* kernels launched since creation */
+    unsigned long long build_launches;
+} hnsw_stats;
+HNSW_API int hnsw_enable_stats(hnsw_handle handle, int on);
+HNSW_API int hnsw_get_stats(hnsw_handle handle, hnsw_stats* out);
+/* tuning knobs: "vis_size_search", "vis_size_build", "blocks_per_sm", "build_batch_max", "build_batch_ratio" */
+HNSW_API int hnsw_set_tuning(hnsw_handle handle, const char* key, int value);
+
+/* Copy the graph to host memory (tests / inspection).  levels[count]; rows0[count][stride0] (-1 padded).
+ * Pass NULL pointers to query sizes only.  Returns count, or -1. */
+HNSW_API int hnsw_export_layer0(hnsw_handle handle, int* levels, int* rows0, int* stride0, int* entryPoint);
+/* rows of one upper layer: rows[count][strideU], all -1 for nodes below that layer */
+HNSW_API int hnsw_export_layer(hnsw_handle handle, int layer, int* rows, int* stride);
+
+/* Host-only: read a snapshot file and write it again (packed or unpacked).  Exercises the codec
+ * without a GPU; used by the CPU test-suite. */
+HNSW_API int hnsw_snapshot_transcode(const char* inPath, const char* outPath, int packed);
+
+/* library identification: returns "hnsw-b200 <version> sm_100a" */
+HNSW_API const char* hnsw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNSW_B200_H */

@@ -1,0 +1,309 @@
+"""
+GPU parity tests (run on the B200 box with `-m gpu`).  Everything goes through the C ABI
+(hnswindex package = ctypes over HNSWIndex.Native.so) and is checked against the oracle
+(the CPU restatement of the reference) on the same serialized graph and the same queries.
+
+Bars (BASELINE.json north_star): id lists identical for >= 99.5 % of queries (the rest only fp32
+ties), distances within 1e-5 relative -- the tests below ask for more: bit-identical distances.
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hnswindex():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as ge
+    ge.build()
+    import hnswindex
+    return hnswindex
+
+
+def sift_like(n, dim=128, rank=16, seed=1234, noise=0.25):
+    """x = zA + 0.25 eps, low intrinsic dimension like SIFT."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((rank, dim)).astype(np.float32)
+    z = rng.standard_normal((n, rank)).astype(np.float32)
+    return (z @ A + noise * rng.standard_normal((n, dim)).astype(np.float32)).astype(np.float32)
+
+
+def _oracle_graph(oracle, tmp_path, metric, data, name, **kw):
+    ix = oracle.OracleIndex(metric, **kw)
+    ix.add(data)
+    path = tmp_path / f"{name}.hnsw"
+    ix.serialize(path, packed=True)
+    return ix, path
+
+
+def _assert_identical(g_ids, g_d, o_ids, o_d, min_same=0.995):
+    same_rows = (g_ids == o_ids).all(axis=1)
+    assert same_rows.mean() >= min_same, f"identical id lists: {same_rows.mean():.4f}"
+    # where ids agree the distances must be the same bits (K1 is bit-exact), NaN padding included
+    a, b = g_d[same_rows].view(np.uint32), o_d[same_rows].view(np.uint32)
+    nan = np.isnan(g_d[same_rows]) & np.isnan(o_d[same_rows])
+    assert np.array_equal(a[~nan], b[~nan])
+    # rows that differ may only differ through exact fp32 ties: the distance lists still agree
+    if (~same_rows).any():
+        assert np.allclose(g_d[~same_rows], o_d[~same_rows], rtol=1e-5, atol=0, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------- search
+@pytest.mark.parametrize("metric,dim,normalize", [
+    ("sq_euclid", 128, False), ("cosine", 128, False), ("ucosine", 128, True),
+    ("sq_euclid", 127, False), ("cosine", 100, False), ("ucosine", 96, True), ("cosine", 960, False), ("sq_euclid", 20, False),
+])
+def test_knn_query_matches_oracle_on_same_graph(hnswindex, oracle, tmp_path, metric, dim, normalize):
+    n = 3000 if dim < 900 else 1200
+    rng = np.random.default_rng(dim)
+    data = rng.random((n, dim), dtype=np.float32)
+    queries = rng.random((400, dim), dtype=np.float32)
+    if normalize:
+        data /= np.linalg.norm(data, axis=1, keepdims=True)
+        queries /= np.linalg.norm(queries, axis=1, keepdims=True)
+    ref, path = _oracle_graph(oracle, tmp_path, metric, data, f"{metric}{dim}")
+    gpu = hnswindex.Index.deserialize(metric, path)
+    assert gpu.count == n and gpu.dim == dim
+    assert gpu.params() == ref.params()
+    for k, min_nn in ((1, 5), (5, 5), (10, 5), (10, 64), (100, 5), (3, 300)):
+        ref.set_min_nn(min_nn)
+        gpu.set_min_nn(min_nn)
+        o_ids, o_d = ref.knn_query(queries, k, threads=8)
+        g_ids, g_d = gpu.knn_query(queries, k)
+        _assert_identical(g_ids, g_d, o_ids, o_d)
+
+
+def test_self_queries_readme_config(hnswindex, oracle, tmp_path):
+    # BASELINE config[0] / README.md:80-96: 2000 x 128 rand, sq_euclid, MaxEdges 16, k=1 batch query
+    rng = np.random.default_rng(1234)
+    data = rng.random((2000, 128), dtype=np.float32)
+    ref, path = _oracle_graph(oracle, tmp_path, "sq_euclid", data, "readme", collection_size=2000)
+    gpu = hnswindex.Index.deserialize("sq_euclid", path)
+    o_ids, o_d = ref.knn_query(data, 1)
+    g_ids, g_d = gpu.knn_query(data, 1)
+    _assert_identical(g_ids, g_d, o_ids, o_d, min_same=1.0)
+    assert (g_ids[:, 0] == np.arange(2000)).mean() > 0.85
+
+
+def test_small_and_ragged_cases(hnswindex, oracle, tmp_path):
+    # fewer nodes than k -> padded with -1 / NaN (HNSWIndexExports.cs:144); single node; single query
+    for n in (1, 2, 7):
+        data = np.random.default_rng(n).random((n, 16), dtype=np.float32)
+        ref, path = _oracle_graph(oracle, tmp_path, "sq_euclid", data, f"tiny{n}")
+        gpu = hnswindex.Index.deserialize("sq_euclid", path)
+        q = np.random.default_rng(99).random((3, 16), dtype=np.float32)
+        o_ids, o_d = ref.knn_query(q, 10)
+        g_ids, g_d = gpu.knn_query(q, 10)
+        assert np.array_equal(g_ids, o_ids)
+        assert np.array_equal(np.isnan(g_d), np.isnan(o_d))
+        assert (g_ids[:, n:] == -1).all() and np.isnan(g_d[:, n:]).all()
+        g1, _ = gpu.knn_query(q[0], 1)  # 1-D query
+        assert g1.shape == (1, 1)
+
+
+def test_query_empty_index_and_dim_mismatch(hnswindex):
+    ix = hnswindex.Index(8)
+    ix.set_collection_size(16)
+    ix.add(np.zeros((1, 8), dtype=np.float32) + 0.5)
+    with pytest.raises(ValueError):
+        ix.knn_query(np.zeros((1, 9), dtype=np.float32), 1)
+    import ctypes as ct
+    q = np.zeros((1, 9), dtype=np.float32)
+    ids = np.zeros((1, 1), dtype=np.int32)
+    d = np.zeros((1, 1), dtype=np.float32)
+    rc = hnswindex.lib.hnsw_knn_query(ix._h, q.ctypes.data_as(ct.POINTER(ct.c_float)), 1, 9, 1, ids.ctypes.data_as(ct.POINTER(ct.c_int)),
+                                     d.ctypes.data_as(ct.POINTER(ct.c_float)))
+    assert rc == -1 and "dimension" in hnswindex.last_error()
+
+
+def test_results_do_not_depend_on_visited_table_size(hnswindex, oracle, tmp_path):
+    # The shared-memory visited table may forget; results must not change, only the work does.
+    data = sift_like(6000)
+    queries = sift_like(300, seed=4321)
+    ref, path = _oracle_graph(oracle, tmp_path, "sq_euclid", data, "vis", max_candidates=100)
+    ref.set_min_nn(48)
+    o_ids, o_d, oc = ref.knn_query(queries, 10, counters=True)
+    work = {}
+    for vis in (64, 256, 4096):
+        gpu = hnswindex.Index.deserialize("sq_euclid", path)
+        gpu.set_min_nn(48)
+        gpu.set_tuning("vis_size_search", vis)
+        gpu.enable_stats(True)
+        g_ids, g_d = gpu.knn_query(queries, 10)
+        _assert_identical(g_ids, g_d, o_ids, o_d, min_same=1.0)
+        work[vis] = gpu.stats()["ndist"]
+        assert gpu.stats()["nexp"] == int(oc[1])          # same expansions as the reference algorithm
+        assert gpu.stats()["row_words"] == int(oc[2])
+    assert work[64] >= work[256] >= work[4096] >= int(oc[0]) - 300 * 8
+    assert work[4096] <= 1.05 * int(oc[0])               # a large table re-evaluates almost nothing
+
+
+def test_exact_knn_matches_oracle(hnswindex, oracle, tmp_path):
+    for metric, dim in (("sq_euclid", 128), ("cosine", 100), ("ucosine", 96)):
+        rng = np.random.default_rng(5)
+        data = rng.standard_normal((5000, dim)).astype(np.float32)
+        q = rng.standard_normal((64, dim)).astype(np.float32)
+        if metric == "ucosine":
+            data /= np.linalg.norm(data, axis=1, keepdims=True)
+            q /= np.linalg.norm(q, axis=1, keepdims=True)
+        ref, path = _oracle_graph(oracle, tmp_path, metric, data, f"exact{metric}", max_edges=4, max_candidates=8)
+        gpu = hnswindex.Index.deserialize(metric, path)
+        for k in (1, 10, 100):
+            o_ids, o_d = ref.exact_knn(q, k)
+            g_ids, g_d = gpu.exact_knn(q, k)
+            assert np.array_equal(g_ids, o_ids), (metric, k)
+            assert np.array_equal(g_d.view(np.uint32), o_d.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------- snapshot
+def test_gpu_serialize_roundtrip(hnswindex, oracle, tmp_path):
+    # GraphSerializationTests.cs:17-48 through the GPU engine: load -> serialize -> load -> same answers,
+    # and the oracle reads the GPU-written file to the same graph.
+    data = oracle.random_vectors(128, 2000)
+    ref, path = _oracle_graph(oracle, tmp_path, "sq_euclid", data, "rt")
+    gpu = hnswindex.Index.deserialize("sq_euclid", path)
+    out = tmp_path / "gpu_written.hnsw"
+    gpu.serialize(out)  # unpacked, the layout protobuf-net writes by default
+    gpu2 = hnswindex.Index.deserialize("sq_euclid", out)
+    ref2 = oracle.OracleIndex.deserialize("sq_euclid", out)
+    a = gpu.knn_query(data, 5)
+    b = gpu2.knn_query(data, 5)
+    c = ref2.knn_query(data, 5)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    _assert_identical(a[0], a[1], c[0], c[1], min_same=1.0)
+    assert ref2.params() == ref.params() and ref2.entry_point == ref.entry_point
+
+
+# ---------------------------------------------------------------------------------------- construction
+def _rows_as_sets(rows):
+    return [frozenset(int(x) for x in r if x >= 0) for r in rows]
+
+
+@pytest.mark.parametrize("metric", ["sq_euclid", "cosine"])
+def test_one_by_one_insertion_builds_the_oracle_graph(hnswindex, oracle, metric):
+    # Adding items one call at a time is the reference's serial Add: the GPU must produce the same
+    # levels, entry point and link sets (row order is free only where the reference's is: the
+    # unsorted early return of Heuristic.cs:13-18).
+    v = oracle.random_vectors(32, 700)
+    ref = oracle.OracleIndex(metric, max_edges=8, max_candidates=40, collection_size=64, allow_removals=False)
+    ref.add(v)
+    gpu = hnswindex.Index(32, metric)
+    gpu.set_max_edges(8); gpu.set_max_candidates(40); gpu.set_collection_size(64); gpu.set_allow_removals(False)
+    ids = [int(gpu.add(v[i])[0]) for i in range(len(v))]
+    assert ids == list(range(700))
+    levels, rows0, ep = gpu.export_layer0()
+    o_rows0, o_levels, _ = ref.export_layer(0, rows0.shape[1])
+    assert np.array_equal(levels, o_levels)
+    assert ep == ref.entry_point
+    mism = sum(a != b for a, b in zip(_rows_as_sets(rows0), _rows_as_sets(o_rows0)))
+    assert mism == 0, f"{mism} layer-0 rows differ"
+    for layer in range(1, int(levels.max()) + 1):
+        g = gpu.export_layer(layer)
+        o, _, _ = ref.export_layer(layer, g.shape[1])
+        assert _rows_as_sets(g) == _rows_as_sets(o), layer
+
+
+def test_reference_recall_windows_on_gpu_built_graphs(hnswindex, oracle):
+    # the reference's own acceptance windows, graph built by batched GPU insertion
+    import json
+    from pathlib import Path
+    cases = json.load(open(Path(__file__).resolve().parent / "golden" / "reference_windows.json"))
+    fx = {"v2000": 2000, "v1000": 1000, "v5000": 5000}
+    for c in cases:
+        v = oracle.normalize_rows_like_reference(oracle.random_vectors(128, fx[c["fixture"]]))
+        ix = hnswindex.Index(128, c["metric"])
+        p = c["params"]
+        if "min_nn" in p: ix.set_min_nn(p["min_nn"])
+        if "max_candidates" in p: ix.set_max_candidates(p["max_candidates"])
+        if "max_edges" in p: ix.set_max_edges(p["max_edges"])
+        if "collection_size" in p: ix.set_collection_size(p["collection_size"])
+        ids = ix.add(v)
+        assert np.array_equal(ids, np.arange(len(v)))
+        res, _ = ix.knn_query(v, 1)
+        r = float((res[:, 0] == ids).mean())
+        assert c["lo"] < r < c["hi"], (c["name"], r)
+        assert abs(r - c["oracle_value"]) < 0.03, (c["name"], r, c["oracle_value"])
+
+
+def test_python_binding_tests_of_the_reference(hnswindex):
+    # bindings/__tests__/parameters_test.py + recall_test.py (the ones on the accelerated path)
+    DIM = 128
+    rng = np.random.default_rng(0)
+    vectors = rng.random((2000, DIM))
+
+    def recall_of(setup):
+        ix = hnswindex.Index(DIM)
+        setup(ix)
+        ids = ix.add(vectors)
+        return float((ids == ix.knn_query(vectors, 1)[0][:, 0]).sum()) / len(ids)
+
+    default = recall_of(lambda ix: None)
+    assert default > 0.85                                          # recall_test.py:15
+    assert recall_of(lambda ix: ix.set_min_nn(1)) < default         # parameters_test.py:7-22
+    assert recall_of(lambda ix: ix.set_max_edges(1)) < 0.1          # :25-34
+    assert recall_of(lambda ix: ix.set_max_candidates(1)) < 0.6     # :37-46
+    assert recall_of(lambda ix: ix.set_allow_removals(False)) > 0.85  # :49-58
+    assert recall_of(lambda ix: ix.set_collection_size(100)) > 0.85   # recall_test.py:37-46
+
+    def seeded():
+        ix = hnswindex.Index(DIM)
+        ix.set_random_seed(1337)
+        ids = [ix.add([v])[0] for v in vectors[:600]]
+        return float((np.array(ids) == ix.knn_query(vectors[:600], 1)[0][:, 0]).sum())
+    assert seeded() == seeded()                                      # parameters_test.py:60-81
+
+
+def test_metric_values_like_reference_python_tests(hnswindex):
+    # bindings/__tests__/metric_test.py: distance to the 2nd neighbour equals float64 numpy within 1e-5
+    rng = np.random.default_rng(3)
+    vectors = rng.random((100, 128))
+    for metric in ("sq_euclid", "cosine", "ucosine"):
+        v = vectors / np.linalg.norm(vectors, axis=1, keepdims=True) if metric == "ucosine" else vectors
+        ix = hnswindex.Index(128, metric=metric)
+        ids = ix.add(v)
+        res_ids, dists = ix.knn_query(v, k=2)
+        lookup = {int(i): v[j] for j, i in enumerate(ids)}
+        for i in range(100):
+            x, y = v[i], lookup[int(res_ids[i, 1])]
+            if metric == "sq_euclid":
+                want = float(np.dot(x - y, x - y))
+            else:
+                want = 1.0 - float(np.dot(x, y) / (np.linalg.norm(x) * np.linalg.norm(y)))
+            assert abs(dists[i, 1] - want) <= 1e-5
+
+
+def test_gpu_built_graph_recall_parity_sift_like(hnswindex, oracle, tmp_path):
+    # north_star: recall@k of the GPU-built graph no more than 0.5 pt below the reference-built one
+    n = 20000
+    data = sift_like(n)
+    queries = sift_like(500, seed=4321)
+    ref = oracle.OracleIndex("sq_euclid", max_candidates=200, allow_removals=False, collection_size=n)
+    ref.add(data)
+    gpu = hnswindex.Index(128, "sq_euclid")
+    gpu.set_max_candidates(200); gpu.set_allow_removals(False); gpu.set_collection_size(n)
+    ids = gpu.add(data)
+    assert np.array_equal(ids, np.arange(n))
+    gt, _ = gpu.exact_knn(queries, 10)
+    gt_o, _ = ref.exact_knn(queries, 10)
+    assert np.array_equal(gt, gt_o)
+
+    def recall(found):
+        return float(np.mean([len(set(found[i]) & set(gt[i])) / 10 for i in range(len(gt))]))
+    for ef in (20, 40, 80):
+        ref.set_min_nn(ef); gpu.set_min_nn(ef)
+        r_ref = recall(ref.knn_query(queries, 10, threads=8)[0])
+        r_gpu = recall(gpu.knn_query(queries, 10)[0])
+        assert r_gpu >= r_ref - 0.005, (ef, r_ref, r_gpu)
+    # and the oracle searching the GPU-built graph agrees with the GPU searching it
+    p = tmp_path / "gpu_built.hnsw"
+    gpu.serialize(p, packed=True)
+    ref2 = oracle.OracleIndex.deserialize("sq_euclid", p)
+    ref2.set_min_nn(80)
+    o = ref2.knn_query(queries, 10, threads=8)
+    g = gpu.knn_query(queries, 10)
+    _assert_identical(g[0], g[1], o[0], o[1])
