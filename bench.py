@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""
+bench.py -- QPS at recall@10 >= 0.95 on 1M x 128 sq_euclid (BASELINE.json metric, config C2).
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A "step" is one pass of the hot path (BatchKnnQuery) over one 10k-query batch.
+  value       whole-job QPS, queries and outputs resident in HBM, CUDA events on the launching stream
+  e2e         the same through the reference-facing C-ABI call hnsw_knn_query with pinned HOST buffers
+              (H2D of the queries and D2H of ids+dists inside the timed region)
+  roofline    HBM gather roofline of the search kernel: algorithmic bytes (oracle-counted distance
+              evaluations x dim x 4 + adjacency words x 4) / CUDA-event kernel time / measured HBM peak
+  cpu_baseline the oracle (C++ restatement of the reference, Parallel.For stand-in on all host cores) on the
+              same graph and queries, bounded sample
+Multi-GPU: one process per GPU (torchrun), graph replicated, each rank searches its own 10k-query batches,
+no data-path collective (SURVEY.md 8e mode 1) -> weak scaling; time = max over ranks.
+"""
+import argparse
+import ctypes as ct
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "hnswindex.net_b200"))
+
+EF_GRID = [10, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096]
+DIM, RANK, K = 128, 16, 10
+M, EFC = 16, 200
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_data(n, nq_total, seed_data=1234, seed_q=4321):
+    """SIFT-shaped x = zA + 0.25 eps, z~N(0,I16); queries from the same distribution, held out."""
+    rng = np.random.default_rng(seed_data)
+    A = rng.standard_normal((RANK, DIM)).astype(np.float32)
+    data = np.empty((n, DIM), dtype=np.float32)
+    for s in range(0, n, 131072):
+        e = min(n, s + 131072)
+        z = rng.standard_normal((e - s, RANK)).astype(np.float32)
+        data[s:e] = z @ A + 0.25 * rng.standard_normal((e - s, DIM)).astype(np.float32)
+    rq = np.random.default_rng(seed_q)
+    q = (rq.standard_normal((nq_total, RANK)).astype(np.float32) @ A + 0.25 * rq.standard_normal((nq_total, DIM)).astype(np.float32))
+    return data, np.ascontiguousarray(q.astype(np.float32))
+
+
+def recall_at_k(found, truth):
+    return float(np.mean([len(set(found[i]) & set(truth[i])) / truth.shape[1] for i in range(len(truth))]))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def pick_ef(search, truth, grid=EF_GRID, target=0.95):
+    for ef in grid:
+        r = recall_at_k(search(ef), truth)
+        log(f"  ef={ef}: recall@10={r:.4f}")
+        if r >= target:
+            return ef, r
+    return grid[-1], r
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import hnswindex
+    from hnswindex import bindings as hb
+    hb.set_device(local)
+
+    n, nq, nb = args.n, args.nq, args.query_batches
+    data, queries = make_data(n, nq * nb, seed_q=4321 + 1000 * rank)
+    snap = Path(args.snapshot_dir) / f"bench_c2_{n}.hnsw"
+
+    # ---- setup (untimed): build once on rank 0, replicate through the serialized snapshot
+    t0 = time.time()
+    build_info = {}
+    if rank == 0:
+        ix = hnswindex.Index(DIM, "sq_euclid")
+        ix.set_collection_size(n); ix.set_max_edges(M); ix.set_max_candidates(EFC); ix.set_allow_removals(False)
+        tb = time.time()
+        ix.add(data)
+        build_s = time.time() - tb
+        build_info = {"inserts_per_s": round(n / build_s), "build_s": round(build_s, 3), "build_kernel_ms": round(ix.stats()["last_build_ms"], 1)}
+        log(f"[bench] GPU build: {n} inserts in {build_s:.2f}s ({n / build_s:.0f}/s)")
+        if world > 1 or not args.no_cpu_baseline:
+            ts = time.time(); ix.serialize(snap, packed=True); log(f"[bench] serialize {time.time() - ts:.1f}s")
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            ix = hnswindex.Index.deserialize("sq_euclid", snap)
+    del data
+
+    # ---- ef = smallest grid value with recall@10 >= 0.95 (GPU search == oracle search on the same graph: tests/)
+    ns = min(2000, nq)
+    truth, _ = ix.exact_knn(queries[:ns], K)
+
+    def search_ef(ef):
+        ix.set_min_nn(ef)
+        return ix.knn_query(queries[:ns], K)[0]
+    if rank == 0:
+        ef, rec = pick_ef(search_ef, truth)
+        sel = torch.tensor([ef], dtype=torch.int32, device="cuda")
+    else:
+        sel = torch.zeros(1, dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.broadcast(sel, 0)
+    ef = int(sel.item())
+    ix.set_min_nn(ef)
+    recall = recall_at_k(ix.knn_query(queries[:ns], K)[0], truth)
+    log(f"[bench] rank {rank}: ef={ef} recall@10={recall:.4f} setup {time.time() - t0:.1f}s")
+
+    # ---- device-resident buffers, engine runs on torch's current stream so torch events bracket it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ix.set_stream(stream.cuda_stream)
+    q_dev = [torch.from_numpy(queries[b * nq:(b + 1) * nq]).cuda() for b in range(nb)]
+    ids_dev = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+    d_dev = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+    # pinned host buffers for the end-to-end (C-ABI, host pointers) path
+    q_pin = [torch.from_numpy(queries[b * nq:(b + 1) * nq]).pin_memory() for b in range(nb)]
+    ids_pin = torch.empty((nq, K), dtype=torch.int32).pin_memory()
+    d_pin = torch.empty((nq, K), dtype=torch.float32).pin_memory()
+    f32p, i32p = ct.POINTER(ct.c_float), ct.POINTER(ct.c_int)
+
+    def step_resident(i):
+        ix.knn_query_device(q_dev[i % nb].data_ptr(), nq, K, ids_dev.data_ptr(), d_dev.data_ptr())
+
+    def step_e2e(i):
+        rc = hnswindex.lib.hnsw_knn_query(ix._h, ct.cast(q_pin[i % nb].data_ptr(), f32p), nq, DIM, K, ct.cast(ids_pin.data_ptr(), i32p),
+                                          ct.cast(d_pin.data_ptr(), f32p))
+        assert rc == 0, hnswindex.last_error()
+
+    def timed(step_fn, steps, warmup, collect_kernel_ms=False):
+        for i in range(warmup):
+            step_fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = []
+        t_wall = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            step_fn(warmup + i)
+            if collect_kernel_ms:
+                kms.append(ix.stats()["last_search_ms"])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t_wall
+        if world > 1:
+            dist.barrier()
+        dev_ms = e0.elapsed_time(e1)
+        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item()), kms
+
+    sampler = ClockSampler(local)
+    launches0 = ix.stats()["search_launches"]
+    if rank == 0:
+        sampler.start()
+    dev_ms, wall_ms, kms = timed(step_resident, args.steps, args.warmup, collect_kernel_ms=True)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ix.stats()["search_launches"] - launches0 - args.warmup
+    e2e_dev_ms, e2e_wall_ms, _ = timed(step_e2e, args.steps, args.warmup)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    total_q = world * nq * args.steps
+    value = total_q / (dev_ms / 1e3)
+    e2e_value = total_q / (e2e_wall_ms / 1e3)   # the host call returns after the D2H: wall clock is the honest end-to-end time
+    kernel_ms = float(np.mean(kms))
+
+    # ---- oracle on the same graph: algorithmic bytes for the roofline + CPU baseline (bounded sample)
+    roof = {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None}
+    cpu = None
+    peak, peak_src = measured_peak()
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        ts = time.time()
+        ref = O.OracleIndex.deserialize("sq_euclid", snap)
+        ref.set_min_nn(ef)
+        log(f"[bench] oracle loaded the GPU-built snapshot in {time.time() - ts:.1f}s")
+        cores = os.cpu_count() or 1
+        o_ids, o_d, cnt = ref.knn_query(queries[:nq], K, threads=cores, counters=True)
+        ix.set_stream(0)
+        g_ids, g_d = ix.knn_query(queries[:nq], K)
+        same = float((g_ids == o_ids).all(axis=1).mean())
+        bytes_vec = int(cnt[0]) * DIM * 4
+        bytes_adj = int(cnt[2]) * 4
+        alg = bytes_vec + bytes_adj            # per launch (one 10k batch; batches are i.i.d.)
+        ach = alg / (kernel_ms / 1e3) / 1e9
+        roof.update({"achieved": round(ach, 1), "peak": peak, "frac": round(ach / peak, 4), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "gathered_vector_GBps": round(bytes_vec / (kernel_ms / 1e3) / 1e9, 1),
+                     "ndist_per_query": round(int(cnt[0]) / nq, 1), "nexp_per_query": round(int(cnt[1]) / nq, 1),
+                     "kernel": "knn_search_kernel<SQ_EUCLID>", "kernel_ms_avg": round(kernel_ms, 4)})
+        prof = ROOT / "profiles" / "search_kernel_traffic.json"
+        if prof.exists():
+            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        # CPU baseline: repeat the 10k batch until ~10 s of work (max 5 passes)
+        t_cpu, passes = 0.0, 0
+        while t_cpu < 10.0 and passes < 5:
+            tc = time.perf_counter(); ref.knn_query(queries[:nq], K, threads=cores); t_cpu += time.perf_counter() - tc; passes += 1
+        cpu = {"value": round(nq * passes / t_cpu, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{passes} x {nq} queries of batch 0 on the same GPU-built 1M graph, ef={ef}, all host threads "
+                         f"(C++ restatement of the reference's Parallel.For BatchKnnQuery, not the .NET runtime)",
+               "id_lists_identical_to_gpu": round(same, 5)}
+        del ref
+    try:
+        snap.unlink()
+    except OSError:
+        pass
+
+    line = {
+        "metric": "QPS at recall@10>=0.95, 1M x 128 sq_euclid", "value": round(value, 1), "unit": "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: {n} x {DIM} fp32 sq_euclid SIFT-shaped (rank-16 + 0.25 noise), M={M}, efConstruction={EFC}, "
+                               f"{nq}-query batch per GPU per step, k={K}, MinNN(ef)={ef} = smallest grid value with recall@10>=0.95",
+                   "recall_at_10": round(recall, 4), "ef": ef, "index_nodes": n, "queries_per_step_per_gpu": nq,
+                   "parallelism": f"graph replicated x{world}, query batches sharded, no collective",
+                   "l2_policy": f"inputs larger than L2: {n * (DIM * 4 + 2 * M * 4) / 1e6:.0f} MB graph vs 126 MB L2, "
+                                f"{nb} distinct query batches rotated", "graph_built_by": "GPU engine (hnsw_add)", **build_info},
+        "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8,
+                "ms_per_step": round(e2e_wall_ms / args.steps, 4), "api": "hnsw_knn_query (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "wall_ms_per_step": round(wall_ms / args.steps, 4),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU path (oracle port: C++ restatement, all host threads).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n, nq = args.n, args.nq
+    data, queries = make_data(n, nq)
+    t0 = time.time()
+    ref = O.OracleIndex("sq_euclid", max_edges=M, max_candidates=EFC, collection_size=n, allow_removals=False)
+    # probe the insert rate, then decide who builds the (untimed) graph
+    probe = min(n, 20000)
+    ref.add(data[:probe], threads=cores)
+    rate = probe / (time.time() - t0)
+    built_by = "oracle (threaded Add on all host cores)"
+    if n > probe and (n - probe) / max(rate * 0.6, 1.0) > args.reference_build_budget_s:
+        # too slow on this host: the graph (setup, untimed) comes from the GPU engine's snapshot instead
+        log(f"[bench-ref] oracle insert rate {rate:.0f}/s: building {n} on CPU would exceed the budget; using the GPU engine for SETUP only")
+        del ref
+        import __graft_entry__ as ge
+        ge.build()
+        import hnswindex
+        ix = hnswindex.Index(DIM, "sq_euclid")
+        ix.set_collection_size(n); ix.set_max_edges(M); ix.set_max_candidates(EFC); ix.set_allow_removals(False)
+        ix.add(data)
+        snap = Path(args.snapshot_dir) / f"bench_ref_{n}.hnsw"
+        ix.serialize(snap, packed=True)
+        del ix
+        ref = O.OracleIndex.deserialize("sq_euclid", snap)
+        snap.unlink()
+        built_by = "GPU engine snapshot (setup only; timed path is the oracle)"
+    elif n > probe:
+        ref.add(data[probe:], threads=cores)
+    log(f"[bench-ref] graph ready in {time.time() - t0:.1f}s ({built_by})")
+    ns = min(1000, nq)
+    truth, _ = ref.exact_knn(queries[:ns], K, threads=cores)
+    # (threaded Add hands out ids in completion order; exact_knn ran on the index's own ids, so they agree)
+
+    def search_ef(ef):
+        ref.set_min_nn(ef)
+        return ref.knn_query(queries[:ns], K, threads=cores)[0]
+    ef, rec = pick_ef(search_ef, truth)
+    ref.set_min_nn(ef)
+    sample = min(nq, args.reference_sample)
+    for _ in range(args.warmup):
+        ref.knn_query(queries[:sample], K, threads=cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        ref.knn_query(queries[:sample], K, threads=cores)
+    el = time.perf_counter() - t
+    value = sample * args.steps / el
+    line = {
+        "impl": "reference",
+        "metric": "QPS at recall@10>=0.95, 1M x 128 sq_euclid", "value": round(value, 1), "unit": "queries/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: {n} x {DIM} fp32 sq_euclid SIFT-shaped (rank-16 + 0.25 noise), M={M}, efConstruction={EFC}, "
+                               f"k={K}, MinNN(ef)={ef} = smallest grid value with recall@10>=0.95; each step = {sample} queries",
+                   "recall_at_10": round(rec, 4), "ef": ef, "index_nodes": n, "graph_built_by": built_by},
+        "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} queries per step on the {n}-node graph; C++ restatement of the reference "
+                                   f"(the .NET runtime is not available), Parallel.For stand-in on all host threads"},
+        "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="index size (C2 = 1M)")
+    ap.add_argument("--nq", type=int, default=10_000, help="queries per step per GPU (C2 = 10k)")
+    ap.add_argument("--query-batches", type=int, default=4, help="distinct query batches rotated across steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--snapshot-dir", default="/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+    ap.add_argument("--reference-sample", type=int, default=10_000)
+    ap.add_argument("--reference-build-budget-s", type=float, default=150.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

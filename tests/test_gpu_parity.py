@@ -41,16 +41,24 @@ def _oracle_graph(oracle, tmp_path, metric, data, name, **kw):
     return ix, path
 
 
-def _assert_identical(g_ids, g_d, o_ids, o_d, min_same=0.995):
+def _assert_identical(g_ids, g_d, o_ids, o_d, min_same=0.995, explain=None):
+    """id lists identical for >= min_same of the queries; every other row must be explained by exact
+    fp32 distance ties: the distance lists are still the same bits, and (when `explain` = (oracle
+    module, metric, data, queries) is given) each id the GPU returned instead really lies at the
+    distance it reports, i.e. it is an equally valid answer under the tie."""
     same_rows = (g_ids == o_ids).all(axis=1)
     assert same_rows.mean() >= min_same, f"identical id lists: {same_rows.mean():.4f}"
-    # where ids agree the distances must be the same bits (K1 is bit-exact), NaN padding included
-    a, b = g_d[same_rows].view(np.uint32), o_d[same_rows].view(np.uint32)
-    nan = np.isnan(g_d[same_rows]) & np.isnan(o_d[same_rows])
-    assert np.array_equal(a[~nan], b[~nan])
-    # rows that differ may only differ through exact fp32 ties: the distance lists still agree
-    if (~same_rows).any():
-        assert np.allclose(g_d[~same_rows], o_d[~same_rows], rtol=1e-5, atol=0, equal_nan=True)
+    nan = np.isnan(g_d) & np.isnan(o_d)
+    assert np.array_equal(np.isnan(g_d), np.isnan(o_d))
+    assert np.array_equal(g_d.view(np.uint32)[~nan], o_d.view(np.uint32)[~nan]), "distances are not bit-identical"
+    if explain is not None and (~same_rows).any():
+        O, metric, data, queries = explain
+        for i in np.nonzero(~same_rows)[0]:
+            for j in np.nonzero(g_ids[i] != o_ids[i])[0]:
+                d = np.float32(O.metric(metric, data[g_ids[i, j]], queries[i]))
+                assert d.view(np.uint32) == g_d[i, j].view(np.uint32), "mismatch not explained by a distance tie"
+                ties = (g_d[i] == g_d[i, j]).sum() + (o_ids[i, j] not in g_ids[i])
+                assert ties >= 2, "mismatch not explained by a distance tie"
 
 
 # ---------------------------------------------------------------------------------------- search
@@ -75,7 +83,11 @@ def test_knn_query_matches_oracle_on_same_graph(hnswindex, oracle, tmp_path, met
         gpu.set_min_nn(min_nn)
         o_ids, o_d = ref.knn_query(queries, k, threads=8)
         g_ids, g_d = gpu.knn_query(queries, k)
-        _assert_identical(g_ids, g_d, o_ids, o_d)
+        # unit-cosine distances of normalised data are 1 - dot with dot in [0.5, 1): multiples of 2^-24,
+        # so exact ties are frequent at k = 100; they are verified to be ties, not counted as parity.
+        # the same holds for cosine of all-positive 960-d data (distances concentrate in a ~0.02 wide band).
+        tie_prone = metric != "sq_euclid" and max(k, min_nn) >= 100
+        _assert_identical(g_ids, g_d, o_ids, o_d, min_same=0.95 if tie_prone else 0.995, explain=(oracle, metric, data, queries))
 
 
 def test_self_queries_readme_config(hnswindex, oracle, tmp_path):
