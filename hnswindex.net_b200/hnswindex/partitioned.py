@@ -1,0 +1,114 @@
+"""
+Partitioned index (mode 2): for graphs that exceed one GPU the data set is cut into
+`world` contiguous id ranges, every rank (one process per GPU) builds / loads an independent
+sub-HNSW over its range, all ranks see all queries, and the per-rank top-k lists are exchanged with
+ONE all-gather (NCCL over NVLink on GPUs) and merged by `merge_keys_kernel` (K7).
+
+The reference has no distributed mode; parity for this mode is defined against the oracle running the
+same sub-graphs + the same merge, and against brute force for recall (tests/test_partitioned_cpu.py,
+tests/test_gpu_multi.py).
+
+The host logic (range split, global ids, gather layout, merge order) is independent of the device
+and is exercised on CPU with the gloo backend; `local_search` is pluggable for that purpose.
+"""
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced id range [start, end) owned by `rank` (first n % world ranks get one more)."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def _ordered(d: np.ndarray) -> np.ndarray:
+    """Order-preserving uint32 image of fp32 (the kernels' key order: negative cosine distances sort first)."""
+    b = np.ascontiguousarray(d, dtype=np.float32).view(np.uint32)
+    return np.where(b >> 31 != 0, ~b, b | np.uint32(0x80000000)).astype(np.uint64)
+
+
+def merge_topk_numpy(ids: np.ndarray, dists: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """CPU statement of merge_keys_kernel: ids/dists [parts, q, k'] -> [q, k], ascending by (distance, id),
+    entries with id < 0 are padding and sort last; output padded with -1 / NaN."""
+    parts, q, kk = ids.shape
+    flat_ids = np.transpose(ids, (1, 0, 2)).reshape(q, parts * kk).astype(np.int64)
+    flat_d = np.transpose(dists, (1, 0, 2)).reshape(q, parts * kk).astype(np.float32)
+    key = (_ordered(flat_d) << np.uint64(32)) | (flat_ids.astype(np.uint64) & np.uint64(0x7FFFFFFF)) << np.uint64(1)
+    key = np.where(flat_ids < 0, np.uint64(0xFFFFFFFFFFFFFFFF), key)
+    order = np.argsort(key, axis=1, kind="stable")[:, :k]
+    out_ids = np.take_along_axis(flat_ids, order, axis=1).astype(np.int32)
+    out_d = np.take_along_axis(flat_d, order, axis=1)
+    pad = out_ids < 0
+    out_ids[pad] = -1
+    out_d[pad] = np.nan
+    if out_ids.shape[1] < k:
+        extra = k - out_ids.shape[1]
+        out_ids = np.concatenate([out_ids, np.full((q, extra), -1, np.int32)], axis=1)
+        out_d = np.concatenate([out_d, np.full((q, extra), np.nan, np.float32)], axis=1)
+    return out_ids, out_d
+
+
+class PartitionedIndex:
+    """One rank's view of a partitioned index.
+
+    local_search(queries[nq, dim] float32, k) -> (local_ids[nq, k] int32, dists[nq, k] float32) searches this rank's
+    sub-graph; ids are local slots (0-based inside the shard).  On a GPU rank pass an `hnswindex.Index`
+    as `index` instead and the search, the id offset and the merge all stay on the device.
+    """
+
+    def __init__(self, rank: int, world: int, total: int, index=None, local_search: Optional[Callable] = None, group=None):
+        if (index is None) == (local_search is None):
+            raise ValueError("give exactly one of index / local_search")
+        self.rank, self.world, self.total = rank, world, total
+        self.start, self.end = shard_range(total, rank, world)
+        self.index, self.local_search, self.group = index, local_search, group
+
+    # ---- device-independent pieces ------------------------------------------------------------
+    def to_global(self, local_ids: np.ndarray) -> np.ndarray:
+        return np.where(local_ids >= 0, local_ids + self.start, -1).astype(np.int32)
+
+    def _gather(self, ids_t, d_t):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return ids_t.unsqueeze(0), d_t.unsqueeze(0)
+        all_ids = [torch.empty_like(ids_t) for _ in range(self.world)]
+        all_d = [torch.empty_like(d_t) for _ in range(self.world)]
+        dist.all_gather(all_ids, ids_t, group=self.group)
+        dist.all_gather(all_d, d_t, group=self.group)
+        return torch.stack(all_ids), torch.stack(all_d)
+
+    # ---- query -----------------------------------------------------------------------------------
+    def knn_query(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Every rank passes the SAME queries; every rank returns the same merged global top-k."""
+        import torch
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if self.index is not None and torch.cuda.is_available():
+            return self._knn_query_cuda(q, k)
+        ids, d = self.local_search(q, k)
+        ids_t = torch.from_numpy(self.to_global(np.asarray(ids)))
+        d_t = torch.from_numpy(np.ascontiguousarray(d, dtype=np.float32))
+        g_ids, g_d = self._gather(ids_t, d_t)
+        return merge_topk_numpy(g_ids.numpy(), g_d.numpy(), k)
+
+    def _knn_query_cuda(self, q: np.ndarray, k: int):
+        import ctypes as ct
+        import torch
+        from . import bindings as hb
+        nq = q.shape[0]
+        q_dev = torch.from_numpy(q).cuda()
+        ids_dev = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+        d_dev = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        self.index.knn_query_device(q_dev.data_ptr(), nq, k, ids_dev.data_ptr(), d_dev.data_ptr())
+        ids_dev = torch.where(ids_dev >= 0, ids_dev + self.start, ids_dev)
+        g_ids, g_d = self._gather(ids_dev.contiguous(), d_dev)
+        out_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+        out_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        rc = hb.lib.hnsw_merge_topk_device(ct.c_void_p(g_ids.contiguous().data_ptr()), ct.c_void_p(g_d.contiguous().data_ptr()), self.world, nq, k,
+                                           ct.c_void_p(out_ids.data_ptr()), ct.c_void_p(out_d.data_ptr()), None)
+        if rc < 0:
+            raise RuntimeError(hb.last_error())
+        return out_ids.cpu().numpy(), out_d.cpu().numpy()
