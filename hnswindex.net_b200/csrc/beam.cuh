@@ -23,12 +23,12 @@
 #pragma once
 #include "common.cuh"
 #include "metric.cuh"
+#include "stage.cuh"
 
 namespace hnsw {
 
-constexpr int kUnroll = 8;  // float4 loads in flight per lane in the distance loop
-
 struct WarpScratch {
+    Stager stg;        // staged neighbour rows + mbarrier (stage.cuh)
     float* q;          // [pitch] query / inserted vector (16 B aligned)
     u64* list;         // [cap] sorted candidate keys
     uint32_t* vis;     // [vis_size] recently visited ids (+1), 2-way buckets
@@ -44,15 +44,18 @@ struct WarpCounters {
 };
 
 __host__ __device__ inline size_t warp_scratch_bytes(int pitch, int cap, int vis_size, int cand_cap) {
-    size_t b = 0;
+    size_t b = kStageBytes;
     b += (size_t)((pitch + 3) & ~3) * 4;
     b += (size_t)cap * 8;
     b += (size_t)vis_size * 4;
     b += (size_t)cand_cap * 8;
-    return (b + 15) & ~(size_t)15;
+    return (b + 127) & ~(size_t)127;
 }
-__device__ __forceinline__ WarpScratch carve_scratch(unsigned char* base, int pitch, int cap, int vis_size, int cand_cap) {
+// Called once per warp at kernel start (initialises the warp's mbarrier).
+__device__ __forceinline__ WarpScratch carve_scratch(unsigned char* base, int pitch, int cap, int vis_size, int cand_cap, int lane) {
     WarpScratch s;
+    stager_init(s.stg, base, lane);
+    base += kStageBytes;
     s.q = reinterpret_cast<float*>(base);
     base += (size_t)((pitch + 3) & ~3) * 4;
     s.list = reinterpret_cast<u64*>(base);
@@ -78,32 +81,51 @@ __device__ __forceinline__ const int* row_ptr(const GraphView& g, int id, int la
 }
 
 // ----------------------------------------------------------------------------
-// distances of cand_id[0..m) to the vector in s.q -> cand_dist[0..m)
-// (16 vectors per pass, one lane pair each)
+// distances of ids[0..m) to the vector q (shared memory) -> out[0..m): 16 rows per pass, staged in
+// shared memory by TMA bulk copies (stage.cuh), one lane pair per row (metric.cuh)
 // ----------------------------------------------------------------------------
 template <int METRIC>
-__device__ __forceinline__ void batch_dist_to(const GraphView& g, const float* q, double q_norm_sqrt, const int* ids, float* out, int m,
-                                              int lane) {
+__device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, const int* ids, float* out,
+                                              int m, int lane) {
+    constexpr bool SQ = METRIC == SQ_EUCLID;
     const int h = lane & 1, grp = lane >> 1;
-    for (int base = 0; base < m; base += 16) {
-        const int j = base + grp;
-        const bool active = j < m;
-        const int id = active ? ids[j] : 0;
+    const int nfull = g.dim >> 3;                 // complete 8-element chunks
+    const int ntail = g.dim - (nfull << 3);       // scalar remainder
+    for (int base = 0; base < m; base += kStageRows) {
+        const int nrows = min(kStageRows, m - base);
+        const bool active = grp < nrows;
+        const int copy_id = lane < nrows ? ids[base + lane] : 0;  // lane r stages row r
+        const int id = active ? ids[base + grp] : 0;              // pair grp evaluates row grp
         double an = 0.0;
         if (METRIC == COSINE && active) an = __ldg(g.norm_sqrt + id);
-        const float* vec = g.vectors + (size_t)id * g.pitch;
-        const float d = pair_distance<METRIC, kUnroll>(vec, q, g.dim, h, active, an, q_norm_sqrt);
-        if (active && h == 0) out[j] = d;
+        PairAcc acc = {0.f, 0.f, 0.f, 0.f};
+        float r = 0.f;
+        for (int f0 = 0; f0 < g.pitch; f0 += kSegFloats) {
+            const int nfl = min(kSegFloats, g.pitch - f0);  // floats of this segment, multiple of 4
+            if (lane == 0) stage_expect(stg, (uint32_t)(nrows * nfl * 4));
+            __syncwarp();
+            if (lane < nrows) stage_copy(stg, stg.buf + lane * kSegPitch, g.vectors + (size_t)copy_id * g.pitch + f0, (uint32_t)(nfl * 4));
+            stage_wait(stg);
+            const float* row = stg.buf + grp * kSegPitch;
+            const int nch = min(nfull - (f0 >> 3), kSegFloats >> 3);
+            if (active && nch > 0) pair_accumulate<SQ>(acc, row, q + f0, nch, h);
+            if (f0 + kSegFloats >= g.pitch) {  // last segment: it also holds the scalar remainder
+                r = pair_hsum<SQ>(acc);
+                if (active && ntail > 0) r = pair_tail<SQ>(r, row + ((nfull << 3) - f0), q + (nfull << 3), ntail);
+            }
+            __syncwarp();  // all lanes are done with the staged rows before the next copies overwrite them
+        }
+        if (active && h == 0) out[base + grp] = metric_finish<METRIC>(r, an, q_norm_sqrt);
     }
     __syncwarp();
 }
 template <int METRIC>
-__device__ __forceinline__ void batch_dist(const GraphView& g, const WarpScratch& s, double q_norm_sqrt, int m, int lane) {
-    batch_dist_to<METRIC>(g, s.q, q_norm_sqrt, s.cand_id, s.cand_dist, m, lane);
+__device__ __forceinline__ void batch_dist(const GraphView& g, WarpScratch& s, double q_norm_sqrt, int m, int lane) {
+    batch_dist_to<METRIC>(g, s.stg, s.q, q_norm_sqrt, s.cand_id, s.cand_dist, m, lane);
 }
 
 template <int METRIC>
-__device__ __forceinline__ float single_dist(const GraphView& g, const WarpScratch& s, double q_norm_sqrt, int id, int lane) {
+__device__ __forceinline__ float single_dist(const GraphView& g, WarpScratch& s, double q_norm_sqrt, int id, int lane) {
     __syncwarp();
     if (lane == 0) s.cand_id[0] = id;
     __syncwarp();
@@ -189,7 +211,7 @@ __device__ __forceinline__ bool vis_test_and_set(const WarpScratch& s, int id) {
 // occurrence on ties), repeat until a scan brings no improvement.
 // ----------------------------------------------------------------------------
 template <int METRIC>
-__device__ __forceinline__ void greedy_layer(const GraphView& g, const WarpScratch& s, double qn, int layer, int& cur, float& cur_d,
+__device__ __forceinline__ void greedy_layer(const GraphView& g, WarpScratch& s, double qn, int layer, int& cur, float& cur_d,
                                              int lane, WarpCounters& wc) {
     bool changed = true;
     while (changed) {
@@ -237,7 +259,7 @@ __device__ __forceinline__ void greedy_layer(const GraphView& g, const WarpScrat
 // s.list[0..st.n) holds the result sorted ascending by (distance, id).
 // ----------------------------------------------------------------------------
 template <int METRIC>
-__device__ __forceinline__ void beam_search(const GraphView& g, const WarpScratch& s, double qn, int layer, int entry, float entry_d,
+__device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, double qn, int layer, int entry, float entry_d,
                                             int ef, BeamState& st, int lane, WarpCounters& wc) {
     st.n = 0;
     st.ef = ef;

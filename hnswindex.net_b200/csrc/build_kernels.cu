@@ -28,11 +28,11 @@ struct BuildScratch {
 };
 
 __host__ __device__ inline size_t build_scratch_bytes(int pitch, int cap, int vis_size, int cand_cap, int sel_cap) {
-    return warp_scratch_bytes(pitch, cap, vis_size, cand_cap) + (size_t)((pitch + 3) & ~3) * 4 + (((size_t)sel_cap * 4 + 15) & ~(size_t)15);
+    return warp_scratch_bytes(pitch, cap, vis_size, cand_cap) + (((size_t)((pitch + 3) & ~3) * 4 + (size_t)sel_cap * 4 + 127) & ~(size_t)127);
 }
-__device__ __forceinline__ BuildScratch carve_build(unsigned char* base, int pitch, int cap, int vis_size, int cand_cap, int sel_cap) {
+__device__ __forceinline__ BuildScratch carve_build(unsigned char* base, int pitch, int cap, int vis_size, int cand_cap, int sel_cap, int lane) {
     BuildScratch b;
-    b.s = carve_scratch(base, pitch, cap, vis_size, cand_cap);
+    b.s = carve_scratch(base, pitch, cap, vis_size, cand_cap, lane);
     base += warp_scratch_bytes(pitch, cap, vis_size, cand_cap);
     b.cvec = reinterpret_cast<float*>(base);
     base += (size_t)((pitch + 3) & ~3) * 4;
@@ -50,7 +50,7 @@ __device__ __forceinline__ void load_vector(const GraphView& g, int id, float* d
 // Heuristic.cs:11-46 on the sorted list[0..n): returns the number selected (ids in b.sel, ascending
 // by distance).  Caller handles the n < maxE early-return case.
 template <int METRIC>
-__device__ __forceinline__ int select_neighbors(const GraphView& g, const BuildScratch& b, const u64* list, int n, int maxE, int lane,
+__device__ __forceinline__ int select_neighbors(const GraphView& g, BuildScratch& b, const u64* list, int n, int maxE, int lane,
                                                 WarpCounters& wc) {
     int nsel = 0;
     for (int i = 0; i < n && nsel < maxE; ++i) {
@@ -62,7 +62,7 @@ __device__ __forceinline__ int select_neighbors(const GraphView& g, const BuildS
             load_vector(g, c, b.cvec, lane);
             double cn = 0.0;
             if (METRIC == COSINE) cn = __ldg(g.norm_sqrt + c);
-            batch_dist_to<METRIC>(g, b.cvec, cn, b.sel, b.s.cand_dist, nsel, lane);
+            batch_dist_to<METRIC>(g, b.s.stg, b.cvec, cn, b.sel, b.s.cand_dist, nsel, lane);
             wc.ndist += nsel;
             bool rej = false;
             for (int j = lane; j < nsel; j += 32) rej |= b.s.cand_dist[j] < cd;  // strict, Heuristic.cs:34
@@ -91,11 +91,11 @@ template <int METRIC>
 __global__ void __launch_bounds__(kThreads)
 build_select_kernel(GraphView g, const int* __restrict__ levels, int first, int count, int efc, int list_cap, int vis_size, int cand_cap,
                     int sel_cap, unsigned* work_counter) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, vis_size, cand_cap, sel_cap);
-    const BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, vis_size, cand_cap, sel_cap);
-    const WarpScratch& s = b.s;
+    BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, vis_size, cand_cap, sel_cap, lane);
+    WarpScratch& s = b.s;
 
     for (;;) {
         unsigned wi = 0;
@@ -168,11 +168,11 @@ template <int METRIC>
 __global__ void __launch_bounds__(kThreads)
 build_link_kernel(GraphView g, const int* __restrict__ levels, int first, int count, int list_cap, int cand_cap, int sel_cap,
                   unsigned* work_counter, int* error_flag) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, 64, cand_cap, sel_cap);
-    const BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, 64, cand_cap, sel_cap);
-    const WarpScratch& s = b.s;
+    BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, 64, cand_cap, sel_cap, lane);
+    WarpScratch& s = b.s;
 
     for (;;) {
         unsigned wi = 0;

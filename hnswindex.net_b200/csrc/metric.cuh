@@ -8,8 +8,11 @@
 // sum elements 8c+j sequentially in c, then combine lanes with a fixed tree.
 // fp32 addition is not associative, so the same eight sequential chains are
 // kept here: one vector is handled by a PAIR of adjacent lanes; lane h (0/1)
-// owns AVX lanes 4h..4h+3 and reads them as one float4 (16 B, coalesced into
-// a full 32 B sector per pair).  A warp therefore evaluates 16 vectors at once.
+// owns AVX lanes 4h..4h+3 and reads them as one float4.  A warp therefore
+// evaluates 16 vectors at once.  The stored rows are NOT gathered with this
+// layout from global memory (16 different 128 B lines per load instruction
+// cap a B200 at ~1.8 TB/s, profiles/r01_microbench_gather_*.log): whole rows
+// are bulk-copied to shared memory first (stage.cuh) and read from there.
 // Explicit _rn intrinsics forbid FMA contraction / reassociation.
 #pragma once
 #include "common.cuh"
@@ -18,73 +21,60 @@ namespace hnsw {
 
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 
-// One pair computes Sum_lanes over the 8-lane chains; returns the horizontally
-// reduced value (same bits in both lanes of the pair).  `active` false = the pair
-// has no vector this pass (it still takes part in the shuffles).
-//   SQ: L[j] = fma(d, d, L[j]), d = a - b ; tree (s0+s1)+(s2+s3) ; tail r += d*d (mul, add)
-//   DOT: L[j] = L[j] + a*b (mul, add)     ; tree (s0+s2)+(s1+s3) ; tail r += a*b
-template <bool SQ, int U>
-__device__ __forceinline__ float pair_reduce(const float* __restrict__ vec, const float* q, int dim, int h, bool active) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const int nch = dim >> 3;
-    if (active) {
-        const float4* v4 = reinterpret_cast<const float4*>(vec) + h;
-        const float4* q4 = reinterpret_cast<const float4*>(q) + h;
-        int c = 0;
-        for (; c + U <= nch; c += U) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = ldg_f4(v4 + 2 * (c + u));
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float4 b = q4[2 * (c + u)];
-                if (SQ) {
-                    float d;
-                    d = __fsub_rn(v[u].x, b.x); a0 = __fmaf_rn(d, d, a0);
-                    d = __fsub_rn(v[u].y, b.y); a1 = __fmaf_rn(d, d, a1);
-                    d = __fsub_rn(v[u].z, b.z); a2 = __fmaf_rn(d, d, a2);
-                    d = __fsub_rn(v[u].w, b.w); a3 = __fmaf_rn(d, d, a3);
-                } else {
-                    a0 = __fadd_rn(a0, __fmul_rn(v[u].x, b.x));
-                    a1 = __fadd_rn(a1, __fmul_rn(v[u].y, b.y));
-                    a2 = __fadd_rn(a2, __fmul_rn(v[u].z, b.z));
-                    a3 = __fadd_rn(a3, __fmul_rn(v[u].w, b.w));
-                }
-            }
-        }
-        for (; c < nch; ++c) {
-            const float4 a = ldg_f4(v4 + 2 * c);
-            const float4 b = q4[2 * c];
-            if (SQ) {
-                float d;
-                d = __fsub_rn(a.x, b.x); a0 = __fmaf_rn(d, d, a0);
-                d = __fsub_rn(a.y, b.y); a1 = __fmaf_rn(d, d, a1);
-                d = __fsub_rn(a.z, b.z); a2 = __fmaf_rn(d, d, a2);
-                d = __fsub_rn(a.w, b.w); a3 = __fmaf_rn(d, d, a3);
-            } else {
-                a0 = __fadd_rn(a0, __fmul_rn(a.x, b.x));
-                a1 = __fadd_rn(a1, __fmul_rn(a.y, b.y));
-                a2 = __fadd_rn(a2, __fmul_rn(a.z, b.z));
-                a3 = __fadd_rn(a3, __fmul_rn(a.w, b.w));
-            }
+// Lane accumulators of one lane pair: lane h holds L[4h..4h+3].
+struct PairAcc {
+    float a0, a1, a2, a3;
+};
+
+// Accumulate `nch` 8-element chunks of a stored vector against the query, both read from SHARED memory
+// (the stored row was staged there by a bulk copy, see stage.cuh).  Sequential in c, as the AVX loop.
+//   SQ : L[j] = fma(d, d, L[j]), d = a - b       (EuclideanMetric.cs:29-30)
+//   DOT: L[j] = L[j] + a*b   (mul, then add)     (CosineMetric.cs:37-38, 114-115)
+template <bool SQ>
+__device__ __forceinline__ void pair_accumulate(PairAcc& acc, const float* row, const float* q, int nch, int h) {
+    const float4* v4 = reinterpret_cast<const float4*>(row) + h;
+    const float4* q4 = reinterpret_cast<const float4*>(q) + h;
+#pragma unroll 4
+    for (int c = 0; c < nch; ++c) {
+        const float4 a = v4[2 * c];
+        const float4 b = q4[2 * c];
+        if (SQ) {
+            float d;
+            d = __fsub_rn(a.x, b.x); acc.a0 = __fmaf_rn(d, d, acc.a0);
+            d = __fsub_rn(a.y, b.y); acc.a1 = __fmaf_rn(d, d, acc.a1);
+            d = __fsub_rn(a.z, b.z); acc.a2 = __fmaf_rn(d, d, acc.a2);
+            d = __fsub_rn(a.w, b.w); acc.a3 = __fmaf_rn(d, d, acc.a3);
+        } else {
+            acc.a0 = __fadd_rn(acc.a0, __fmul_rn(a.x, b.x));
+            acc.a1 = __fadd_rn(acc.a1, __fmul_rn(a.y, b.y));
+            acc.a2 = __fadd_rn(acc.a2, __fmul_rn(a.z, b.z));
+            acc.a3 = __fadd_rn(acc.a3, __fmul_rn(a.w, b.w));
         }
     }
-    // lower + upper half: s[j] = L[j] + L[j+4] (the partner lane holds the other half)
-    const float s0 = __fadd_rn(a0, __shfl_xor_sync(FULL, a0, 1));
-    const float s1 = __fadd_rn(a1, __shfl_xor_sync(FULL, a1, 1));
-    const float s2 = __fadd_rn(a2, __shfl_xor_sync(FULL, a2, 1));
-    const float s3 = __fadd_rn(a3, __shfl_xor_sync(FULL, a3, 1));
-    float r = SQ ? __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3))   // two hadd
-                 : __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));  // movehl + shuffle(0x55)
-    if (active) {
-        for (int i = nch << 3; i < dim; ++i) {  // scalar remainder, both lanes redundantly
-            const float a = __ldg(vec + i), b = q[i];
-            if (SQ) {
-                const float d = __fsub_rn(a, b);
-                r = __fadd_rn(r, __fmul_rn(d, d));
-            } else {
-                r = __fadd_rn(r, __fmul_rn(a, b));
-            }
+}
+
+// Horizontal reduction (all 32 lanes must call): s[j] = L[j] + L[j+4] with the partner lane, then
+//   SQ : (s0+s1)+(s2+s3)  -- two hadd            (EuclideanMetric.cs:45-49)
+//   DOT: (s0+s2)+(s1+s3)  -- movehl + shuffle    (CosineMetric.cs:145-171)
+template <bool SQ>
+__device__ __forceinline__ float pair_hsum(const PairAcc& acc) {
+    const float s0 = __fadd_rn(acc.a0, __shfl_xor_sync(FULL, acc.a0, 1));
+    const float s1 = __fadd_rn(acc.a1, __shfl_xor_sync(FULL, acc.a1, 1));
+    const float s2 = __fadd_rn(acc.a2, __shfl_xor_sync(FULL, acc.a2, 1));
+    const float s3 = __fadd_rn(acc.a3, __shfl_xor_sync(FULL, acc.a3, 1));
+    return SQ ? __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)) : __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
+}
+
+// Scalar remainder (dim % 8 elements), separate mul and add (EuclideanMetric.cs:53-57, CosineMetric.cs:78-85)
+template <bool SQ>
+__device__ __forceinline__ float pair_tail(float r, const float* row, const float* q, int n) {
+    for (int i = 0; i < n; ++i) {
+        const float a = row[i], b = q[i];
+        if (SQ) {
+            const float d = __fsub_rn(a, b);
+            r = __fadd_rn(r, __fmul_rn(d, d));
+        } else {
+            r = __fadd_rn(r, __fmul_rn(a, b));
         }
     }
     return r;
@@ -97,13 +87,11 @@ __device__ __forceinline__ float cosine_finish(float dot, double sqrt_na, double
     return __fsub_rn(1.0f, __fdiv_rn(dot, denom));
 }
 
-template <int METRIC, int U>
-__device__ __forceinline__ float pair_distance(const float* __restrict__ vec, const float* q, int dim, int h, bool active,
-                                               double sqrt_na, double sqrt_nb) {
-    if (METRIC == SQ_EUCLID) return pair_reduce<true, U>(vec, q, dim, h, active);
-    const float dot = pair_reduce<false, U>(vec, q, dim, h, active);
-    if (METRIC == COSINE) return cosine_finish(dot, sqrt_na, sqrt_nb);
-    return __fsub_rn(1.0f, dot);
+template <int METRIC>
+__device__ __forceinline__ float metric_finish(float r, double sqrt_na, double sqrt_nb) {
+    if (METRIC == SQ_EUCLID) return r;
+    if (METRIC == COSINE) return cosine_finish(r, sqrt_na, sqrt_nb);
+    return __fsub_rn(1.0f, r);  // CosineMetric.cs:141
 }
 
 // Norm accumulator of one vector in the cosine metric's order (A[j] += a*a; cosine tree; tail),

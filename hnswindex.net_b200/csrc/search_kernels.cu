@@ -20,10 +20,10 @@ template <int METRIC>
 __global__ void __launch_bounds__(kThreads)
 knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int vis_size, int cand_cap,
                   int* __restrict__ out_ids, float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis_size, cand_cap);
-    const WarpScratch s = carve_scratch(smem + warp * per_warp, g.pitch, ef, vis_size, cand_cap);
+    WarpScratch s = carve_scratch(smem + warp * per_warp, g.pitch, ef, vis_size, cand_cap, lane);
 
     for (;;) {
         unsigned qi = 0;
