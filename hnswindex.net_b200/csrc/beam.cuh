@@ -39,6 +39,9 @@ struct WarpScratch {
     int cap;           // list capacity (>= ef)
 };
 
+constexpr int kPrefetchRows = 1;  // flags bit 0: L2-prefetch the adjacency rows of accepted candidates
+constexpr int kGuessRow = 2;      // flags bit 1: load the likely next candidate's row while the last pass is inserted
+
 struct WarpCounters {
     unsigned ndist = 0, nexp = 0, row_words = 0;
 };
@@ -82,8 +85,53 @@ __device__ __forceinline__ const int* row_ptr(const GraphView& g, int id, int la
 
 // ----------------------------------------------------------------------------
 // distances of ids[0..m) to the vector q (shared memory) -> out[0..m): 16 rows per pass, staged in
-// shared memory by TMA bulk copies (stage.cuh), one lane pair per row (metric.cuh)
+// shared memory by asynchronous full-row copies (stage.cuh), one lane pair per row (metric.cuh)
 // ----------------------------------------------------------------------------
+// start copying floats [f0, f0+nfl) of rows ids[base .. base+nrows) into the staging buffer (asynchronous)
+__device__ __forceinline__ void stage_issue(const GraphView& g, Stager& stg, const int* ids, int base, int nrows, int f0, int nfl, int lane) {
+#ifdef HNSW_STAGE_BULK
+    const int copy_id = lane < nrows ? ids[base + lane] : 0;  // lane r stages row r
+    if (lane == 0) stage_expect(stg, (uint32_t)(nrows * nfl * 4));
+    __syncwarp();
+    if (lane < nrows) stage_copy(stg, stg.buf + lane * kSegPitch, g.vectors + (size_t)copy_id * g.pitch + f0, (uint32_t)(nfl * 4));
+#else
+    if (lane * 4 < nfl) {
+        const float* src0 = g.vectors + f0 + lane * 4;
+        float* dst0 = stg.buf + lane * 4;
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r) cp_async_16(dst0 + r * kSegPitch, src0 + (size_t)ids[base + r] * g.pitch);
+    }
+#endif
+}
+// wait until the copies started by stage_issue have landed and are visible to the whole warp
+__device__ __forceinline__ void stage_complete(Stager& stg) {
+#ifdef HNSW_STAGE_BULK
+    stage_wait(stg);
+#else
+    cp_async_wait_all();
+    __syncwarp();
+#endif
+}
+
+// rows of at most kSegFloats floats (one segment), already staged: distances of ids[base .. base+nrows) -> out
+template <int METRIC>
+__device__ __forceinline__ void compute_staged(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, const int* ids, float* out,
+                                               int base, int nrows, int lane) {
+    constexpr bool SQ = METRIC == SQ_EUCLID;
+    const int h = lane & 1, grp = lane >> 1;
+    const int nfull = g.dim >> 3, ntail = g.dim - (nfull << 3);
+    const bool active = grp < nrows;
+    double an = 0.0;
+    if (METRIC == COSINE && active) an = __ldg(g.norm_sqrt + ids[base + grp]);
+    PairAcc acc = {0.f, 0.f, 0.f, 0.f};
+    const float* row = stg.buf + grp * kSegPitch;
+    if (active) pair_accumulate<SQ>(acc, row, q, nfull, h);
+    float r = pair_hsum<SQ>(acc);
+    if (active && ntail > 0) r = pair_tail<SQ>(r, row + (nfull << 3), q + (nfull << 3), ntail);
+    if (active && h == 0) out[base + grp] = metric_finish<METRIC>(r, an, q_norm_sqrt);
+    __syncwarp();  // staged rows are free again, distances are visible
+}
+
 template <int METRIC>
 __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, const int* ids, float* out,
                                               int m, int lane) {
@@ -93,19 +141,22 @@ __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, c
     const int ntail = g.dim - (nfull << 3);       // scalar remainder
     for (int base = 0; base < m; base += kStageRows) {
         const int nrows = min(kStageRows, m - base);
+        if (g.pitch <= kSegFloats) {
+            stage_issue(g, stg, ids, base, nrows, 0, g.pitch, lane);
+            stage_complete(stg);
+            compute_staged<METRIC>(g, stg, q, q_norm_sqrt, ids, out, base, nrows, lane);
+            continue;
+        }
+        // long rows: segments of kSegFloats floats, lane accumulators carried across segments
         const bool active = grp < nrows;
-        const int copy_id = lane < nrows ? ids[base + lane] : 0;  // lane r stages row r
-        const int id = active ? ids[base + grp] : 0;              // pair grp evaluates row grp
         double an = 0.0;
-        if (METRIC == COSINE && active) an = __ldg(g.norm_sqrt + id);
+        if (METRIC == COSINE && active) an = __ldg(g.norm_sqrt + ids[base + grp]);
         PairAcc acc = {0.f, 0.f, 0.f, 0.f};
         float r = 0.f;
         for (int f0 = 0; f0 < g.pitch; f0 += kSegFloats) {
             const int nfl = min(kSegFloats, g.pitch - f0);  // floats of this segment, multiple of 4
-            if (lane == 0) stage_expect(stg, (uint32_t)(nrows * nfl * 4));
-            __syncwarp();
-            if (lane < nrows) stage_copy(stg, stg.buf + lane * kSegPitch, g.vectors + (size_t)copy_id * g.pitch + f0, (uint32_t)(nfl * 4));
-            stage_wait(stg);
+            stage_issue(g, stg, ids, base, nrows, f0, nfl, lane);
+            stage_complete(stg);
             const float* row = stg.buf + grp * kSegPitch;
             const int nch = min(nfull - (f0 >> 3), kSegFloats >> 3);
             if (active && nch > 0) pair_accumulate<SQ>(acc, row, q + f0, nch, h);
@@ -169,6 +220,24 @@ __device__ __forceinline__ int list_lower_bound(const u64* list, int n, u64 key,
 // full.  Returns false when the id is already present (duplicate) or falls off the end.
 __device__ __forceinline__ bool list_insert(u64* list, BeamState& st, u64 key, int lane) {
     const int n = st.n;
+    if (n <= 64) {
+        // whole list in two registers per lane: one pass finds the position, detects duplicates and shifts
+        const u64 v0 = lane < n ? list[lane] : ~0ull;
+        const u64 v1 = lane + 32 < n ? list[lane + 32] : ~0ull;
+        const int pos = __popc(__ballot_sync(FULL, v0 < key)) + __popc(__ballot_sync(FULL, v1 < key));
+        const u64 at = __shfl_sync(FULL, pos < 32 ? v0 : v1, pos & 31);  // list[pos], ~0 beyond the end
+        if ((at >> 1) == (key >> 1)) return false;                       // same distance bits + id
+        if (pos >= st.ef) return false;
+        const int last = (n == st.ef) ? n - 1 : n;                       // entries [pos, last) move up by one
+        if (lane >= pos && lane < last) list[lane + 1] = v0;
+        if (lane + 32 >= pos && lane + 32 < last) list[lane + 33] = v1;
+        if (lane == 0) list[pos] = key;
+        __syncwarp();
+        if (n < st.ef) st.n = n + 1;
+        st.far_ord = (st.n == st.ef) ? key_ord(list[st.ef - 1]) : 0xFFFFFFFFu;
+        if (pos < st.cursor) st.cursor = pos;
+        return true;
+    }
     const int pos = list_lower_bound(list, n, key, lane);
     if (pos < n && (list[pos] >> 1) == (key >> 1)) return false;  // same distance bits + id
     if (pos >= st.ef) return false;
@@ -254,13 +323,38 @@ __device__ __forceinline__ void greedy_layer(const GraphView& g, WarpScratch& s,
     }
 }
 
+// Insert candidates [lo, hi) of the current expansion in stored order; a candidate is accepted iff
+// |top| < ef or d < far (strict), re-evaluated after every insertion (GraphNavigator.cs:233-246).
+__device__ __forceinline__ void insert_candidates(const GraphView& g, WarpScratch& s, BeamState& st, int lo, int hi, int layer, int lane, int flags) {
+    for (int jb = lo; jb < hi; jb += 32) {
+        const int j = jb + lane;
+        const bool have = j < hi;
+        const u64 mykey = have ? make_key(s.cand_dist[j], s.cand_id[j]) : ~0ull;
+        bool pending = have;
+        for (;;) {
+            const bool want = pending && (st.n < st.ef || key_ord(mykey) < st.far_ord);
+            const unsigned mk = __ballot_sync(FULL, want);
+            if (!mk) break;
+            const int src = __ffs(mk) - 1;
+            const u64 kn = __shfl_sync(FULL, mykey, src);
+            if (lane == src) pending = false;
+            const bool inserted = list_insert(s.list, st, kn, lane);
+            // optional: pull the adjacency row of an accepted candidate into L2 (measured: no gain at C2)
+            if (inserted && lane == src && layer == 0 && (flags & kPrefetchRows)) {
+                const char* rp = reinterpret_cast<const char*>(g.adj0 + (size_t)key_id(kn) * g.stride0);
+                for (int off = 0; off < g.stride0 * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------
 // Beam search of width ef on one layer (GraphNavigator.cs:194-256).  On return
 // s.list[0..st.n) holds the result sorted ascending by (distance, id).
 // ----------------------------------------------------------------------------
 template <int METRIC>
 __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, double qn, int layer, int entry, float entry_d,
-                                            int ef, BeamState& st, int lane, WarpCounters& wc) {
+                                            int ef, BeamState& st, int lane, WarpCounters& wc, int flags = kPrefetchRows) {
     st.n = 0;
     st.ef = ef;
     st.far_ord = 0xFFFFFFFFu;
@@ -269,6 +363,7 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
     list_insert(s.list, st, make_key(entry_d, entry), lane);
     if (lane == 0) vis_test_and_set(s, entry);
     __syncwarp();
+    int guess_id = -1, guess_nb = -1;  // adjacency word [lane] of the candidate expected to be expanded next
 
     for (;;) {
         // closest unexpanded entry
@@ -293,7 +388,9 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
         int m = 0, deg = 0;
         for (int rb = 0; rb < stride; rb += 32) {
             const int slot = rb + lane;
-            const int nb = slot < stride ? row[slot] : -1;
+            int nb;
+            if (guess_id == c) nb = guess_nb;  // row already fetched under the previous insertion (stride <= 32)
+            else nb = slot < stride ? row[slot] : -1;
             deg += __popc(__ballot_sync(FULL, nb >= 0));
             bool fresh = false;
             if (nb >= 0) fresh = vis_test_and_set(s, nb);
@@ -306,23 +403,35 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
         wc.row_words += deg + 1;
         if (m == 0) continue;
         wc.ndist += m;
-        batch_dist<METRIC>(g, s, qn, m, lane);
 
-        // insert in stored order; a candidate is accepted iff |top| < ef or d < far (strict)
-        for (int jb = 0; jb < m; jb += 32) {
-            const int j = jb + lane;
-            const bool have = j < m;
-            const u64 mykey = have ? make_key(s.cand_dist[j], s.cand_id[j]) : ~0ull;
-            bool pending = have;
-            for (;;) {
-                const bool want = pending && (st.n < st.ef || key_ord(mykey) < st.far_ord);
-                const unsigned mk = __ballot_sync(FULL, want);
-                if (!mk) break;
-                const int src = __ffs(mk) - 1;
-                const u64 kn = __shfl_sync(FULL, mykey, src);
-                if (lane == src) pending = false;
-                list_insert(s.list, st, kn, lane);
+        if (g.pitch <= kSegFloats) {
+            // Software pipeline over passes of 16 rows: the copies of pass p+1 are in flight while the
+            // candidates of pass p are inserted (stored order is kept: pass p is inserted before p+1).
+            stage_issue(g, s.stg, s.cand_id, 0, min(kStageRows, m), 0, g.pitch, lane);
+            for (int base = 0; base < m; base += kStageRows) {
+                const int nrows = min(kStageRows, m - base);
+                stage_complete(s.stg);
+                compute_staged<METRIC>(g, s.stg, s.q, qn, s.cand_id, s.cand_dist, base, nrows, lane);
+                const int nbase = base + kStageRows;
+                if (nbase < m) {
+                    stage_issue(g, s.stg, s.cand_id, nbase, min(kStageRows, m - nbase), 0, g.pitch, lane);
+                } else if ((flags & kGuessRow) && layer == 0 && g.stride0 <= 32) {
+                    // Last pass: unless one of its candidates lands in front of it, the next expansion is the
+                    // closest entry still unexpanded now -- start loading its row under the insertion work.
+                    guess_id = -1;
+                    for (int b2 = st.cursor & ~31; b2 < st.n; b2 += 32) {
+                        const int idx = b2 + lane;
+                        const bool un = idx < st.n && !(s.list[idx] & 1ull);
+                        const unsigned mk = __ballot_sync(FULL, un);
+                        if (mk) { guess_id = key_id(s.list[b2 + __ffs(mk) - 1]); break; }
+                    }
+                    if (guess_id >= 0) guess_nb = lane < g.stride0 ? __ldg(g.adj0 + (size_t)guess_id * g.stride0 + lane) : -1;
+                }
+                insert_candidates(g, s, st, base, base + nrows, layer, lane, flags);
             }
+        } else {
+            batch_dist<METRIC>(g, s, qn, m, lane);
+            insert_candidates(g, s, st, 0, m, layer, lane, flags);
         }
     }
 }

@@ -107,6 +107,7 @@ void Index::set_tuning(const std::string& key, int value) {
     if (key == "vis_size_search") tuning_.vis_size_search = value;
     else if (key == "vis_size_build") tuning_.vis_size_build = value;
     else if (key == "blocks_per_sm") tuning_.blocks_per_sm = value;
+    else if (key == "flags") tuning_.flags = value;
     else if (key == "build_batch_max") build_batch_max_ = std::max(1, value);
     else if (key == "build_batch_ratio") build_batch_ratio_ = std::max(1, value);
     else throw std::invalid_argument("unknown tuning key: " + key);

@@ -11,6 +11,7 @@ struct Tuning {
     int vis_size_search = 0;  // 0 = derive from ef
     int vis_size_build = 0;
     int blocks_per_sm = 0;    // 0 = occupancy query
+    int flags = 2;            // bit 0: L2-prefetch rows of accepted candidates (no gain); bit 1: guess-row load
 };
 
 // per-query counters written by the search kernel when requested

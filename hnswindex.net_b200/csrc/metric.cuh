@@ -30,21 +30,49 @@ struct PairAcc {
 // (the stored row was staged there by a bulk copy, see stage.cuh).  Sequential in c, as the AVX loop.
 //   SQ : L[j] = fma(d, d, L[j]), d = a - b       (EuclideanMetric.cs:29-30)
 //   DOT: L[j] = L[j] + a*b   (mul, then add)     (CosineMetric.cs:37-38, 114-115)
+// Blackwell packed fp32x2 arithmetic (SASS FADD2 / FFMA2): two IEEE round-to-nearest operations per
+// instruction, bit-identical to the scalar ones.  Only used for the sq_euclid chain (sub, then a real
+// FMA); the cosine chains need mul-then-add WITHOUT fusion and ptxas contracts mul.rn.f32x2 +
+// add.rn.f32x2 into FFMA2, so they stay scalar.
+__device__ __forceinline__ u64 pack_f32x2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 sub_f32x2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma_f32x2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 template <bool SQ>
 __device__ __forceinline__ void pair_accumulate(PairAcc& acc, const float* row, const float* q, int nch, int h) {
     const float4* v4 = reinterpret_cast<const float4*>(row) + h;
     const float4* q4 = reinterpret_cast<const float4*>(q) + h;
+    if (SQ) {
+        u64 lo = pack_f32x2(acc.a0, acc.a1), hi = pack_f32x2(acc.a2, acc.a3);
 #pragma unroll 4
-    for (int c = 0; c < nch; ++c) {
-        const float4 a = v4[2 * c];
-        const float4 b = q4[2 * c];
-        if (SQ) {
-            float d;
-            d = __fsub_rn(a.x, b.x); acc.a0 = __fmaf_rn(d, d, acc.a0);
-            d = __fsub_rn(a.y, b.y); acc.a1 = __fmaf_rn(d, d, acc.a1);
-            d = __fsub_rn(a.z, b.z); acc.a2 = __fmaf_rn(d, d, acc.a2);
-            d = __fsub_rn(a.w, b.w); acc.a3 = __fmaf_rn(d, d, acc.a3);
-        } else {
+        for (int c = 0; c < nch; ++c) {
+            const float4 a = v4[2 * c];
+            const float4 b = q4[2 * c];
+            const u64 dlo = sub_f32x2(pack_f32x2(a.x, a.y), pack_f32x2(b.x, b.y));
+            const u64 dhi = sub_f32x2(pack_f32x2(a.z, a.w), pack_f32x2(b.z, b.w));
+            lo = fma_f32x2(dlo, dlo, lo);
+            hi = fma_f32x2(dhi, dhi, hi);
+        }
+        unpack_f32x2(lo, acc.a0, acc.a1);
+        unpack_f32x2(hi, acc.a2, acc.a3);
+    } else {
+#pragma unroll 4
+        for (int c = 0; c < nch; ++c) {
+            const float4 a = v4[2 * c];
+            const float4 b = q4[2 * c];
             acc.a0 = __fadd_rn(acc.a0, __fmul_rn(a.x, b.x));
             acc.a1 = __fadd_rn(acc.a1, __fmul_rn(a.y, b.y));
             acc.a2 = __fadd_rn(acc.a2, __fmul_rn(a.z, b.z));

@@ -64,4 +64,17 @@ __device__ __forceinline__ void stage_wait(Stager& st) {
     st.phase ^= 1u;
 }
 
+// ---- alternative: Ampere-style cp.async (SASS LDGSTS), 16 B per lane, one warp instruction per row -------------
+// Same full-row access pattern and bandwidth as the bulk copy in the microbenchmark, but ~5 instead of ~10
+// issue slots per staged row (ptxas serialises per-lane UBLKCP through ELECT/R2UR because the instruction
+// takes uniform operands), which matters once the search kernel is issue-bound.
+__device__ __forceinline__ void cp_async_16(float* dst, const float* src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 }  // namespace hnsw
