@@ -5,6 +5,8 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/hnsw_b200.h"
 #include "engine.hpp"
@@ -102,15 +104,31 @@ int hnsw_knn_query(hnsw_handle handle, const float* vectors, int count, int dim,
 
 int hnsw_range_query(hnsw_handle handle, const float* vectors, int count, int dim, float range, void** outIds, void** outDists, int* counts) {
     if (!handle) return 0;
-    HNSW_TRY
-    (void)vectors; (void)dim; (void)range;
-    for (int i = 0; i < count; ++i) {
-        if (outIds) outIds[i] = nullptr;
-        if (outDists) outDists[i] = nullptr;
-        if (counts) counts[i] = 0;
+    try {
+        if (count > 0 && (vectors == nullptr || outIds == nullptr || outDists == nullptr || counts == nullptr)) throw std::invalid_argument("null buffer");
+        for (int i = 0; i < count; ++i) { outIds[i] = nullptr; outDists[i] = nullptr; counts[i] = 0; }
+        std::vector<std::vector<std::pair<float, int>>> res;
+        get(handle)->range_query(vectors, count, dim, range, res);
+        for (int i = 0; i < count; ++i) {
+            const int n = (int)res[i].size();
+            // caller frees with hnsw_free_results (Marshal.AllocHGlobal in HNSWIndexExports.cs:172-173)
+            int* ids = n > 0 ? (int*)std::malloc(sizeof(int) * (size_t)n) : nullptr;
+            float* dists = n > 0 ? (float*)std::malloc(sizeof(float) * (size_t)n) : nullptr;
+            if (n > 0 && (!ids || !dists)) { std::free(ids); std::free(dists); throw std::bad_alloc(); }
+            for (int j = 0; j < n; ++j) { ids[j] = res[i][j].second; dists[j] = res[i][j].first; }
+            outIds[i] = ids; outDists[i] = dists; counts[i] = n;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        // HNSWIndexExports.cs:187-196: free everything handed out so far, zero the counts
+        for (int i = 0; i < count; ++i) {
+            if (outIds && outIds[i]) { std::free(outIds[i]); outIds[i] = nullptr; }
+            if (outDists && outDists[i]) { std::free(outDists[i]); outDists[i] = nullptr; }
+            if (counts) counts[i] = 0;
+        }
+        set_error(e.what());
+        return -1;
     }
-    throw std::runtime_error("RangeQuery is not yet accelerated by this engine (next tier after KnnQuery / Add).");
-    HNSW_CATCH(-1)
 }
 
 void hnsw_free_results(void** idsArray, void** distsArray, int count) {

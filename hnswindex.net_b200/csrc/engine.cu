@@ -383,6 +383,74 @@ void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_
 }
 
 // ---------------------------------------------------------------------------------------------
+// BatchRangeQuery (HNSWIndex.cs:160-168)
+// ---------------------------------------------------------------------------------------------
+void Index::range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out) {
+    std::lock_guard<std::mutex> lock(mu_);
+    out.assign((size_t)std::max(count, 0), {});
+    if (count <= 0 || length_ <= 0) return;  // HNSWIndex.cs:146
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    ensure_query_scratch(count, 1);
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
+
+    std::vector<int> todo(count);
+    for (int i = 0; i < count; ++i) todo[i] = i;
+    int cap = 1024;
+    const int cap_max = std::max(1024, length_);
+    while (!todo.empty()) {
+        cap = std::min(cap, cap_max);
+        int hash_size = 4096;
+        while (hash_size < 4 * cap) hash_size <<= 1;  // load factor <= 0.5 at 2*cap visited nodes
+        const size_t per_q = (size_t)cap * 8 + (size_t)hash_size * 4 + 8;
+        const int chunk = (int)std::max<size_t>(1, std::min<size_t>(todo.size(), ((size_t)768 << 20) / per_q));
+        u64* d_keys = nullptr;
+        uint32_t* d_hash = nullptr;
+        int *d_cnt = nullptr, *d_map = nullptr;
+        HNSW_CUDA_CHECK(cudaMalloc(&d_keys, (size_t)chunk * cap * 8));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_hash, (size_t)chunk * hash_size * 4));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_cnt, (size_t)chunk * 4));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_map, (size_t)chunk * 4));
+        std::vector<int> retry;
+        try {
+            std::vector<int> cnt(chunk);
+            std::vector<u64> keys;
+            for (size_t c0 = 0; c0 < todo.size(); c0 += chunk) {
+                const int nw = (int)std::min<size_t>(chunk, todo.size() - c0);
+                HNSW_CUDA_CHECK(cudaMemcpyAsync(d_map, todo.data() + c0, (size_t)nw * 4, cudaMemcpyHostToDevice, stream_));
+                launch_range_search((int)metric_, view(), d_q_, d_map, nw, range, cap, hash_size, d_keys, d_hash, d_cnt, d_counters_ + 3, tuning_, stream_);
+                stats_.search_launches += 1;
+                HNSW_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nw * 4, cudaMemcpyDeviceToHost, stream_));
+                HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+                int maxn = 0;
+                for (int w = 0; w < nw; ++w) maxn = std::max(maxn, cnt[w]);
+                keys.resize((size_t)nw * cap);
+                if (maxn > 0) {
+                    HNSW_CUDA_CHECK(cudaMemcpyAsync(keys.data(), d_keys, (size_t)nw * cap * 8, cudaMemcpyDeviceToHost, stream_));
+                    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+                }
+                for (int w = 0; w < nw; ++w) {
+                    const int qi = todo[c0 + w];
+                    if (cnt[w] < 0) { retry.push_back(qi); continue; }
+                    u64* kq = keys.data() + (size_t)w * cap;
+                    std::sort(kq, kq + cnt[w]);  // ascending by (distance, id): OrderBy(c => c.Dist), HNSWIndex.cs:154
+                    auto& dst = out[qi];
+                    dst.resize(cnt[w]);
+                    for (int j = 0; j < cnt[w]; ++j) dst[j] = {key_dist(kq[j]), key_id(kq[j])};
+                }
+            }
+        } catch (...) {
+            cudaFree(d_keys); cudaFree(d_hash); cudaFree(d_cnt); cudaFree(d_map);
+            throw;
+        }
+        cudaFree(d_keys); cudaFree(d_hash); cudaFree(d_cnt); cudaFree(d_map);
+        if (!retry.empty() && cap >= cap_max) throw std::runtime_error("range_query: result does not fit the index size (internal error)");
+        todo.swap(retry);
+        cap *= 4;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Serialize / Deserialize (HNSWIndex.cs:210-229)
 // ---------------------------------------------------------------------------------------------
 void Index::export_graph(HostGraph& g) {

@@ -15,6 +15,7 @@
 
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -58,6 +59,8 @@ public:
     // queries / outputs already resident in device memory of this index's GPU
     void knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists);
     void exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists);
+    // BatchRangeQuery (HNSWIndex.cs:160-168): per query, (id, distance) ascending by distance
+    void range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out);
     void serialize(const std::string& path, bool packed);
 
     int count() const { return length_; }

@@ -35,6 +35,13 @@ void launch_item_norms(const float* d_vectors, int pitch, int dim, int first, in
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int first, int count, int ef_construction,
                         unsigned* d_work_counter, const Tuning& t, cudaStream_t stream);
 
+// RangeQuery (HNSWIndex.cs:144-168): traversal of all in-range nodes reachable from the layer-0 entry.  Work item w handles
+// query qmap[w] (or w when qmap is null); out_keys [nwork][cap] unsorted (distance|id) keys, out_count[w] = result size or -1
+// when cap / the visited table (hash [nwork][hash_size], power of two) overflowed.
+void launch_range_search(int metric, const GraphView& g, const float* d_queries, const int* d_qmap, int nwork, float range, int cap,
+                         int hash_size, u64* d_out_keys, uint32_t* d_hash, int* d_out_count, unsigned* d_work_counter, const Tuning& t,
+                         cudaStream_t stream);
+
 // K3: exact brute-force top-k (recall ground truth), same metric arithmetic.
 void launch_exact_knn(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists,
                       void* d_scratch, size_t scratch_bytes, cudaStream_t stream);

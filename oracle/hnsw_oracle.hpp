@@ -794,6 +794,52 @@ public:
         return topCandidates.ToArray();
     }
 
+    // GraphNavigator.cs:262-325 (SearchLayerRange; lock-free, stateless search)
+    std::vector<NodeDistance> SearchLayerRange(int entryPointId, int layer, float range, const float* q, Counters* c) {
+        BinaryHeap<FartherFirst> topCandidates(MaxEdges(layer));
+        BinaryHeap<CloserFirst> candidates(MaxEdges(layer) * 2);
+        NodeDistance entry{entryPointId, Distance(entryPointId, q, c)};
+        float farthest = std::numeric_limits<float>::max();
+        if (entry.Dist <= range) {
+            topCandidates.Push(entry);
+            farthest = entry.Dist;
+        }
+        candidates.Push(entry);
+        VisitedList* visited = GetFreeVisitedList();
+        visited->Add(entryPointId);
+        while (candidates.Count() > 0) {
+            NodeDistance closest = candidates.Peek();
+            if (closest.Dist > farthest && closest.Dist > range) break;
+            candidates.Pop();
+            const EdgeList& e = Nodes[closest.Id]->OutEdges[layer];
+            if (c) { c->nexp++; c->row_words += e.Count + 1; }
+            for (int i = 0; i < e.Count; ++i) {
+                int nb = e.Buffer[i];
+                if (visited->Contains(nb)) continue;
+                float d = Distance(nb, q, c);
+                if (d <= range) {
+                    NodeDistance sel{nb, d};
+                    candidates.Push(sel);
+                    topCandidates.Push(sel);
+                    if (topCandidates.Peek().Dist > range) topCandidates.Pop();
+                    if (topCandidates.Count() > 0) farthest = topCandidates.Peek().Dist;
+                }
+                visited->Add(nb);
+            }
+        }
+        ReleaseVisitedList(visited);
+        return topCandidates.ToArray();
+    }
+
+    // HNSWIndex.cs:144-155
+    std::vector<NodeDistance> RangeQuery(const float* q, float range, Counters* c = nullptr) {
+        if (Count() <= 0) return {};
+        Node* ep = FindEntryPoint(0, q, c);
+        auto top = SearchLayerRange(ep->Id, 0, range, q, c);
+        std::stable_sort(top.begin(), top.end(), [](const NodeDistance& a, const NodeDistance& b) { return float_compare_to(a.Dist, b.Dist) < 0; });
+        return top;
+    }
+
     // HNSWIndex.cs:107-124
     std::vector<NodeDistance> KnnQuery(const float* q, int k, Counters* c = nullptr) {
         if (Count() <= 0 || k < 1) return {};

@@ -59,6 +59,8 @@ def lib():
     L.orc_add_frozen_batches.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, i32p, ct.c_int, ct.c_int]
     L.orc_knn_query.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, ct.c_int, u64p]
     L.orc_knn_query_counters.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, u64p]
+    L.orc_range_query.restype = ct.c_longlong
+    L.orc_range_query.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_float, ct.POINTER(ct.c_longlong), i32p, f32p, ct.c_int]
     L.orc_exact_knn.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, ct.c_int]
     L.orc_node_level.argtypes = [ct.c_void_p, ct.c_int]
     L.orc_node_row.argtypes = [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, i32p, ct.c_int]
@@ -231,6 +233,22 @@ class OracleIndex:
         if rc < 0:
             raise RuntimeError(lib().orc_last_error().decode())
         return out
+
+    def range_query(self, queries, radius, threads=os.cpu_count() or 1):
+        """HNSWIndex.BatchRangeQuery (HNSWIndex.cs:160-168): per-query (ids, dists), ascending by distance."""
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        n = q.shape[0]
+        off = np.zeros(n + 1, dtype=np.int64)
+        offp = off.ctypes.data_as(ct.POINTER(ct.c_longlong))
+        total = lib().orc_range_query(self._h, _fp(q), n, q.shape[1], float(radius), offp, None, None, threads)
+        if total < 0:
+            raise RuntimeError(lib().orc_last_error().decode())
+        ids = np.empty(max(total, 1), dtype=np.int32)
+        d = np.empty(max(total, 1), dtype=np.float32)
+        lib().orc_range_query(self._h, _fp(q), n, q.shape[1], float(radius), offp, _ip(ids), _fp(d), threads)
+        return [ids[off[i]:off[i + 1]].copy() for i in range(n)], [d[off[i]:off[i + 1]].copy() for i in range(n)]
 
     def exact_knn(self, queries, k, threads=os.cpu_count() or 1):
         q = _f32(queries)

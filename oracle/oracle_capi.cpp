@@ -118,6 +118,27 @@ int orc_knn_query_counters(void* h, const float* q, int count, int dim, int k, u
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
+// HNSWIndex.BatchRangeQuery (HNSWIndex.cs:160-168): results concatenated; offsets[count+1]
+// two-call protocol: pass ids == null to get the total size
+long long orc_range_query(void* h, const float* q, int count, int dim, float range, long long* offsets, int* ids, float* dists, int threads) {
+    try {
+        Index* ix = (Index*)h;
+        if (dim != ix->dim) throw std::runtime_error("dimension mismatch");
+        std::vector<std::vector<NodeDistance>> res(count);
+        std::atomic<int> next{0};
+        auto work = [&]() { for (;;) { int i = next.fetch_add(1); if (i >= count) break; res[i] = ix->RangeQuery(q + (size_t)i * dim, range); } };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < std::max(1, threads); t++) pool.emplace_back(work);
+        for (auto& th : pool) th.join();
+        long long total = 0;
+        for (int i = 0; i < count; i++) { offsets[i] = total; total += (long long)res[i].size(); }
+        offsets[count] = total;
+        if (ids && dists)
+            for (int i = 0; i < count; i++)
+                for (size_t j = 0; j < res[i].size(); j++) { ids[offsets[i] + j] = res[i][j].Id; dists[offsets[i] + j] = res[i][j].Dist; }
+        return total;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
 int orc_exact_knn(void* h, const float* q, int count, int dim, int k, int* outIds, float* outDists, int threads) {
     try {
         Index* ix = (Index*)h;

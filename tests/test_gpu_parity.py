@@ -319,3 +319,40 @@ def test_gpu_built_graph_recall_parity_sift_like(hnswindex, oracle, tmp_path):
     o = ref2.knn_query(queries, 10, threads=8)
     g = gpu.knn_query(queries, 10)
     _assert_identical(g[0], g[1], o[0], o[1])
+
+
+# ---------------------------------------------------------------------------------------- range query
+@pytest.mark.parametrize("metric,radius", [("sq_euclid", 16.0), ("cosine", 0.2), ("sq_euclid", 1e-3), ("sq_euclid", 40.0)])
+def test_range_query_matches_oracle(hnswindex, oracle, tmp_path, metric, radius):
+    # HNSWIndex.BatchRangeQuery (HNSWIndex.cs:160-168) on the same graph: same result set, same distances,
+    # ascending; radius 40 returns (almost) the whole index and exercises the grow-and-retry path.
+    rng = np.random.default_rng(77)
+    n = 2000 if radius < 40 else 1500
+    data = rng.random((n, 128), dtype=np.float32)
+    ref, path = _oracle_graph(oracle, tmp_path, metric, data, f"range{metric}{radius}", collection_size=100)
+    gpu = hnswindex.Index.deserialize(metric, path)
+    q = data[:300]
+    o_ids, o_d = ref.range_query(q, radius)
+    g_ids, g_d = gpu.range_query(q, radius)
+    assert len(g_ids) == len(q)
+    for i in range(len(q)):
+        assert len(g_ids[i]) == len(o_ids[i]), i
+        assert (np.diff(g_d[i]) >= 0).all() and (g_d[i] <= radius).all()
+        go = np.lexsort((g_ids[i], g_d[i])); oo = np.lexsort((o_ids[i], o_d[i]))
+        assert np.array_equal(g_ids[i][go], o_ids[i][oo])
+        assert np.array_equal(g_d[i][go].view(np.uint32), o_d[i][oo].view(np.uint32))
+    if radius >= 40:
+        assert np.mean([len(x) for x in g_ids]) > 0.9 * n
+
+
+def test_range_query_reference_python_test(hnswindex):
+    # bindings/__tests__/recall_test.py:49-58
+    vectors = np.random.default_rng(1).random((2000, 128))
+    index = hnswindex.Index(128)
+    index.set_collection_size(100)
+    index.add(vectors)
+    result_ids, distances = index.range_query(vectors, 16.0)
+    assert len(result_ids) == 2000
+    for d in distances:
+        assert all(d < 16.0)
+    assert sum(len(d) for d in distances) > 2000   # every vector finds at least itself
