@@ -275,11 +275,11 @@ def run_b200(args):
         prof = ROOT / "profiles" / "search_kernel_traffic.json"
         if prof.exists():
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
-        # CPU baseline: repeat the 10k batch until ~10 s of work (max 5 passes)
+        # CPU baseline (N=1 only): repeat the 10k batch until ~10 s of work (max 5 passes)
         t_cpu, passes = 0.0, 0
-        while t_cpu < 10.0 and passes < 5:
+        while world == 1 and t_cpu < 10.0 and passes < 5:
             tc = time.perf_counter(); ref.knn_query(queries[:nq], K, threads=cores); t_cpu += time.perf_counter() - tc; passes += 1
-        cpu = {"value": round(nq * passes / t_cpu, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+        cpu = None if world > 1 else {"value": round(nq * passes / t_cpu, 1), "unit": "queries/s", "cores": cores, "kind": "port",
                "sample": f"{passes} x {nq} queries of batch 0 on the same GPU-built 1M graph, ef={ef}, all host threads "
                          f"(C++ restatement of the reference's Parallel.For BatchKnnQuery, not the .NET runtime)",
                "id_lists_identical_to_gpu": round(same, 5)}

@@ -238,6 +238,33 @@ __device__ __forceinline__ bool list_insert(u64* list, BeamState& st, u64 key, i
         if (pos < st.cursor) st.cursor = pos;
         return true;
     }
+    if (n <= 256) {
+        // same single pass with up to eight registers per lane (construction: ef = MaxCandidates ~ 100-200)
+        u64 v[8];
+        int pos = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int idx = c * 32 + lane;
+            v[c] = idx < n ? list[idx] : ~0ull;
+            pos += __popc(__ballot_sync(FULL, v[c] < key));
+        }
+        const u64 at = pos < n ? list[pos] : ~0ull;
+        __syncwarp();  // every lane has read list[pos] before any lane overwrites it below
+        if ((at >> 1) == (key >> 1)) return false;
+        if (pos >= st.ef) return false;
+        const int last = (n == st.ef) ? n - 1 : n;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int idx = c * 32 + lane;
+            if (idx >= pos && idx < last) list[idx + 1] = v[c];
+        }
+        if (lane == 0) list[pos] = key;
+        __syncwarp();
+        if (n < st.ef) st.n = n + 1;
+        st.far_ord = (st.n == st.ef) ? key_ord(list[st.ef - 1]) : 0xFFFFFFFFu;
+        if (pos < st.cursor) st.cursor = pos;
+        return true;
+    }
     const int pos = list_lower_bound(list, n, key, lane);
     if (pos < n && (list[pos] >> 1) == (key >> 1)) return false;  // same distance bits + id
     if (pos >= st.ef) return false;

@@ -88,7 +88,7 @@ __device__ __forceinline__ int* row_ptr_mut(const GraphView& g, int id, int laye
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 build_select_kernel(GraphView g, const int* __restrict__ levels, int first, int count, int efc, int list_cap, int vis_size, int cand_cap,
                     int sel_cap, unsigned* work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -165,7 +165,7 @@ __device__ __forceinline__ void unlock_node(int* locks, int n, int lane) {
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 build_link_kernel(GraphView g, const int* __restrict__ levels, int first, int count, int list_cap, int cand_cap, int sel_cap,
                   unsigned* work_counter, int* error_flag) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -257,7 +257,8 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int
     const int list_cap_link = maxE0 + 1;
     const int cand_cap = ((std::max(g.stride0, g.strideU) + 1 + 31) / 32) * 32;
     const int sel_cap = std::max(maxE0, list_cap_sel < maxE0 ? list_cap_sel : maxE0);
-    int vis = t.vis_size_build > 0 ? std::max(64, pow2_ge(t.vis_size_build)) : std::min(8192, std::max(256, pow2_ge(8 * efc)));
+    // small table: shared memory per warp decides the occupancy of this latency-bound kernel (see search_kernels.cu)
+    int vis = t.vis_size_build > 0 ? std::max(64, pow2_ge(t.vis_size_build)) : std::min(2048, std::max(256, pow2_ge(2 * efc)));
     const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap) * kWarpsPerBlock;
     const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap) * kWarpsPerBlock;
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, 2 * sizeof(unsigned), stream));

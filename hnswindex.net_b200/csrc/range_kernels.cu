@@ -29,7 +29,7 @@ __device__ __forceinline__ bool global_test_and_set(uint32_t* tab, uint32_t mask
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 5)
 range_search_kernel(GraphView g, const float* __restrict__ queries, const int* __restrict__ qmap, int nwork, float range, int cap, int hash_size,
                     int cand_cap, u64* out_keys, uint32_t* hash, int* out_count, unsigned* work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];

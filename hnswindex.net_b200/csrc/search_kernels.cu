@@ -17,7 +17,7 @@
 namespace hnsw {
 
 template <int METRIC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 5)
 knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int vis_size, int cand_cap, int flags,
                   int* __restrict__ out_ids, float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats) {
     extern __shared__ __align__(128) unsigned char smem[];
