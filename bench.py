@@ -384,6 +384,95 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- partitioned mode (C4)
+def run_partitioned(args):
+    """BASELINE config C4: 1.25M x 96 ucosine per GPU (10M over 8), every rank searches ALL queries on its own
+    sub-graph, per-rank top-k lists are exchanged with one NCCL all-gather and merged (K7).  Not the headline
+    metric: a second workload, printed with its own metric name."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import hnswindex
+    from hnswindex import bindings as hb
+    from hnswindex import partitioned as P
+    hb.set_device(local)
+    dim, rank_lr, k, per_rank, nq = 96, 16, 10, args.n_per_rank, args.nq
+    total = per_rank * world
+    rng = np.random.default_rng(99)
+    A = rng.standard_normal((rank_lr, dim)).astype(np.float32)
+
+    def gen(n, seed):
+        r = np.random.default_rng(seed)
+        out = np.empty((n, dim), dtype=np.float32)
+        for s0 in range(0, n, 131072):
+            e = min(n, s0 + 131072)
+            out[s0:e] = r.standard_normal((e - s0, rank_lr)).astype(np.float32) @ A + 0.25 * r.standard_normal((e - s0, dim)).astype(np.float32)
+        out /= np.linalg.norm(out, axis=1, keepdims=True)
+        return out
+    s0, e0 = P.shard_range(total, rank, world)
+    shard = gen(e0 - s0, 1234 + rank)          # shard r of the data set (independent seeds = disjoint ranges)
+    queries = gen(nq, 4321)                    # identical on every rank
+    ix = hnswindex.Index(dim, "ucosine")
+    ix.set_collection_size(e0 - s0); ix.set_max_edges(16); ix.set_max_candidates(200); ix.set_allow_removals(False)
+    tb = time.time(); ix.add(shard); build_s = time.time() - tb
+    del shard
+    pix = P.PartitionedIndex(rank, world, total, index=ix)
+    # ground truth: exact top-k per shard, merged the same way
+    ns = min(1000, nq)
+    e_ids, e_d = ix.exact_knn(queries[:ns], k)
+    e_ids = np.where(e_ids >= 0, e_ids + s0, -1).astype(np.int32)
+    g_ids, g_d = pix._gather(torch.from_numpy(e_ids).cuda(), torch.from_numpy(e_d).cuda())
+    truth, _ = P.merge_topk_numpy(g_ids.cpu().numpy(), g_d.cpu().numpy(), k)
+    ef = None
+    for cand in EF_GRID:
+        ix.set_min_nn(cand)
+        r = recall_at_k(pix.knn_query(queries[:ns], k)[0], truth)
+        if rank == 0:
+            log(f"  ef={cand}: recall@10={r:.4f}")
+        if r >= 0.95:
+            ef = cand
+            break
+    ix.set_min_nn(ef or EF_GRID[-1])
+    for i in range(args.warmup):
+        pix.knn_query(queries, k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = time.perf_counter()
+    for i in range(args.steps):
+        ids, d = pix.knn_query(queries, k)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t
+    tt = torch.tensor([el], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    el = float(tt.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "QPS at recall@10>=0.95, partitioned index (C4: 1.25M x 96 ucosine per GPU, all-gather top-k merge)",
+            "value": round(nq * args.steps / el, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(el / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"C4: {total} x {dim} fp32 ucosine (rank-16 + 0.25 noise, L2-normalised) in {world} sub-graphs of {per_rank}, "
+                                   f"{nq} queries seen by every rank, k={k}, ef={ef}, NCCL all-gather of [{nq},{k}] ids+dists per rank + merge kernel",
+                       "recall_at_10": round(r, 4), "ef": ef, "build_s_per_shard": round(build_s, 2)},
+            "e2e": {"value": round(nq * args.steps / el, 1), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 8},
+            "gpu_launches": int(args.steps * 2)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -397,11 +486,15 @@ def main():
     ap.add_argument("--snapshot-dir", default="/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
     ap.add_argument("--reference-sample", type=int, default=10_000)
     ap.add_argument("--reference-build-budget-s", type=float, default=150.0)
+    ap.add_argument("--mode", default="replicated", choices=["replicated", "partitioned"], help="partitioned = BASELINE config C4 (secondary workload)")
+    ap.add_argument("--n-per-rank", type=int, default=1_250_000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "partitioned":
+        run_partitioned(args)
     else:
         run_b200(args)
 
