@@ -233,18 +233,21 @@ static int pow2_ge(int v) {
 }
 
 template <typename Kern>
-static int persistent_grid(Kern kern, size_t smem, const Tuning& t, int work_items) {
+static int persistent_grid(Kern kern, size_t smem_per_warp, const Tuning& t, int work_items, int& warps) {
     int dev = 0, max_optin = 0, sms = 0, per_sm = 0;
     HNSW_CUDA_CHECK(cudaGetDevice(&dev));
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    warps = kWarpsPerBlock;
+    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) warps >>= 1;
+    const size_t smem = smem_per_warp * warps;
     if (smem > (size_t)max_optin)
-        throw std::runtime_error("MaxCandidates / MaxEdges too large for shared memory: need " + std::to_string(smem) + " B per block");
+        throw std::runtime_error("MaxCandidates / MaxEdges too large for shared memory: need " + std::to_string(smem) + " B per warp");
     HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem));
     if (per_sm < 1) per_sm = 1;
     if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);
-    const int need = (work_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int need = (work_items + warps - 1) / warps;
     return std::max(1, std::min(need, sms * per_sm));
 }
 
@@ -259,18 +262,19 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int
     const int sel_cap = std::max(maxE0, list_cap_sel < maxE0 ? list_cap_sel : maxE0);
     // small table: shared memory per warp decides the occupancy of this latency-bound kernel (see search_kernels.cu)
     int vis = t.vis_size_build > 0 ? std::max(64, pow2_ge(t.vis_size_build)) : std::min(2048, std::max(256, pow2_ge(2 * efc)));
-    const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap) * kWarpsPerBlock;
-    const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap) * kWarpsPerBlock;
+    const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap);   // per warp
+    const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap);  // per warp
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, 2 * sizeof(unsigned), stream));
     int* err = reinterpret_cast<int*>(d_work_counter + 2);
 #define HNSW_LAUNCH_BUILD(M)                                                                                                    \
     {                                                                                                                           \
-        const int g1 = persistent_grid(build_select_kernel<M>, smem_sel, t, count);                                            \
-        build_select_kernel<M><<<g1, kThreads, smem_sel, stream>>>(g, d_levels, first, count, efc, list_cap_sel, vis, cand_cap, \
-                                                                   sel_cap, d_work_counter);                                   \
-        const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, count);                                             \
-        build_link_kernel<M><<<g2, kThreads, smem_link, stream>>>(g, d_levels, first, count, list_cap_link, cand_cap, sel_cap, \
-                                                                  d_work_counter + 1, err);                                    \
+        int w1 = 0, w2 = 0;                                                                                                     \
+        const int g1 = persistent_grid(build_select_kernel<M>, smem_sel, t, count, w1);                                        \
+        build_select_kernel<M><<<g1, 32 * w1, smem_sel * w1, stream>>>(g, d_levels, first, count, efc, list_cap_sel, vis,      \
+                                                                       cand_cap, sel_cap, d_work_counter);                     \
+        const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, count, w2);                                         \
+        build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, stream>>>(g, d_levels, first, count, list_cap_link, cand_cap,      \
+                                                                      sel_cap, d_work_counter + 1, err);                       \
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_BUILD(SQ_EUCLID) break;

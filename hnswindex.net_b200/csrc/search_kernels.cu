@@ -96,22 +96,27 @@ int pick_vis_size(int requested, int ef) {
     return std::min(4096, std::max(256, pow2_at_least(4 * ef)));
 }
 
+// Persistent launch shape: `warps` independent warps per block (4, fewer when one warp's scratch is large),
+// at most one resident wave of blocks.  Returns the grid size and sets `warps`.
 template <typename Kern>
-static int configure_persistent(Kern kern, size_t smem, const Tuning& t, int work_items, int items_per_block) {
+static int configure_persistent(Kern kern, size_t smem_per_warp, const Tuning& t, int work_items, int& warps) {
     int dev = 0, max_optin = 0;
     HNSW_CUDA_CHECK(cudaGetDevice(&dev));
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    warps = kWarpsPerBlock;
+    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) warps >>= 1;
+    const size_t smem = smem_per_warp * warps;
     if (smem > (size_t)max_optin)
-        throw std::runtime_error("search width too large for shared memory: need " + std::to_string(smem) + " B per block, have " +
-                                 std::to_string(max_optin));
+        throw std::runtime_error("search width (max(MinNN, k)) too large for shared memory: need " + std::to_string(smem) +
+                                 " B per warp, have " + std::to_string(max_optin));
     HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem));
     if (per_sm < 1) per_sm = 1;
     if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);
     const int sms = device_sm_count();
-    const int need = (work_items + items_per_block - 1) / items_per_block;
-    return std::max(1, std::min(need, sms * per_sm));  // persistent: at most one resident wave
+    const int need = (work_items + warps - 1) / warps;
+    return std::max(1, std::min(need, sms * per_sm));
 }
 
 void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int* d_ids, float* d_dists,
@@ -119,13 +124,14 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
     if (nq <= 0) return;
     const int vis = pick_vis_size(t.vis_size_search, ef);
     const int cand_cap = ((std::max(g.stride0, g.strideU) + 31) / 32) * 32;
-    const size_t smem = warp_scratch_bytes(g.pitch, ef, vis, cand_cap) * kWarpsPerBlock;
+    const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis, cand_cap);
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
 #define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
     {                                                                                                                           \
-        const int grid = configure_persistent(knn_search_kernel<M>, smem, t, nq, kWarpsPerBlock);                               \
-        knn_search_kernel<M><<<grid, kThreads, smem, stream>>>(g, d_queries, nq, k, ef, vis, cand_cap, t.flags, d_ids, d_dists,         \
-                                                               d_work_counter, d_stats);                                       \
+        int warps = 0;                                                                                                          \
+        const int grid = configure_persistent(knn_search_kernel<M>, per_warp, t, nq, warps);                                   \
+        knn_search_kernel<M><<<grid, 32 * warps, per_warp * warps, stream>>>(g, d_queries, nq, k, ef, vis, cand_cap, t.flags,  \
+                                                                             d_ids, d_dists, d_work_counter, d_stats);         \
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_SEARCH(SQ_EUCLID) break;

@@ -65,6 +65,7 @@ def _assert_identical(g_ids, g_d, o_ids, o_d, min_same=0.995, explain=None):
 @pytest.mark.parametrize("metric,dim,normalize", [
     ("sq_euclid", 128, False), ("cosine", 128, False), ("ucosine", 128, True),
     ("sq_euclid", 127, False), ("cosine", 100, False), ("ucosine", 96, True), ("cosine", 960, False), ("sq_euclid", 20, False),
+    ("sq_euclid", 3, False), ("cosine", 5, False), ("ucosine", 260, True),
 ])
 def test_knn_query_matches_oracle_on_same_graph(hnswindex, oracle, tmp_path, metric, dim, normalize):
     n = 3000 if dim < 900 else 1200
@@ -78,7 +79,7 @@ def test_knn_query_matches_oracle_on_same_graph(hnswindex, oracle, tmp_path, met
     gpu = hnswindex.Index.deserialize(metric, path)
     assert gpu.count == n and gpu.dim == dim
     assert gpu.params() == ref.params()
-    for k, min_nn in ((1, 5), (5, 5), (10, 5), (10, 64), (100, 5), (3, 300)):
+    for k, min_nn in ((1, 5), (5, 5), (10, 5), (10, 64), (100, 5), (3, 300), (2, 2900), (1, 8000)):
         ref.set_min_nn(min_nn)
         gpu.set_min_nn(min_nn)
         o_ids, o_d = ref.knn_query(queries, k, threads=8)
