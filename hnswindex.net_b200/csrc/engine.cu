@@ -108,6 +108,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "vis_size_build") tuning_.vis_size_build = value;
     else if (key == "blocks_per_sm") tuning_.blocks_per_sm = value;
     else if (key == "flags") tuning_.flags = value;
+    else if (key == "zero_copy") zero_copy_ = value != 0;
     else if (key == "build_batch_max") build_batch_max_ = std::max(1, value);
     else if (key == "build_batch_ratio") build_batch_ratio_ = std::max(1, value);
     else throw std::invalid_argument("unknown tuning key: " + key);
@@ -304,6 +305,17 @@ void Index::fetch_query_stats(int count) {
     for (auto& q : h) { stats_.ndist += q.ndist; stats_.nexp += q.nexp; stats_.row_words += q.row_words; }
 }
 
+// Device-visible alias of a host buffer when it is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory):
+// the kernel can then read or write it in place over PCIe, so the transfer overlaps the search instead of
+// preceding / following it.  Pageable memory returns nullptr and takes the staged cudaMemcpy path.
+template <typename T>
+static T* pinned_alias(const T* host) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return nullptr;
+    return reinterpret_cast<T*>(a.devicePointer);
+}
+
 void Index::knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
     std::lock_guard<std::mutex> lock(mu_);
     if (count <= 0 || k < 1) return;
@@ -316,14 +328,23 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
     ensure_query_scratch(count, k);
     if (collect_stats_) ensure_stats(count);
     const int ef = std::max(params_.MinNN, k);  // HNSWIndex.cs:115
-    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
+    const float* q_src = zero_copy_ ? pinned_alias(queries) : nullptr;
+    int* ids_dst = zero_copy_ ? pinned_alias(out_ids) : nullptr;
+    float* d_dst = zero_copy_ ? pinned_alias(out_dists) : nullptr;
+    const bool direct_out = ids_dst != nullptr && d_dst != nullptr;
+    if (!q_src) {
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
+        q_src = d_q_;
+    }
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-    launch_knn_search((int)metric_, view(), d_q_, count, k, ef, d_ids_, d_dists_, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr, tuning_,
-                      stream_);
+    launch_knn_search((int)metric_, view(), q_src, count, k, ef, direct_out ? ids_dst : d_ids_, direct_out ? d_dst : d_dists_, d_counters_ + 3,
+                      collect_stats_ ? d_stats_ : nullptr, tuning_, stream_);
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     stats_.search_launches += 1;
-    HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
-    HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists, d_dists_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
+    if (!direct_out) {
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists, d_dists_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
+    }
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
     float ms = 0.f;
     HNSW_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));

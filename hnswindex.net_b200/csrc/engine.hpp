@@ -95,6 +95,7 @@ private:
     int length_ = 0, capacity_ = 0, dev_capacity_ = 0;
     int entry_ = -1, top_ = -1;
     bool collect_stats_ = false;
+    bool zero_copy_ = true;        // page-locked caller buffers are read / written in place by the kernel
     IndexStats stats_;
     int build_batch_max_ = 4096;   // new nodes per build launch (upper bound)
     int build_batch_ratio_ = 32;   // ... and at most 1/ratio of the nodes already linked

@@ -133,7 +133,8 @@ typedef struct hnsw_stats {
 } hnsw_stats;
 HNSW_API int hnsw_enable_stats(hnsw_handle handle, int on);
 HNSW_API int hnsw_get_stats(hnsw_handle handle, hnsw_stats* out);
-/* tuning knobs: "vis_size_search", "vis_size_build", "blocks_per_sm", "build_batch_max", "build_batch_ratio" */
+/* tuning knobs: "vis_size_search", "vis_size_build", "blocks_per_sm", "build_batch_max", "build_batch_ratio",
+ * "flags", "zero_copy" (1 = page-locked caller buffers of hnsw_knn_query are accessed in place by the kernel) */
 HNSW_API int hnsw_set_tuning(hnsw_handle handle, const char* key, int value);
 
 /* Copy the graph to host memory (tests / inspection).  levels[count]; rows0[count][stride0] (-1 padded).

@@ -357,3 +357,27 @@ def test_range_query_reference_python_test(hnswindex):
     for d in distances:
         assert all(d < 16.0)
     assert sum(len(d) for d in distances) > 2000   # every vector finds at least itself
+
+
+def test_pinned_host_buffers_take_the_zero_copy_path_with_identical_results(hnswindex):
+    # page-locked caller buffers are read / written in place by the kernel; results must equal the staged path
+    import ctypes as ct
+    import torch
+    rng = np.random.default_rng(11)
+    data = rng.random((5000, 64), dtype=np.float32)
+    q = rng.random((777, 64), dtype=np.float32)
+    ix = hnswindex.Index(64, "cosine")
+    ix.set_collection_size(5000)
+    ix.add(data)
+    a_ids, a_d = ix.knn_query(q, 7)                      # pageable numpy buffers
+    qp = torch.from_numpy(q).pin_memory()
+    ip = torch.full((777, 7), -5, dtype=torch.int32).pin_memory()
+    dp = torch.full((777, 7), -5.0, dtype=torch.float32).pin_memory()
+    f32p, i32p = ct.POINTER(ct.c_float), ct.POINTER(ct.c_int)
+    rc = hnswindex.lib.hnsw_knn_query(ix._h, ct.cast(qp.data_ptr(), f32p), 777, 64, 7, ct.cast(ip.data_ptr(), i32p), ct.cast(dp.data_ptr(), f32p))
+    assert rc == 0, hnswindex.last_error()
+    assert np.array_equal(ip.numpy(), a_ids) and np.array_equal(dp.numpy().view(np.uint32), a_d.view(np.uint32))
+    ix.set_tuning("zero_copy", 0)
+    ip.fill_(-5)
+    rc = hnswindex.lib.hnsw_knn_query(ix._h, ct.cast(qp.data_ptr(), f32p), 777, 64, 7, ct.cast(ip.data_ptr(), i32p), ct.cast(dp.data_ptr(), f32p))
+    assert rc == 0 and np.array_equal(ip.numpy(), a_ids)
