@@ -37,6 +37,9 @@ struct WarpScratch {
     int vis_size;      // power of two >= 64
     int vis_shift;     // 32 - log2(vis_size / 2)
     int cap;           // list capacity (>= ef)
+    uint32_t* gvis;    // optional exact visited set of this warp in GLOBAL memory (open addressing, ids + 1), or null
+    int gvis_size;     // slots, power of two
+    int gvis_shift;    // 32 - log2(gvis_size)
 };
 
 constexpr int kPrefetchRows = 1;  // flags bit 0: L2-prefetch the adjacency rows of accepted candidates
@@ -71,6 +74,9 @@ __device__ __forceinline__ WarpScratch carve_scratch(unsigned char* base, int pi
     s.vis_size = vis_size;
     s.vis_shift = 32 - (31 - __clz(vis_size >> 1));
     s.cap = cap;
+    s.gvis = nullptr;
+    s.gvis_size = 0;
+    s.gvis_shift = 0;
     return s;
 }
 
@@ -95,11 +101,26 @@ __device__ __forceinline__ void stage_issue(const GraphView& g, Stager& stg, con
     __syncwarp();
     if (lane < nrows) stage_copy(stg, stg.buf + lane * kSegPitch, g.vectors + (size_t)copy_id * g.pitch + f0, (uint32_t)(nfl * 4));
 #else
-    if (lane * 4 < nfl) {
-        const float* src0 = g.vectors + f0 + lane * 4;
-        float* dst0 = stg.buf + lane * 4;
-#pragma unroll 4
-        for (int r = 0; r < nrows; ++r) cp_async_16(dst0 + r * kSegPitch, src0 + (size_t)ids[base + r] * g.pitch);
+    // Lane r fetches the id of row r once; every row then costs one SHFL, one 32x32->64 multiply-add for the address
+    // and one LDGSTS (16 B per lane = the whole row per instruction).
+    const int myid = lane < nrows ? ids[base + lane] : 0;
+    const char* src0 = reinterpret_cast<const char*>(g.vectors) + (size_t)(f0 + lane * 4) * 4;
+    const uint32_t dst0 = stg.buf_s + lane * 16;
+    const unsigned pitch_bytes = (unsigned)g.pitch * 4u;
+    const bool act = lane * 4 < nfl;  // lanes beyond the row length copy nothing
+    const int limit = act ? nrows : 0;
+    if (nrows == kStageRows) {        // warp-uniform: the shuffles below stay convergent
+#pragma unroll
+        for (int r = 0; r < kStageRows; ++r) {
+            const unsigned id = (unsigned)__shfl_sync(FULL, myid, r);
+            if (act) cp_async_16s(dst0 + r * (kSegPitch * 4), src0 + (size_t)id * pitch_bytes);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kStageRows; ++r) {
+            const unsigned id = (unsigned)__shfl_sync(FULL, myid, r);
+            if (r < limit) cp_async_16s(dst0 + r * (kSegPitch * 4), src0 + (size_t)id * pitch_bytes);
+        }
     }
 #endif
 }
@@ -238,25 +259,37 @@ __device__ __forceinline__ bool list_insert(u64* list, BeamState& st, u64 key, i
         if (pos < st.cursor) st.cursor = pos;
         return true;
     }
-    if (n <= 256) {
-        // same single pass with up to eight registers per lane (construction: ef = MaxCandidates ~ 100-200)
-        u64 v[8];
-        int pos = 0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int idx = c * 32 + lane;
-            v[c] = idx < n ? list[idx] : ~0ull;
-            pos += __popc(__ballot_sync(FULL, v[c] < key));
+    if (n <= 1024) {
+        // Two-level search (construction: ef = MaxCandidates ~ 100-200): lane c looks at the LAST entry of chunk c
+        // (32 entries per chunk), the ballot names the first chunk that is not entirely below the key, a second
+        // ballot over that chunk gives the position.  Only the chunks from there to the end are shifted.
+        const int nch = (n + 31) >> 5;
+        u64 bnd = ~0ull;
+        if (lane < nch) bnd = list[min(lane * 32 + 31, n - 1)];
+        const int ci = __popc(__ballot_sync(FULL, bnd < key));  // chunks entirely below the key
+        int pos = n;
+        u64 v = ~0ull, at = ~0ull;
+        if (ci < nch) {
+            const int idx = ci * 32 + lane;
+            if (idx < n) v = list[idx];
+            const int off = __popc(__ballot_sync(FULL, v < key));  // < 32: the chunk's last entry is >= key
+            pos = ci * 32 + off;
+            at = __shfl_sync(FULL, v, off);  // list[pos]
         }
-        const u64 at = pos < n ? list[pos] : ~0ull;
-        __syncwarp();  // every lane has read list[pos] before any lane overwrites it below
-        if ((at >> 1) == (key >> 1)) return false;
+        if ((at >> 1) == (key >> 1)) return false;  // same distance bits + id
         if (pos >= st.ef) return false;
-        const int last = (n == st.ef) ? n - 1 : n;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int idx = c * 32 + lane;
-            if (idx >= pos && idx < last) list[idx + 1] = v[c];
+        const int last = (n == st.ef) ? n - 1 : n;  // entries [pos, last) move up by one
+        __syncwarp();                               // every lane has read its entries before any is overwritten
+        if (last > pos) {
+            for (int c = (last - 1) >> 5; c > ci; --c) {  // top chunk first: its successor has already moved
+                const int idx = c * 32 + lane;
+                u64 w = 0;
+                if (idx < last) w = list[idx];
+                __syncwarp();
+                if (idx < last) list[idx + 1] = w;
+            }
+            const int idx = ci * 32 + lane;
+            if (idx >= pos && idx < last) list[idx + 1] = v;
         }
         if (lane == 0) list[pos] = key;
         __syncwarp();
@@ -298,6 +331,31 @@ __device__ __forceinline__ bool vis_test_and_set(const WarpScratch& s, int id) {
     if (v0 == tag || v1 == tag) return false;
     s.vis[2 * b + 1] = v0;
     s.vis[2 * b] = tag;
+    return true;
+}
+
+// Exact second level behind the shared-memory table (construction, where a search touches thousands of nodes and a
+// forgetful table re-evaluates ~60 % of them): a per-warp open-addressing set in global memory (L2 atomics).  Still
+// "never invents": when 16 probes find neither the id nor a free slot the node is simply evaluated again.
+__device__ __forceinline__ void gvis_attach(WarpScratch& s, uint32_t* table, int slots) {
+    s.gvis = table;
+    s.gvis_size = slots;
+    s.gvis_shift = 32 - (31 - __clz(slots));
+}
+__device__ __forceinline__ void gvis_clear(const WarpScratch& s, int lane) {
+    uint4* t = reinterpret_cast<uint4*>(s.gvis);
+    for (int i = lane; i < (s.gvis_size >> 2); i += 32) t[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+}
+__device__ __forceinline__ bool gvis_test_and_set(const WarpScratch& s, int id) {
+    const uint32_t tag = (uint32_t)id + 1u;
+    uint32_t slot = (tag * 0x9E3779B1u) >> s.gvis_shift;
+    for (int p = 0; p < 16; ++p) {
+        const uint32_t old = atomicCAS(s.gvis + slot, 0u, tag);
+        if (old == 0u) return true;
+        if (old == tag) return false;
+        slot = (slot + 1u) & (uint32_t)(s.gvis_size - 1);
+    }
     return true;
 }
 
@@ -387,8 +445,12 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
     st.far_ord = 0xFFFFFFFFu;
     st.cursor = 0;
     vis_clear(s, lane);
+    if (s.gvis != nullptr) gvis_clear(s, lane);
     list_insert(s.list, st, make_key(entry_d, entry), lane);
-    if (lane == 0) vis_test_and_set(s, entry);
+    if (lane == 0) {
+        vis_test_and_set(s, entry);
+        if (s.gvis != nullptr) gvis_test_and_set(s, entry);
+    }
     __syncwarp();
     int guess_id = -1, guess_nb = -1;  // adjacency word [lane] of the candidate expected to be expanded next
 
@@ -421,6 +483,7 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
             deg += __popc(__ballot_sync(FULL, nb >= 0));
             bool fresh = false;
             if (nb >= 0) fresh = vis_test_and_set(s, nb);
+            if (s.gvis != nullptr && fresh) fresh = gvis_test_and_set(s, nb);
             const unsigned mk = __ballot_sync(FULL, fresh);
             if (fresh) s.cand_id[m + __popc(mk & ((1u << lane) - 1u))] = nb;
             m += __popc(mk);

@@ -23,19 +23,25 @@ namespace hnsw {
 
 struct BuildScratch {
     WarpScratch s;
-    float* cvec;  // [pitch] second vector buffer (heuristic: the candidate under test)
+    float* cvec;  // [2][pitch] vector buffers of the heuristic (the vector under test, double-buffered)
     int* sel;     // [sel_cap] selected neighbour ids
 };
 
+// Cycle / work counters of the construction kernels (d_build_prof, 16 words; Index::build_profile()).
+enum BuildProf : int {
+    BP_INSERTS = 0, BP_CYC_DESCENT, BP_CYC_SEARCH, BP_CYC_SELECT, BP_NDIST_SEARCH, BP_NDIST_SELECT,
+    BP_CYC_LINK, BP_CYC_PRUNE, BP_PRUNES, BP_NDIST_PRUNE, BP_CYC_LOCK, BP_CYC_SELECT_KERNEL, BP_LINKS, BP_WORDS
+};
+
 __host__ __device__ inline size_t build_scratch_bytes(int pitch, int cap, int vis_size, int cand_cap, int sel_cap) {
-    return warp_scratch_bytes(pitch, cap, vis_size, cand_cap) + (((size_t)((pitch + 3) & ~3) * 4 + (size_t)sel_cap * 4 + 127) & ~(size_t)127);
+    return warp_scratch_bytes(pitch, cap, vis_size, cand_cap) + (((size_t)((pitch + 3) & ~3) * 8 + (size_t)sel_cap * 4 + 127) & ~(size_t)127);
 }
 __device__ __forceinline__ BuildScratch carve_build(unsigned char* base, int pitch, int cap, int vis_size, int cand_cap, int sel_cap, int lane) {
     BuildScratch b;
     b.s = carve_scratch(base, pitch, cap, vis_size, cand_cap, lane);
     base += warp_scratch_bytes(pitch, cap, vis_size, cand_cap);
     b.cvec = reinterpret_cast<float*>(base);
-    base += (size_t)((pitch + 3) & ~3) * 4;
+    base += (size_t)((pitch + 3) & ~3) * 8;
     b.sel = reinterpret_cast<int*>(base);
     return b;
 }
@@ -49,9 +55,10 @@ __device__ __forceinline__ void load_vector(const GraphView& g, int id, float* d
 
 // Heuristic.cs:11-46 on the sorted list[0..n): returns the number selected (ids in b.sel, ascending
 // by distance).  Caller handles the n < maxE early-return case.
+// Long rows (more than one staging segment): candidate by candidate, the selected rows re-staged for each.
 template <int METRIC>
-__device__ __forceinline__ int select_neighbors(const GraphView& g, BuildScratch& b, const u64* list, int n, int maxE, int lane,
-                                                WarpCounters& wc) {
+__device__ __forceinline__ int select_neighbors_long(const GraphView& g, BuildScratch& b, const u64* list, int n, int maxE, int lane,
+                                                     unsigned& ndist) {
     int nsel = 0;
     for (int i = 0; i < n && nsel < maxE; ++i) {
         const u64 e = list[i];
@@ -63,7 +70,7 @@ __device__ __forceinline__ int select_neighbors(const GraphView& g, BuildScratch
             double cn = 0.0;
             if (METRIC == COSINE) cn = __ldg(g.norm_sqrt + c);
             batch_dist_to<METRIC>(g, b.s.stg, b.cvec, cn, b.sel, b.s.cand_dist, nsel, lane);
-            wc.ndist += nsel;
+            ndist += nsel;
             bool rej = false;
             for (int j = lane; j < nsel; j += 32) rej |= b.s.cand_dist[j] < cd;  // strict, Heuristic.cs:34
             ok = !__any_sync(FULL, rej);
@@ -78,6 +85,98 @@ __device__ __forceinline__ int select_neighbors(const GraphView& g, BuildScratch
     return nsel;
 }
 
+// distance between one staged row (this lane pair's) and a vector in shared memory; both lanes of the pair get it
+template <int METRIC>
+__device__ __forceinline__ float staged_row_dist(const GraphView& g, const float* row, const float* q, double an, double qn, bool active, int h) {
+    constexpr bool SQ = METRIC == SQ_EUCLID;
+    const int nfull = g.dim >> 3, ntail = g.dim - (nfull << 3);
+    PairAcc acc = {0.f, 0.f, 0.f, 0.f};
+    if (active) pair_accumulate<SQ>(acc, row, q, nfull, h);
+    float r = pair_hsum<SQ>(acc);
+    if (active && ntail > 0) r = pair_tail<SQ>(r, row + (nfull << 3), q + (nfull << 3), ntail);
+    return metric_finish<METRIC>(r, an, qn);
+}
+
+// Rows of one staging segment: the sorted candidates are taken in WINDOWS of 16.  A window's rows are staged once
+// (one lane pair per candidate); every neighbour selected before the window is streamed through a double-buffered
+// vector slot (cp.async, the next one in flight under the current pass) and tested against all 16 rows in one pass;
+// then the window is resolved in order, a newly selected candidate being tested against the later ones straight out
+// of the staging buffer.  A candidate is dropped at the first selected neighbour that is strictly closer to it than
+// the base vector is (Heuristic.cs:31-35), so it is evaluated against exactly the neighbours the reference tries.
+template <int METRIC>
+__device__ __forceinline__ int select_neighbors_windowed(const GraphView& g, BuildScratch& b, const u64* list, int n, int maxE, int lane,
+                                                         unsigned& ndist) {
+    WarpScratch& s = b.s;
+    const int h = lane & 1, grp = lane >> 1;
+    const int pitch4 = g.pitch >> 2;
+    int nsel = 0;
+    for (int w0 = 0; w0 < n && nsel < maxE; w0 += kStageRows) {
+        const int nw = min(kStageRows, n - w0);
+        if (lane < nw) s.cand_id[lane] = key_id(list[w0 + lane]);
+        __syncwarp();
+        stage_issue(g, s.stg, s.cand_id, 0, nw, 0, g.pitch, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int nsel0 = nsel;
+        if (nsel0 > 0 && lane < pitch4) cp_async_16(b.cvec + lane * 4, g.vectors + (size_t)b.sel[0] * g.pitch + lane * 4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const bool have = grp < nw;
+        const u64 mykey = have ? list[w0 + grp] : 0ull;
+        const int myid = key_id(mykey);
+        const float cd = key_dist(mykey);
+        double an = 0.0;
+        if (METRIC == COSINE && have) an = __ldg(g.norm_sqrt + myid);
+        const float* row = s.stg.buf + grp * kSegPitch;
+        bool rej = !have;
+        // neighbours selected in earlier windows
+        for (int j = 0; j < nsel0; ++j) {
+            if (__all_sync(FULL, rej)) break;
+            float* qv = b.cvec + (j & 1) * g.pitch;
+            if (j + 1 < nsel0) {
+                if (lane < pitch4) cp_async_16(b.cvec + ((j + 1) & 1) * g.pitch + lane * 4, g.vectors + (size_t)b.sel[j + 1] * g.pitch + lane * 4);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncwarp();
+            double qn = 0.0;
+            if (METRIC == COSINE) qn = __ldg(g.norm_sqrt + b.sel[j]);
+            const bool act = !rej;
+            ndist += __popc(__ballot_sync(FULL, act && h == 0));
+            const float d = staged_row_dist<METRIC>(g, row, qv, an, qn, act, h);
+            if (act && d < cd) rej = true;  // strict, Heuristic.cs:34
+            __syncwarp();                   // the slot of j is free for the copy issued two iterations later
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        // the window itself, in order
+        for (int gi = 0; gi < nw; ++gi) {
+            if (__shfl_sync(FULL, (int)rej, gi * 2)) continue;
+            if (lane == 0) b.sel[nsel] = s.cand_id[gi];
+            ++nsel;
+            if (nsel == maxE) break;
+            const bool act = !rej && grp > gi;
+            const unsigned later = __ballot_sync(FULL, act && h == 0);
+            if (!later) continue;
+            ndist += __popc(later);
+            double qn = 0.0;
+            if (METRIC == COSINE) qn = __ldg(g.norm_sqrt + s.cand_id[gi]);
+            const float d = staged_row_dist<METRIC>(g, row, s.stg.buf + gi * kSegPitch, an, qn, act, h);
+            if (act && d < cd) rej = true;
+        }
+        __syncwarp();  // staged rows, cand_id and sel are consistent before the next window overwrites them
+    }
+    return nsel;
+}
+
+template <int METRIC>
+__device__ __forceinline__ int select_neighbors(const GraphView& g, BuildScratch& b, const u64* list, int n, int maxE, int lane, unsigned& ndist) {
+#ifndef HNSW_STAGE_BULK
+    if (g.pitch <= kSegFloats) return select_neighbors_windowed<METRIC>(g, b, list, n, maxE, lane, ndist);
+#endif
+    return select_neighbors_long<METRIC>(g, b, list, n, maxE, lane, ndist);
+}
+
 __device__ __forceinline__ int* row_ptr_mut(const GraphView& g, int id, int layer, int& stride) {
     if (layer == 0) {
         stride = g.stride0;
@@ -90,12 +189,16 @@ __device__ __forceinline__ int* row_ptr_mut(const GraphView& g, int id, int laye
 template <int METRIC>
 __global__ void __launch_bounds__(kThreads, 4)
 build_select_kernel(GraphView g, const int* __restrict__ levels, int first, int count, int efc, int list_cap, int vis_size, int cand_cap,
-                    int sel_cap, unsigned* work_counter) {
+                    int sel_cap, unsigned* work_counter, u64* prof, uint32_t* gvis, int gvis_slots) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, vis_size, cand_cap, sel_cap);
     BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, vis_size, cand_cap, sel_cap, lane);
     WarpScratch& s = b.s;
+    if (gvis_slots > 0) gvis_attach(s, gvis + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * gvis_slots, gvis_slots);
+    long long cyc_descent = 0, cyc_search = 0, cyc_select = 0;
+    unsigned n_items = 0, nd_search = 0, nd_select = 0;
+    const long long t_begin = clock64();
 
     for (;;) {
         unsigned wi = 0;
@@ -104,7 +207,9 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, int first, int 
         if (wi >= (unsigned)count) break;
         const int v = first + (int)wi;
         const int level = __ldg(levels + v);
+        ++n_items;
 
+        long long t0 = clock64();
         load_vector(g, v, s.q, lane);
         double qn = 0.0;
         if (METRIC == COSINE) qn = __ldg(g.norm_sqrt + v);
@@ -113,10 +218,15 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, int first, int 
         int cur = g.entry;
         float cur_d = single_dist<METRIC>(g, s, qn, cur, lane);
         for (int layer = g.top_layer; layer > level; --layer) greedy_layer<METRIC>(g, s, qn, layer, cur, cur_d, lane, wc);
+        long long t1 = clock64();
+        cyc_descent += t1 - t0;
 
         for (int layer = min(level, g.top_layer); layer >= 0; --layer) {
             BeamState st;
+            t0 = clock64();
             beam_search<METRIC>(g, s, qn, layer, cur, cur_d, efc, st, lane, wc);
+            t1 = clock64();
+            cyc_search += t1 - t0;
             const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
             int nsel;
             int next;
@@ -130,10 +240,11 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, int first, int 
                 next_d = key_dist(s.list[st.n - 1]);
                 __syncwarp();
             } else {
-                nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, wc);
+                nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, nd_select);
                 next = key_id(s.list[0]);  // the closest candidate is always selected first
                 next_d = key_dist(s.list[0]);
             }
+            cyc_select += clock64() - t1;
             int stride;
             int* row = row_ptr_mut(g, v, layer, stride);
             for (int j = lane; j < stride; j += 32) row[j] = j < nsel ? b.sel[j] : -1;
@@ -141,7 +252,17 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, int first, int 
             cur = next;
             cur_d = next_d;
         }
+        nd_search += wc.ndist;
         __syncwarp();
+    }
+    if (lane == 0 && n_items > 0) {
+        atomicAdd(prof + BP_INSERTS, (u64)n_items);
+        atomicAdd(prof + BP_CYC_DESCENT, (u64)cyc_descent);
+        atomicAdd(prof + BP_CYC_SEARCH, (u64)cyc_search);
+        atomicAdd(prof + BP_CYC_SELECT, (u64)cyc_select);
+        atomicAdd(prof + BP_NDIST_SEARCH, (u64)nd_search);
+        atomicAdd(prof + BP_NDIST_SELECT, (u64)nd_select);
+        atomicAdd(prof + BP_CYC_SELECT_KERNEL, (u64)(clock64() - t_begin));
     }
 }
 
@@ -167,12 +288,15 @@ __device__ __forceinline__ void unlock_node(int* locks, int n, int lane) {
 template <int METRIC>
 __global__ void __launch_bounds__(kThreads, 4)
 build_link_kernel(GraphView g, const int* __restrict__ levels, int first, int count, int list_cap, int cand_cap, int sel_cap,
-                  unsigned* work_counter, int* error_flag) {
+                  unsigned* work_counter, int* error_flag, u64* prof) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, 64, cand_cap, sel_cap);
     BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, 64, cand_cap, sel_cap, lane);
     WarpScratch& s = b.s;
+    long long cyc_prune = 0, cyc_lock = 0;
+    unsigned n_prunes = 0, nd_prune = 0, n_links = 0;
+    const long long t_begin = clock64();
 
     for (;;) {
         unsigned wi = 0;
@@ -181,7 +305,6 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, int first, int co
         if (wi >= (unsigned)count) break;
         const int v = first + (int)wi;
         const int level = __ldg(levels + v);
-        WarpCounters wc;
 
         for (int layer = min(level, g.top_layer); layer >= 0; --layer) {
             const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
@@ -190,7 +313,10 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, int first, int co
             for (int t = 0; t < vstride; ++t) {
                 const int n = __ldcg(vrow + t);
                 if (n < 0) break;
+                const long long tl = clock64();
                 if (!lock_node(g.locks, n, lane, error_flag)) continue;
+                cyc_lock += clock64() - tl;
+                ++n_links;
                 int stride;
                 int* row = row_ptr_mut(g, n, layer, stride);
                 // current row of n, read past L1 (other SMs update it under the same lock)
@@ -206,23 +332,34 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, int first, int co
                     if (lane == 0) row[cnt] = v;  // EdgeList.Add, GraphConnector.cs:207
                 } else {
                     // PruneOverflow (GraphConnector.cs:222-262): heuristic over the row plus the new link
+                    const long long tp = clock64();
+                    ++n_prunes;
                     if (lane == 0) s.cand_id[cnt] = v;
                     const int m = cnt + 1;
                     load_vector(g, n, s.q, lane);
                     double nn = 0.0;
                     if (METRIC == COSINE) nn = __ldg(g.norm_sqrt + n);
                     batch_dist<METRIC>(g, s, nn, m, lane);
-                    wc.ndist += m;
+                    nd_prune += m;
                     BeamState st;
                     st.n = 0; st.ef = list_cap; st.far_ord = 0xFFFFFFFFu; st.cursor = 0;
                     for (int j = 0; j < m; ++j) list_insert(s.list, st, make_key(s.cand_dist[j], s.cand_id[j]), lane);
-                    const int nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, wc);
+                    const int nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, nd_prune);
                     for (int j = lane; j < stride; j += 32) row[j] = j < nsel ? b.sel[j] : -1;
+                    cyc_prune += clock64() - tp;
                 }
                 unlock_node(g.locks, n, lane);
             }
         }
         __syncwarp();
+    }
+    if (lane == 0 && n_links > 0) {
+        atomicAdd(prof + BP_CYC_LINK, (u64)(clock64() - t_begin));
+        atomicAdd(prof + BP_CYC_PRUNE, (u64)cyc_prune);
+        atomicAdd(prof + BP_CYC_LOCK, (u64)cyc_lock);
+        atomicAdd(prof + BP_PRUNES, (u64)n_prunes);
+        atomicAdd(prof + BP_NDIST_PRUNE, (u64)nd_prune);
+        atomicAdd(prof + BP_LINKS, (u64)n_links);
     }
 }
 
@@ -251,9 +388,17 @@ static int persistent_grid(Kern kern, size_t smem_per_warp, const Tuning& t, int
     return std::max(1, std::min(need, sms * per_sm));
 }
 
+// slots of the global visited set each warp of the select kernel gets (0 = not used)
+static int gvis_slots_per_warp(const uint32_t* d_gvis, size_t gvis_words, size_t warps, const Tuning& t) {
+    if (d_gvis == nullptr || t.vis_global_build <= 0 || warps == 0) return 0;
+    int slots = pow2_ge(t.vis_global_build);
+    while (slots >= 1024 && (size_t)slots * warps > gvis_words) slots >>= 1;
+    return slots >= 1024 ? slots : 0;
+}
+
 // d_work_counter: three consecutive words -- [0] select work, [1] link work, [2] error flag
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int first, int count, int efc, unsigned* d_work_counter,
-                        const Tuning& t, cudaStream_t stream) {
+                        u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream) {
     if (count <= 0) return;
     const int maxE0 = 2 * g.max_edges;
     const int list_cap_sel = std::max(efc, 1);
@@ -262,6 +407,7 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int
     const int sel_cap = std::max(maxE0, list_cap_sel < maxE0 ? list_cap_sel : maxE0);
     // small table: shared memory per warp decides the occupancy of this latency-bound kernel (see search_kernels.cu)
     int vis = t.vis_size_build > 0 ? std::max(64, pow2_ge(t.vis_size_build)) : std::min(2048, std::max(256, pow2_ge(2 * efc)));
+    if (t.vis_size_build <= 0 && d_gvis != nullptr && t.vis_global_build > 0) vis = 256;  // first-level filter only
     const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap);   // per warp
     const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap);  // per warp
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, 2 * sizeof(unsigned), stream));
@@ -270,11 +416,13 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int
     {                                                                                                                           \
         int w1 = 0, w2 = 0;                                                                                                     \
         const int g1 = persistent_grid(build_select_kernel<M>, smem_sel, t, count, w1);                                        \
+        const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                        \
         build_select_kernel<M><<<g1, 32 * w1, smem_sel * w1, stream>>>(g, d_levels, first, count, efc, list_cap_sel, vis,      \
-                                                                       cand_cap, sel_cap, d_work_counter);                     \
+                                                                       cand_cap, sel_cap, d_work_counter, d_build_prof,        \
+                                                                       d_gvis, gslots);                                        \
         const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, count, w2);                                         \
         build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, stream>>>(g, d_levels, first, count, list_cap_link, cand_cap,      \
-                                                                      sel_cap, d_work_counter + 1, err);                       \
+                                                                      sel_cap, d_work_counter + 1, err, d_build_prof);         \
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_BUILD(SQ_EUCLID) break;

@@ -237,6 +237,13 @@ int hnsw_get_stats(hnsw_handle handle, hnsw_stats* out) {
     return 0;
     HNSW_CATCH(-1)
 }
+int hnsw_get_build_profile(hnsw_handle handle, unsigned long long* out16, int reset) {
+    HNSW_TRY
+    if (!out16) throw std::invalid_argument("null output");
+    get(handle)->build_profile(out16, reset != 0);
+    return 0;
+    HNSW_CATCH(-1)
+}
 int hnsw_set_tuning(hnsw_handle handle, const char* key, int value) {
     HNSW_TRY
     get(handle)->set_tuning(key ? key : "", value);

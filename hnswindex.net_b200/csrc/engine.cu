@@ -88,6 +88,8 @@ Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), par
     HNSW_CUDA_CHECK(cudaEventCreate(&ev1_));
     HNSW_CUDA_CHECK(cudaMalloc(&d_counters_, 8 * sizeof(unsigned)));
     HNSW_CUDA_CHECK(cudaMemset(d_counters_, 0, 8 * sizeof(unsigned)));
+    HNSW_CUDA_CHECK(cudaMalloc(&d_build_prof_, 16 * sizeof(u64)));
+    HNSW_CUDA_CHECK(cudaMemset(d_build_prof_, 0, 16 * sizeof(u64)));
     stride0_ = stride_for(2 * params_.MaxEdges);
     strideU_ = stride_for(params_.MaxEdges);
     capacity_ = std::max(1, params_.CollectionSize);
@@ -96,7 +98,7 @@ Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), par
 Index::~Index() {
     cudaSetDevice(device_);
     cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
-    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_);
+    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -106,6 +108,7 @@ Index::~Index() {
 void Index::set_tuning(const std::string& key, int value) {
     if (key == "vis_size_search") tuning_.vis_size_search = value;
     else if (key == "vis_size_build") tuning_.vis_size_build = value;
+    else if (key == "vis_global_build") tuning_.vis_global_build = value;
     else if (key == "blocks_per_sm") tuning_.blocks_per_sm = value;
     else if (key == "flags") tuning_.flags = value;
     else if (key == "zero_copy") zero_copy_ = value != 0;
@@ -131,6 +134,14 @@ GraphView Index::view() const {
     g.top_layer = top_;
     g.count = length_;
     return g;
+}
+
+void Index::build_profile(unsigned long long out[16], bool reset) {
+    std::lock_guard<std::mutex> lock(mu_);
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    HNSW_CUDA_CHECK(cudaMemcpy(out, d_build_prof_, 16 * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (reset) HNSW_CUDA_CHECK(cudaMemset(d_build_prof_, 0, 16 * sizeof(u64)));
 }
 
 void Index::ensure_dim(int dim) {
@@ -245,6 +256,16 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_ + first, upper_off_.data() + first, (size_t)nnew * 4, cudaMemcpyHostToDevice, stream_));
     if (metric_ == COSINE) launch_item_norms(d_vectors_, pitch_, dim_, first, nnew, d_norms_, stream_);
 
+    if (tuning_.vis_global_build > 0) {  // room for 16 warps per SM
+        int slots = 1024;
+        while (slots < tuning_.vis_global_build) slots <<= 1;
+        const size_t words = (size_t)device_sm_count() * 16 * slots;
+        if (words > gvis_words_) {
+            cudaFree(d_gvis_); d_gvis_ = nullptr; gvis_words_ = 0;
+            HNSW_CUDA_CHECK(cudaMalloc(&d_gvis_, words * sizeof(uint32_t)));
+            gvis_words_ = words;
+        }
+    }
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     int done = 0;
     while (done < nnew) {
@@ -263,7 +284,8 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
             while (done + batch < nnew && batch < b && levels_[v + batch] <= top_) ++batch;
         }
         length_ = v;  // nodes visible to this batch
-        launch_build_batch((int)metric_, view(), d_levels_, v, batch, params_.MaxCandidates, d_counters_, tuning_, stream_);
+        launch_build_batch((int)metric_, view(), d_levels_, v, batch, params_.MaxCandidates, d_counters_, d_build_prof_, d_gvis_, gvis_words_, tuning_,
+                           stream_);
         stats_.build_launches += 2;
         if (new_top) {  // GraphConnector.cs:36-41
             entry_ = v;

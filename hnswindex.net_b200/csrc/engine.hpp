@@ -72,6 +72,8 @@ public:
     void set_stream(cudaStream_t s);
     void enable_stats(bool on) { collect_stats_ = on; }
     IndexStats stats() const { return stats_; }
+    // cycle / work counters of the construction kernels since creation or the last reset (build_kernels.cu BuildProf)
+    void build_profile(unsigned long long out[16], bool reset);
     void export_graph(HostGraph& g);  // device -> host copy of the whole index
     int device() const { return device_; }
 
@@ -97,8 +99,8 @@ private:
     bool collect_stats_ = false;
     bool zero_copy_ = true;        // page-locked caller buffers are read / written in place by the kernel
     IndexStats stats_;
-    int build_batch_max_ = 4096;   // new nodes per build launch (upper bound)
-    int build_batch_ratio_ = 32;   // ... and at most 1/ratio of the nodes already linked
+    int build_batch_max_ = 16384;  // new nodes per build launch (upper bound)
+    int build_batch_ratio_ = 16;   // ... and at most 1/ratio of the nodes already linked
 
     std::vector<int> levels_, upper_off_;
     int upper_rows_ = 0, upper_rows_cap_ = 0;
@@ -111,6 +113,9 @@ private:
     int* d_locks_ = nullptr;
     int* d_levels_ = nullptr;
     unsigned* d_counters_ = nullptr;  // [0..2] build, [3] search
+    u64* d_build_prof_ = nullptr;     // [16]
+    uint32_t* d_gvis_ = nullptr;      // per-warp visited sets of the build search (allocated by the first add)
+    size_t gvis_words_ = 0;
 
     float* d_q_ = nullptr;
     int* d_ids_ = nullptr;

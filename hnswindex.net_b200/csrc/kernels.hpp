@@ -10,6 +10,8 @@ namespace hnsw {
 struct Tuning {
     int vis_size_search = 0;  // 0 = derive from ef
     int vis_size_build = 0;
+    int vis_global_build = 0;     // slots per warp of an exact global-memory visited set for the build search (0 = off;
+                                  // -23 % evaluations but one more L2 round trip per expansion: no net gain at 1M x 128)
     int blocks_per_sm = 0;    // 0 = occupancy query
     int flags = 2;            // bit 0: L2-prefetch rows of accepted candidates (no gain); bit 1: guess-row load
 };
@@ -32,8 +34,9 @@ void launch_item_norms(const float* d_vectors, int pitch, int dim, int first, in
 // K4+K5: for new nodes [first, first+count): descent, per-layer beam search (ef = MaxCandidates) against the
 // graph as it stands, relative-neighbour selection, write the node's own rows.
 // K6: reverse links with per-node locks and overflow pruning.
+// d_build_prof: 16 u64 cycle / work counters accumulated by the kernels (build_kernels.cu BuildProf).
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int first, int count, int ef_construction,
-                        unsigned* d_work_counter, const Tuning& t, cudaStream_t stream);
+                        unsigned* d_work_counter, u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream);
 
 // RangeQuery (HNSWIndex.cs:144-168): traversal of all in-range nodes reachable from the layer-0 entry.  Work item w handles
 // query qmap[w] (or w when qmap is null); out_keys [nwork][cap] unsorted (distance|id) keys, out_count[w] = result size or -1

@@ -24,12 +24,14 @@ constexpr int kStageBytes = kStageRows * kSegPitch * 4 + 16;  // + the mbarrier 
 
 struct Stager {
     float* buf;        // [kStageRows][kSegPitch]
+    uint32_t buf_s;    // shared-space address of buf
     uint32_t bar;      // shared-space address of the warp's mbarrier
     uint32_t phase;    // parity of the phase to wait for next
 };
 
 __device__ __forceinline__ void stager_init(Stager& st, unsigned char* base, int lane) {
     st.buf = reinterpret_cast<float*>(base);
+    st.buf_s = (uint32_t)__cvta_generic_to_shared(base);
     st.bar = (uint32_t)__cvta_generic_to_shared(base + kStageRows * kSegPitch * 4);
     st.phase = 0;
     if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st.bar) : "memory");
@@ -71,6 +73,10 @@ __device__ __forceinline__ void stage_wait(Stager& st) {
 __device__ __forceinline__ void cp_async_16(float* dst, const float* src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+// same with the destination already a shared-space address and the source a byte pointer
+__device__ __forceinline__ void cp_async_16s(uint32_t dst_s, const char* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;" ::: "memory");

@@ -71,6 +71,7 @@ def _load():
         "hnsw_merge_topk_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
         "hnsw_enable_stats": (ct.c_int, [ct.c_void_p, ct.c_int]),
         "hnsw_get_stats": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
+        "hnsw_get_build_profile": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
         "hnsw_set_tuning": (ct.c_int, [ct.c_void_p, ct.c_char_p, ct.c_int]),
         "hnsw_export_layer0": (ct.c_int, [ct.c_void_p, i32p, i32p, i32p, i32p]),
         "hnsw_export_layer": (ct.c_int, [ct.c_void_p, ct.c_int, i32p, i32p]),
@@ -278,6 +279,15 @@ class Index:
         s = _Stats()
         _check(lib.hnsw_get_stats(self._h, ct.byref(s)))
         return {f: getattr(s, f) for f, _ in s._fields_}
+
+    _BUILD_PROFILE_FIELDS = ("inserts", "cyc_descent", "cyc_search", "cyc_select", "ndist_search", "ndist_select", "cyc_link_kernel",
+                             "cyc_prune", "prunes", "ndist_prune", "cyc_lock", "cyc_select_kernel", "links")
+
+    def build_profile(self, reset: bool = False) -> dict:
+        """Cycle / work counters of the construction kernels (per-warp SM cycles summed over warps)."""
+        out = (ct.c_ulonglong * 16)()
+        _check(lib.hnsw_get_build_profile(self._h, out, int(reset)))
+        return {f: int(out[i]) for i, f in enumerate(self._BUILD_PROFILE_FIELDS)}
 
     def set_tuning(self, key: str, value: int) -> None:
         _check(lib.hnsw_set_tuning(self._h, key.encode(), int(value)))

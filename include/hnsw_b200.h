@@ -133,6 +133,11 @@ typedef struct hnsw_stats {
 } hnsw_stats;
 HNSW_API int hnsw_enable_stats(hnsw_handle handle, int on);
 HNSW_API int hnsw_get_stats(hnsw_handle handle, hnsw_stats* out);
+/* Construction profile since creation / the last reset, 16 words: {inserts, descent cycles, beam-search cycles,
+ * heuristic cycles, search distance evaluations, heuristic evaluations, link-kernel warp cycles, overflow-prune
+ * cycles, overflow prunes, prune evaluations, lock-wait cycles, select-kernel warp cycles, reverse links, 0...}.
+ * Cycles are per-warp SM clock cycles summed over warps. */
+HNSW_API int hnsw_get_build_profile(hnsw_handle handle, unsigned long long* out16, int reset);
 /* tuning knobs: "vis_size_search", "vis_size_build", "blocks_per_sm", "build_batch_max", "build_batch_ratio",
  * "flags", "zero_copy" (1 = page-locked caller buffers of hnsw_knn_query are accessed in place by the kernel) */
 HNSW_API int hnsw_set_tuning(hnsw_handle handle, const char* key, int value);

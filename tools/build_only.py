@@ -20,4 +20,11 @@ out = {"N": N, "build_s": round(tb, 3), "inserts_per_s": round(N / tb), "last_ad
 for ef in (32, 48, 64):
     ix.set_min_nn(ef); ids, _ = ix.knn_query(q, 10)
     out[f"recall@10_ef{ef}"] = round(float(np.mean([len(set(ids[i]) & set(gt[i])) / 10 for i in range(len(q))])), 4)
+bp = ix.build_profile()
+cyc = {k: v for k, v in bp.items() if k.startswith("cyc_")}
+sel_total = max(1, bp["cyc_select_kernel"]); link_total = max(1, bp["cyc_link_kernel"])
+out["profile"] = {"select_share": {k: round(bp[k] / sel_total, 3) for k in ("cyc_descent", "cyc_search", "cyc_select")},
+                  "link_share": {k: round(bp[k] / link_total, 3) for k in ("cyc_prune", "cyc_lock")},
+                  "select_vs_link_cycles": round(sel_total / link_total, 2),
+                  "per_insert": {k: round(bp[k] / max(1, bp["inserts"]), 1) for k in ("ndist_search", "ndist_select", "ndist_prune", "prunes", "links")}}
 print(json.dumps(out), flush=True)
