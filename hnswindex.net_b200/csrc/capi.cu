@@ -102,6 +102,44 @@ int hnsw_knn_query(hnsw_handle handle, const float* vectors, int count, int dim,
     HNSW_CATCH(-1)
 }
 
+int hnsw_knn_query_layer(hnsw_handle handle, const float* vectors, int count, int dim, int k, int layer, int* outIds, float* outDists) {
+    if (!handle) return 0;
+    HNSW_TRY
+    if (count > 0 && (vectors == nullptr || outIds == nullptr || outDists == nullptr)) throw std::invalid_argument("null buffer");
+    get(handle)->knn_query(vectors, count, dim, k, outIds, outDists, layer);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_multilayer_knn_query(hnsw_handle handle, const float* vectors, int count, int dim, int k, int maxLayer, int minLayer, int* outIds,
+                              float* outDists) {
+    HNSW_TRY
+    return get(handle)->multilayer_knn_query(vectors, count, dim, k, maxLayer, minLayer, outIds, outDists);
+    HNSW_CATCH(-1)
+}
+int hnsw_top_layer(hnsw_handle handle) { return handle ? reinterpret_cast<Index*>(handle)->top_layer() : -1; }
+int hnsw_entry_point(hnsw_handle handle) { return handle ? reinterpret_cast<Index*>(handle)->entry_point() : -1; }
+int hnsw_get_info(hnsw_handle handle, hnsw_layer_info* out, int maxLayers) {
+    HNSW_TRY
+    const auto info = get(handle)->get_info();
+    for (int i = 0; i < (int)info.size() && i < maxLayers && out != nullptr; ++i) {
+        const auto& s = info[i];
+        out[i].layerId = s.LayerId; out[i].nodesCount = s.NodesCount;
+        out[i].maxOutEdges = s.MaxOutEdges; out[i].minOutEdges = s.MinOutEdges;
+        out[i].maxInEdges = s.MaxInEdges; out[i].minInEdges = s.MinInEdges;
+        out[i].avgOutEdges = s.AvgOutEdges; out[i].avgInEdges = s.AvgInEdges;
+        out[i].outEdgesMedian = s.OutEdgesMedian; out[i].inEdgesMedian = s.InEdgesMedian;
+    }
+    return (int)info.size();
+    HNSW_CATCH(-1)
+}
+int hnsw_connected_components(hnsw_handle handle, int* counts, int maxLayers) {
+    HNSW_TRY
+    const auto c = get(handle)->connected_component_counts();
+    for (int i = 0; i < (int)c.size() && i < maxLayers && counts != nullptr; ++i) counts[i] = c[i];
+    return (int)c.size();
+    HNSW_CATCH(-1)
+}
+
 int hnsw_range_query(hnsw_handle handle, const float* vectors, int count, int dim, float range, void** outIds, void** outDists, int* counts) {
     if (!handle) return 0;
     try {

@@ -338,13 +338,15 @@ static T* pinned_alias(const T* host) {
     return reinterpret_cast<T*>(a.devicePointer);
 }
 
-void Index::knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
+void Index::knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists, int layer) {
     std::lock_guard<std::mutex> lock(mu_);
     if (count <= 0 || k < 1) return;
     if (length_ <= 0) {  // HNSWIndex.cs:109
         fill_empty(out_ids, out_dists, (size_t)count * k);
         return;
     }
+    // the reference indexes OutEdges[layer] of a node found on that layer: IndexOutOfRangeException beyond the top layer
+    if (layer < 0 || layer > top_) throw std::out_of_range("layer " + std::to_string(layer) + " does not exist (top layer is " + std::to_string(top_) + ")");
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
     ensure_query_scratch(count, k);
@@ -359,7 +361,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
         q_src = d_q_;
     }
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-    launch_knn_search((int)metric_, view(), q_src, count, k, ef, direct_out ? ids_dst : d_ids_, direct_out ? d_dst : d_dists_, d_counters_ + 3,
+    launch_knn_search((int)metric_, view(), q_src, count, k, ef, layer, direct_out ? ids_dst : d_ids_, direct_out ? d_dst : d_dists_, d_counters_ + 3,
                       collect_stats_ ? d_stats_ : nullptr, tuning_, stream_);
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     stats_.search_launches += 1;
@@ -383,7 +385,7 @@ void Index::knn_query_device(const float* d_queries, int count, int dim, int k, 
     if (collect_stats_) ensure_stats(count);
     const int ef = std::max(params_.MinNN, k);
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-    launch_knn_search((int)metric_, view(), d_queries, count, k, ef, d_ids, d_dists, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr, tuning_,
+    launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr, tuning_,
                       stream_);
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     stats_.search_launches += 1;
@@ -392,6 +394,28 @@ void Index::knn_query_device(const float* d_queries, int count, int dim, int k, 
     HNSW_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats_.last_search_ms = ms;
     if (collect_stats_) fetch_query_stats(count);
+}
+
+// MultiLayerKnnQuery (HNSWIndex.cs:173-187) for a batch of queries.  Returns the number of layers L = min(top, maxLayer) + 1;
+// outputs are [count][L][k] (pass null pointers to query L only).
+int Index::multilayer_knn_query(const float* queries, int count, int dim, int k, int max_layer, int min_layer, int* out_ids, float* out_dists) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (length_ <= 0 || k < 1) return 0;  // HNSWIndex.cs:176
+    if (max_layer < 0) throw std::out_of_range("maxLayer must not be negative");
+    const int top_l = std::min(top_, max_layer);
+    const int layers = top_l + 1;
+    if (out_ids == nullptr || out_dists == nullptr || count <= 0) return layers;
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    ensure_query_scratch(count, k * layers);
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
+    launch_multilayer_search((int)metric_, view(), d_q_, count, k, top_l, std::max(min_layer, 0), d_ids_, d_dists_, d_counters_ + 3, tuning_, stream_);
+    stats_.search_launches += 1;
+    const size_t n = (size_t)count * layers * k;
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids_, n * 4, cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists, d_dists_, n * 4, cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return layers;
 }
 
 void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
@@ -496,7 +520,7 @@ void Index::range_query(const float* queries, int count, int dim, float range, s
 // ---------------------------------------------------------------------------------------------
 // Serialize / Deserialize (HNSWIndex.cs:210-229)
 // ---------------------------------------------------------------------------------------------
-void Index::export_graph(HostGraph& g) {
+void Index::export_graph(HostGraph& g, bool with_vectors) {
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     g = HostGraph();
     g.params = params_;
@@ -508,16 +532,104 @@ void Index::export_graph(HostGraph& g) {
     g.strideU = strideU_;
     g.levels.assign(levels_.begin(), levels_.begin() + length_);
     g.upper_off.assign(upper_off_.begin(), upper_off_.begin() + length_);
-    g.vectors.resize((size_t)length_ * g.dim);
+    if (with_vectors) g.vectors.resize((size_t)length_ * g.dim);
     g.adj0.resize((size_t)length_ * stride0_);
     g.adjU.resize((size_t)upper_rows_ * strideU_);
     if (length_ > 0) {
-        HNSW_CUDA_CHECK(cudaMemcpy2DAsync(g.vectors.data(), (size_t)g.dim * 4, d_vectors_, (size_t)pitch_ * 4, (size_t)g.dim * 4, (size_t)length_,
-                                          cudaMemcpyDeviceToHost, stream_));
+        if (with_vectors)
+            HNSW_CUDA_CHECK(cudaMemcpy2DAsync(g.vectors.data(), (size_t)g.dim * 4, d_vectors_, (size_t)pitch_ * 4, (size_t)g.dim * 4, (size_t)length_,
+                                              cudaMemcpyDeviceToHost, stream_));
         HNSW_CUDA_CHECK(cudaMemcpyAsync(g.adj0.data(), d_adj0_, g.adj0.size() * 4, cudaMemcpyDeviceToHost, stream_));
         if (!g.adjU.empty()) HNSW_CUDA_CHECK(cudaMemcpyAsync(g.adjU.data(), d_adjU_, g.adjU.size() * 4, cudaMemcpyDeviceToHost, stream_));
         HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Diagnostics, host side from the exported adjacency
+// ---------------------------------------------------------------------------------------------
+namespace {
+const int* host_row(const HostGraph& g, int id, int layer, int& stride) {
+    if (layer == 0) { stride = g.stride0; return g.adj0.data() + (size_t)id * g.stride0; }
+    stride = g.strideU;
+    return g.adjU.data() + ((size_t)g.upper_off[id] + (layer - 1)) * g.strideU;
+}
+int median_like_reference(std::vector<int>& v) {  // HNSWInfo.cs:45-51
+    std::sort(v.begin(), v.end());
+    const size_t n = v.size();
+    return n % 2 == 0 ? (v[n / 2 - 1] + v[n / 2]) / 2 : v[n / 2];
+}
+}  // namespace
+
+std::vector<Index::LayerInfo> Index::get_info() {
+    std::lock_guard<std::mutex> lock(mu_);
+    std::vector<LayerInfo> out;
+    if (length_ <= 0) return out;
+    HostGraph g;
+    export_graph(g, false);
+    const bool has_in = params_.AllowRemovals;
+    for (int layer = 0; layer <= top_; ++layer) {
+        std::vector<int> outdeg, indeg_all(g.length, 0), ids;
+        for (int i = 0; i < g.length; ++i) {
+            if (g.levels[i] < layer) continue;
+            int stride;
+            const int* row = host_row(g, i, layer, stride);
+            int d = 0;
+            while (d < stride && row[d] >= 0) { indeg_all[row[d]]++; ++d; }
+            outdeg.push_back(d);
+            ids.push_back(i);
+        }
+        LayerInfo li{};
+        li.LayerId = layer;
+        li.NodesCount = (int)ids.size();
+        if (ids.empty()) { out.push_back(li); continue; }
+        std::vector<int> indeg;
+        for (int id : ids) indeg.push_back(indeg_all[id]);
+        auto stats = [](std::vector<int>& v, int& mx, int& mn, double& avg, int& med) {
+            mx = *std::max_element(v.begin(), v.end());
+            mn = *std::min_element(v.begin(), v.end());
+            long long sum = 0;
+            for (int x : v) sum += x;
+            avg = (double)sum / (double)v.size();
+            med = median_like_reference(v);
+        };
+        stats(outdeg, li.MaxOutEdges, li.MinOutEdges, li.AvgOutEdges, li.OutEdgesMedian);
+        if (has_in) stats(indeg, li.MaxInEdges, li.MinInEdges, li.AvgInEdges, li.InEdgesMedian);
+        out.push_back(li);
+    }
+    return out;
+}
+
+std::vector<int> Index::connected_component_counts() {
+    std::lock_guard<std::mutex> lock(mu_);
+    std::vector<int> counts;
+    if (length_ <= 0) return counts;
+    HostGraph g;
+    export_graph(g, false);
+    counts.assign(top_ + 1, 0);
+    std::vector<int> parent(g.length);
+    for (int layer = 0; layer <= top_; ++layer) {
+        for (int i = 0; i < g.length; ++i) parent[i] = i;
+        auto find = [&](int x) {
+            while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+            return x;
+        };
+        for (int i = 0; i < g.length; ++i) {
+            if (g.levels[i] < layer) continue;
+            int stride;
+            const int* row = host_row(g, i, layer, stride);
+            for (int j = 0; j < stride && row[j] >= 0; ++j) {
+                if (g.levels[row[j]] < layer) continue;  // GraphNavigator.cs:372 nodesOnLayerSet.Contains
+                const int a = find(i), b = find(row[j]);
+                if (a != b) parent[a] = b;
+            }
+        }
+        int c = 0;
+        for (int i = 0; i < g.length; ++i)
+            if (g.levels[i] >= layer && find(i) == i) ++c;
+        counts[layer] = c;
+    }
+    return counts;
 }
 
 void Index::serialize(const std::string& path, bool packed) {

@@ -55,7 +55,12 @@ public:
     static Index* from_snapshot(MetricKind metric, const std::string& path);
 
     int add(const float* vectors, int count, int dim, int* out_ids);
-    void knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists);
+    // `layer`: HNSWIndex.cs:107/129 optional argument (0 = base layer)
+    void knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists, int layer = 0);
+    // MultiLayerKnnQuery (HNSWIndex.cs:173-187), batched; returns the layer count, outputs [count][layers][k]
+    int multilayer_knn_query(const float* queries, int count, int dim, int k, int max_layer, int min_layer, int* out_ids, float* out_dists);
+    int top_layer() const { return top_; }
+    int entry_point() const { return entry_; }
     // queries / outputs already resident in device memory of this index's GPU
     void knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists);
     void exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists);
@@ -74,7 +79,16 @@ public:
     IndexStats stats() const { return stats_; }
     // cycle / work counters of the construction kernels since creation or the last reset (build_kernels.cu BuildProf)
     void build_profile(unsigned long long out[16], bool reset);
-    void export_graph(HostGraph& g);  // device -> host copy of the whole index
+    void export_graph(HostGraph& g, bool with_vectors = true);  // device -> host copy of the whole index
+
+    // HNSWInfo.LayerInfo (HNSWInfo.cs:19-53): degree statistics of one layer, computed from the exported adjacency
+    struct LayerInfo {
+        int LayerId, NodesCount, MaxOutEdges, MinOutEdges, MaxInEdges, MinInEdges;
+        double AvgOutEdges, AvgInEdges;
+        int OutEdgesMedian, InEdgesMedian;
+    };
+    std::vector<LayerInfo> get_info();                      // HNSWIndex.GetInfo, HNSWIndex.cs:192-196
+    std::vector<int> connected_component_counts();          // HNSWIndex.GetConnectedComponentCounts, GraphNavigator.cs:331-419
     int device() const { return device_; }
 
 private:

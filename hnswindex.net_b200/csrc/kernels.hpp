@@ -25,8 +25,14 @@ int device_sm_count();
 
 // K2: batched KnnQuery (HNSWIndex.cs:107-137).  queries: device [nq][dim] dense fp32;
 // out_ids/out_dists: device [nq][k], rows ascending, padded with -1 / NaN.
-void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int* d_ids, float* d_dists,
+// `layer`: the layer searched (HNSWIndex.cs:107 `layer` argument; 0 = base layer), descent stops above it.
+void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
                        unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream);
+
+// MultiLayerKnnQuery (HNSWIndex.cs:173-187): out_* are [nq][top_l + 1][k], rows of layers below min_layer all padding,
+// each row the layer's sorted result without its first entry.
+void launch_multilayer_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int top_l, int min_layer, int* d_ids,
+                              float* d_dists, unsigned* d_work_counter, const Tuning& t, cudaStream_t stream);
 
 // per-item sqrt((double)normA) in the cosine metric's accumulation order
 void launch_item_norms(const float* d_vectors, int pitch, int dim, int first, int count, double* d_norm_sqrt, cudaStream_t stream);

@@ -16,9 +16,11 @@
 
 namespace hnsw {
 
-template <int METRIC>
+// ANY_LAYER = false: the base-layer search of the headline path (layer is the constant 0 throughout);
+// ANY_LAYER = true: KnnQuery(..., layer > 0), a separate instantiation so that the hot kernel stays untouched.
+template <int METRIC, bool ANY_LAYER>
 __global__ void __launch_bounds__(kThreads, 5)
-knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int vis_size, int cand_cap, int flags,
+knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int layer, int vis_size, int cand_cap, int flags,
                   int* __restrict__ out_ids, float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -41,10 +43,11 @@ knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
         int cur = g.entry;
         float cur_d = single_dist<METRIC>(g, s, qn, cur, lane);
         wc.ndist++;
-        for (int layer = g.top_layer; layer > 0; --layer) greedy_layer<METRIC>(g, s, qn, layer, cur, cur_d, lane, wc);
+        const int target = ANY_LAYER ? layer : 0;
+        for (int l = g.top_layer; l > target; --l) greedy_layer<METRIC>(g, s, qn, l, cur, cur_d, lane, wc);
 
         BeamState st;
-        beam_search<METRIC>(g, s, qn, 0, cur, cur_d, ef, st, lane, wc, flags);
+        beam_search<METRIC>(g, s, qn, target, cur, cur_d, ef, st, lane, wc, ANY_LAYER ? 0 : flags);
 
         for (int j = lane; j < k; j += 32) {
             int id = -1;
@@ -63,6 +66,64 @@ knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
             stats[qi] = qs;
         }
         __syncwarp();
+    }
+}
+
+// MultiLayerKnnQuery (HNSWIndex.cs:173-187), one warp per query: from layer `top_l` = min(top layer, maxLayer) down to
+// min_layer one beam search of width k per layer, each entered from the closest result of the layer above; a layer's
+// output row is its sorted result WITHOUT the first entry (at most k-1 entries, padded with -1 / NaN).
+// out_* are [nq][top_l + 1][k]; rows of layers below min_layer are all padding.
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads, 5)
+multilayer_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int top_l, int min_layer, int vis_size, int cand_cap,
+                         int* __restrict__ out_ids, float* __restrict__ out_dists, unsigned* work_counter) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = warp_scratch_bytes(g.pitch, k, vis_size, cand_cap);
+    WarpScratch s = carve_scratch(smem + warp * per_warp, g.pitch, k, vis_size, cand_cap, lane);
+    const int layers = top_l + 1;
+
+    for (;;) {
+        unsigned qi = 0;
+        if (lane == 0) qi = atomicAdd(work_counter, 1u);
+        qi = __shfl_sync(FULL, qi, 0);
+        if (qi >= (unsigned)nq) break;
+
+        const float* qsrc = queries + (size_t)qi * g.dim;
+        for (int i = lane; i < g.pitch; i += 32) s.q[i] = i < g.dim ? __ldg(qsrc + i) : 0.f;
+        __syncwarp();
+        double qn = 0.0;
+        if (METRIC == COSINE) qn = pair_norm_sqrt(s.q, g.dim, lane & 1);
+
+        WarpCounters wc;
+        int cur = g.entry;
+        float cur_d = single_dist<METRIC>(g, s, qn, cur, lane);
+        for (int l = g.top_layer; l > top_l; --l) greedy_layer<METRIC>(g, s, qn, l, cur, cur_d, lane, wc);  // FindEntryPointQuery(maxLayer)
+
+        for (int layer = top_l; layer >= 0; --layer) {
+            int* oi = out_ids + ((size_t)qi * layers + layer) * k;
+            float* od = out_dists + ((size_t)qi * layers + layer) * k;
+            int n = 0;
+            if (layer >= min_layer) {
+                BeamState st;
+                beam_search<METRIC>(g, s, qn, layer, cur, cur_d, k, st, lane, wc, 0);
+                n = st.n;
+                cur = key_id(s.list[0]);
+                cur_d = key_dist(s.list[0]);
+            }
+            for (int j = lane; j < k; j += 32) {
+                int id = -1;
+                float d = CUDART_NAN_F;
+                if (j + 1 < n) {
+                    const u64 e = s.list[j + 1];
+                    id = key_id(e);
+                    d = key_dist(e);
+                }
+                oi[j] = id;
+                od[j] = d;
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -119,7 +180,7 @@ static int configure_persistent(Kern kern, size_t smem_per_warp, const Tuning& t
     return std::max(1, std::min(need, sms * per_sm));
 }
 
-void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int* d_ids, float* d_dists,
+void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
                        unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream) {
     if (nq <= 0) return;
     const int vis = pick_vis_size(t.vis_size_search, ef);
@@ -129,9 +190,15 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
 #define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
     {                                                                                                                           \
         int warps = 0;                                                                                                          \
-        const int grid = configure_persistent(knn_search_kernel<M>, per_warp, t, nq, warps);                                   \
-        knn_search_kernel<M><<<grid, 32 * warps, per_warp * warps, stream>>>(g, d_queries, nq, k, ef, vis, cand_cap, t.flags,  \
-                                                                             d_ids, d_dists, d_work_counter, d_stats);         \
+        if (layer == 0) {                                                                                                       \
+            const int grid = configure_persistent(knn_search_kernel<M, false>, per_warp, t, nq, warps);                        \
+            knn_search_kernel<M, false><<<grid, 32 * warps, per_warp * warps, stream>>>(                                       \
+                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
+        } else {                                                                                                                \
+            const int grid = configure_persistent(knn_search_kernel<M, true>, per_warp, t, nq, warps);                         \
+            knn_search_kernel<M, true><<<grid, 32 * warps, per_warp * warps, stream>>>(                                        \
+                g, d_queries, nq, k, ef, layer, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);              \
+        }                                                                                                                       \
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_SEARCH(SQ_EUCLID) break;
@@ -139,6 +206,29 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
         default: HNSW_LAUNCH_SEARCH(UCOSINE) break;
     }
 #undef HNSW_LAUNCH_SEARCH
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_multilayer_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int top_l, int min_layer, int* d_ids,
+                              float* d_dists, unsigned* d_work_counter, const Tuning& t, cudaStream_t stream) {
+    if (nq <= 0) return;
+    const int vis = pick_vis_size(t.vis_size_search, k);
+    const int cand_cap = ((std::max(g.stride0, g.strideU) + 31) / 32) * 32;
+    const size_t per_warp = warp_scratch_bytes(g.pitch, k, vis, cand_cap);
+    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
+#define HNSW_LAUNCH_ML(M)                                                                                                        \
+    {                                                                                                                            \
+        int warps = 0;                                                                                                           \
+        const int grid = configure_persistent(multilayer_search_kernel<M>, per_warp, t, nq, warps);                             \
+        multilayer_search_kernel<M><<<grid, 32 * warps, per_warp * warps, stream>>>(g, d_queries, nq, k, top_l, min_layer, vis, \
+                                                                                    cand_cap, d_ids, d_dists, d_work_counter);  \
+    }
+    switch (metric) {
+        case SQ_EUCLID: HNSW_LAUNCH_ML(SQ_EUCLID) break;
+        case COSINE: HNSW_LAUNCH_ML(COSINE) break;
+        default: HNSW_LAUNCH_ML(UCOSINE) break;
+    }
+#undef HNSW_LAUNCH_ML
     HNSW_CUDA_CHECK(cudaGetLastError());
 }
 

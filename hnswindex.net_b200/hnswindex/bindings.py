@@ -71,6 +71,12 @@ def _load():
         "hnsw_merge_topk_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
         "hnsw_enable_stats": (ct.c_int, [ct.c_void_p, ct.c_int]),
         "hnsw_get_stats": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
+        "hnsw_knn_query_layer": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
+        "hnsw_multilayer_knn_query": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
+        "hnsw_top_layer": (ct.c_int, [ct.c_void_p]),
+        "hnsw_entry_point": (ct.c_int, [ct.c_void_p]),
+        "hnsw_get_info": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
+        "hnsw_connected_components": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
         "hnsw_get_build_profile": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
         "hnsw_set_tuning": (ct.c_int, [ct.c_void_p, ct.c_char_p, ct.c_int]),
         "hnsw_export_layer0": (ct.c_int, [ct.c_void_p, i32p, i32p, i32p, i32p]),
@@ -86,6 +92,12 @@ def _load():
 
 
 lib = _load()
+
+
+class _LayerInfo(ct.Structure):
+    _fields_ = [("layerId", ct.c_int), ("nodesCount", ct.c_int), ("maxOutEdges", ct.c_int), ("minOutEdges", ct.c_int),
+                ("maxInEdges", ct.c_int), ("minInEdges", ct.c_int), ("avgOutEdges", ct.c_double), ("avgInEdges", ct.c_double),
+                ("outEdgesMedian", ct.c_int), ("inEdgesMedian", ct.c_int)]
 
 
 class _Stats(ct.Structure):
@@ -254,6 +266,58 @@ class Index:
         d = dict(zip(keys, (int(x) for x in ints)))
         d["distribution_rate"] = rate.value
         return d
+
+    # ---- C# surface the reference's native shim does not export (HNSWIndex.cs) ---------------------------
+    def knn_query_layer(self, queries, k: int, layer: int) -> Tuple[np.ndarray, np.ndarray]:
+        """BatchKnnQuery(queries, k, layer: layer) -- HNSWIndex.cs:129-137."""
+        q = _rows_f32(queries, self.dim)
+        n = int(q.shape[0])
+        ids = np.empty((n, k), dtype=np.int32)
+        dists = np.empty((n, k), dtype=np.float32)
+        if self._h is None:
+            ids.fill(-1); dists.fill(np.nan)
+            return ids, dists
+        _check(lib.hnsw_knn_query_layer(self._h, _fp(q), n, self.dim, int(k), int(layer), _ip(ids), _fp(dists)))
+        return ids, dists
+
+    def multilayer_knn_query(self, queries, k: int, max_layer: int = 2 ** 31 - 1, min_layer: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """MultiLayerKnnQuery (HNSWIndex.cs:173-187) for every query: (ids, dists) of shape [n, layers, k]; a layer's row is
+        its ascending result without the first entry, padded with -1 / NaN."""
+        q = _rows_f32(queries, self.dim)
+        n = int(q.shape[0])
+        layers = lib.hnsw_multilayer_knn_query(self._h, None, 0, self.dim, int(k), int(max_layer), int(min_layer), None, None) if self._h else 0
+        _check(layers)
+        ids = np.empty((n, layers, k), dtype=np.int32)
+        dists = np.empty((n, layers, k), dtype=np.float32)
+        if layers > 0 and n > 0:
+            _check(lib.hnsw_multilayer_knn_query(self._h, _fp(q), n, self.dim, int(k), int(max_layer), int(min_layer), _ip(ids), _fp(dists)))
+        return ids, dists
+
+    def top_layer(self) -> int:
+        return lib.hnsw_top_layer(self._h) if self._h else -1
+
+    def entry_point(self) -> int:
+        return lib.hnsw_entry_point(self._h) if self._h else -1
+
+    def get_info(self) -> List[dict]:
+        """GetInfo (HNSWIndex.cs:192-196): one dict per layer with the fields of HNSWInfo.LayerInfo."""
+        if not self._h:
+            return []
+        n = lib.hnsw_get_info(self._h, None, 0)
+        _check(n)
+        arr = (_LayerInfo * max(n, 1))()
+        _check(lib.hnsw_get_info(self._h, arr, n))
+        return [{f: getattr(arr[i], f) for f, _ in _LayerInfo._fields_} for i in range(n)]
+
+    def connected_component_counts(self) -> np.ndarray:
+        """GetConnectedComponentCounts (HNSWIndex.cs:202-205)."""
+        if not self._h:
+            return np.zeros(0, dtype=np.int32)
+        n = lib.hnsw_connected_components(self._h, None, 0)
+        _check(n)
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        _check(lib.hnsw_connected_components(self._h, _ip(out), n))
+        return out[:n]
 
     # ---- engine extras -------------------------------------------------------------------------------
     def exact_knn(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:

@@ -103,6 +103,29 @@ HNSW_API int hnsw_index_set_min_nn(hnsw_handle handle, int minNN);
  * CollectionSize, RandomSeed, AllowRemovals}, rate = DistributionRate */
 HNSW_API int hnsw_index_get_params(hnsw_handle handle, int* ints7, double* rate);
 
+/* KnnQuery / BatchKnnQuery with the reference's optional `layer` argument (HNSWIndex.cs:107,129): the search runs on
+ * that layer (entry found by descending the layers above it).  -1 + last error when the layer does not exist. */
+HNSW_API int hnsw_knn_query_layer(hnsw_handle handle, const float* vectors, int count, int dim, int k, int layer, int* outIds, float* outDists);
+/* MultiLayerKnnQuery (HNSWIndex.cs:173-187), batched over queries: one search of width k per layer from
+ * min(top layer, maxLayer) down to minLayer.  Returns the number of layers L = min(top, maxLayer) + 1 (0 for an empty
+ * index) or -1; outIds / outDists are [count][L][k], each row the layer's ascending result WITHOUT its first entry (as
+ * the reference), padded with -1 / NaN; layers below minLayer are all padding.  NULL outputs: query L only. */
+HNSW_API int hnsw_multilayer_knn_query(hnsw_handle handle, const float* vectors, int count, int dim, int k, int maxLayer, int minLayer,
+                                       int* outIds, float* outDists);
+HNSW_API int hnsw_top_layer(hnsw_handle handle);   /* MaxLayer of the entry point, -1 when empty */
+HNSW_API int hnsw_entry_point(hnsw_handle handle); /* EntryPointId, -1 when empty */
+
+/* GetInfo (HNSWIndex.cs:192-196, HNSWInfo.cs): per-layer degree statistics.  Returns the number of layers; fills at
+ * most maxLayers entries.  In-edge fields are 0 when AllowRemovals is false, as in the reference. */
+typedef struct hnsw_layer_info {
+    int layerId, nodesCount, maxOutEdges, minOutEdges, maxInEdges, minInEdges;
+    double avgOutEdges, avgInEdges;
+    int outEdgesMedian, inEdgesMedian;
+} hnsw_layer_info;
+HNSW_API int hnsw_get_info(hnsw_handle handle, hnsw_layer_info* out, int maxLayers);
+/* GetConnectedComponentCounts (HNSWIndex.cs:202-205, GraphNavigator.cs:331-419): weakly connected components per layer. */
+HNSW_API int hnsw_connected_components(hnsw_handle handle, int* counts, int maxLayers);
+
 /* One process per GPU: select the CUDA device used by indexes created afterwards on this thread. */
 HNSW_API int hnsw_set_device(int device);
 HNSW_API int hnsw_device_count(void);

@@ -840,20 +840,39 @@ public:
         return top;
     }
 
-    // HNSWIndex.cs:107-124
-    std::vector<NodeDistance> KnnQuery(const float* q, int k, Counters* c = nullptr) {
+    // HNSWIndex.cs:107-124 (layer = the optional 4th argument, 0 = base layer)
+    std::vector<NodeDistance> KnnQuery(const float* q, int k, Counters* c = nullptr, int layer = 0) {
         if (Count() <= 0 || k < 1) return {};
         int neighborsAmount = std::max(p.MinNN, k);
-        Node* ep = FindEntryPoint(0, q, c);
-        auto top = SearchLayer<false>(ep->Id, 0, neighborsAmount, q, c);
+        Node* ep = FindEntryPoint(layer, q, c);
+        if (layer < 0 || layer > ep->MaxLayer()) throw std::out_of_range("layer");  // OutEdges[layer]: IndexOutOfRangeException
+        auto top = SearchLayer<false>(ep->Id, layer, neighborsAmount, q, c);
         // OrderBy(c => c.Dist) is a stable sort; Comparer<float>.Default
         std::stable_sort(top.begin(), top.end(), [](const NodeDistance& a, const NodeDistance& b) { return float_compare_to(a.Dist, b.Dist) < 0; });
         if (k < (int)top.size()) top.resize(k);
         return top;
     }
 
+    // HNSWIndex.cs:173-187: one search of width k per layer from min(ep.MaxLayer, maxLayer) down to minLayer, each
+    // entered from the closest result of the layer above; a layer's result is the sorted list WITHOUT its first
+    // element.  result[layer] stays empty for layers below minLayer.
+    std::vector<std::vector<NodeDistance>> MultiLayerKnnQuery(const float* q, int k, int maxLayer, int minLayer) {
+        if (Count() <= 0 || k < 1) return {};
+        Node* entry = Nodes[EntryPointId].get();
+        Node* ep = entry->MaxLayer() >= maxLayer ? FindEntryPoint(maxLayer, q, nullptr) : entry;
+        int topL = std::min(ep->MaxLayer(), maxLayer);
+        std::vector<std::vector<NodeDistance>> result((size_t)std::max(topL + 1, 0));
+        for (int layer = topL; layer >= minLayer; layer--) {
+            auto cand = SearchLayer<false>(ep->Id, layer, k, q, nullptr);
+            std::stable_sort(cand.begin(), cand.end(), [](const NodeDistance& a, const NodeDistance& b) { return float_compare_to(a.Dist, b.Dist) < 0; });
+            ep = Nodes[cand[0].Id].get();
+            result[layer].assign(cand.begin() + 1, cand.end());
+        }
+        return result;
+    }
+
     // HNSWIndex.cs:129-137 + HNSWIndexExports.cs:135-145 (padding with -1 / NaN)
-    void BatchKnnQuery(const float* q, int count, int k, int* outIds, float* outDists, int threads, Counters* total = nullptr) {
+    void BatchKnnQuery(const float* q, int count, int k, int* outIds, float* outDists, int threads, Counters* total = nullptr, int layer = 0) {
         std::atomic<int> next{0};
         std::vector<Counters> cs(std::max(threads, 1));
         auto work = [&](int t) {
@@ -861,7 +880,7 @@ public:
                 int base = next.fetch_add(16);
                 if (base >= count) break;
                 for (int i = base; i < std::min(count, base + 16); i++) {
-                    auto res = KnnQuery(q + (size_t)i * dim, k, total ? &cs[t] : nullptr);
+                    auto res = KnnQuery(q + (size_t)i * dim, k, total ? &cs[t] : nullptr, layer);
                     int n = std::min(k, (int)res.size());
                     for (int j = 0; j < n; j++) {
                         outIds[(size_t)i * k + j] = res[j].Id;

@@ -59,6 +59,8 @@ def lib():
     L.orc_add_frozen_batches.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, i32p, ct.c_int, ct.c_int]
     L.orc_knn_query.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, ct.c_int, u64p]
     L.orc_knn_query_counters.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, u64p]
+    L.orc_knn_query_layer.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, ct.c_int]
+    L.orc_multilayer_knn_query.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, i32p, f32p]
     L.orc_range_query.restype = ct.c_longlong
     L.orc_range_query.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_float, ct.POINTER(ct.c_longlong), i32p, f32p, ct.c_int]
     L.orc_exact_knn.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, ct.c_int]
@@ -224,6 +226,29 @@ class OracleIndex:
         if rc < 0:
             raise RuntimeError(lib().orc_last_error().decode())
         return (ids, dists, c) if counters else (ids, dists)
+
+    def knn_query_layer(self, queries, k, layer, threads=1):
+        """BatchKnnQuery(..., layer) -- HNSWIndex.cs:107-137."""
+        q = _f32(queries)
+        ids = np.empty((q.shape[0], k), dtype=np.int32)
+        dists = np.empty((q.shape[0], k), dtype=np.float32)
+        rc = lib().orc_knn_query_layer(self._h, _fp(q), q.shape[0], q.shape[1], k, int(layer), _ip(ids), _fp(dists), threads)
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error().decode())
+        return ids, dists
+
+    def multilayer_knn_query(self, queries, k, max_layer=2 ** 31 - 1, min_layer=0):
+        """MultiLayerKnnQuery (HNSWIndex.cs:173-187) per query: (ids, dists) of shape [n, layers, k], -1 / NaN padded."""
+        q = _f32(queries)
+        layers = lib().orc_multilayer_knn_query(self._h, _fp(q), min(1, q.shape[0]), q.shape[1], k, int(max_layer), int(min_layer), 0, None, None)
+        if layers < 0:
+            raise RuntimeError(lib().orc_last_error().decode())
+        ids = np.empty((q.shape[0], layers, k), dtype=np.int32)
+        dists = np.empty((q.shape[0], layers, k), dtype=np.float32)
+        rc = lib().orc_multilayer_knn_query(self._h, _fp(q), q.shape[0], q.shape[1], k, int(max_layer), int(min_layer), layers, _ip(ids), _fp(dists))
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error().decode())
+        return ids, dists
 
     def knn_query_counters(self, queries, k):
         """Per-query (ndist, nexp, row_words) -- the roofline's algorithmic work."""

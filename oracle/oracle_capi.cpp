@@ -105,6 +105,37 @@ int orc_knn_query(void* h, const float* q, int count, int dim, int k, int* outId
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
+// BatchKnnQuery(queries, k, layer: L) -- HNSWIndex.cs:129-137
+int orc_knn_query_layer(void* h, const float* q, int count, int dim, int k, int layer, int* outIds, float* outDists, int threads) {
+    try {
+        Index* ix = (Index*)h;
+        if (dim != ix->dim) throw std::runtime_error("dimension mismatch");
+        ix->BatchKnnQuery(q, count, k, outIds, outDists, threads, nullptr, layer);
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+// MultiLayerKnnQuery (HNSWIndex.cs:173-187) per query; out arrays [count][layers][k] padded with -1 / NaN, a layer's
+// row holds at most k-1 entries (the first one is dropped by the reference).  Returns the number of layers.
+int orc_multilayer_knn_query(void* h, const float* q, int count, int dim, int k, int maxLayer, int minLayer, int layers, int* outIds, float* outDists) {
+    try {
+        Index* ix = (Index*)h;
+        if (dim != ix->dim) throw std::runtime_error("dimension mismatch");
+        int got = 0;
+        for (int i = 0; i < count; i++) {
+            auto res = ix->MultiLayerKnnQuery(q + (size_t)i * dim, k, maxLayer, minLayer);
+            got = (int)res.size();
+            if (outIds == nullptr) break;
+            if (got != layers) throw std::runtime_error("layer count mismatch");
+            for (int l = 0; l < layers; l++)
+                for (int j = 0; j < k; j++) {
+                    const size_t o = ((size_t)i * layers + l) * k + j;
+                    if (j < (int)res[l].size()) { outIds[o] = res[l][j].Id; outDists[o] = res[l][j].Dist; }
+                    else { outIds[o] = -1; outDists[o] = std::numeric_limits<float>::quiet_NaN(); }
+                }
+        }
+        return got;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
 // per-query counters (ndist, nexp, row_words) for the roofline's algorithmic bytes
 int orc_knn_query_counters(void* h, const float* q, int count, int dim, int k, uint64_t* perQuery /*count*3*/) {
     try {

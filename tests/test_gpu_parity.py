@@ -381,3 +381,83 @@ def test_pinned_host_buffers_take_the_zero_copy_path_with_identical_results(hnsw
     ip.fill_(-5)
     rc = hnswindex.lib.hnsw_knn_query(ix._h, ct.cast(qp.data_ptr(), f32p), 777, 64, 7, ct.cast(ip.data_ptr(), i32p), ct.cast(dp.data_ptr(), f32p))
     assert rc == 0 and np.array_equal(ip.numpy(), a_ids)
+
+
+# ------------------------------------------------------------------ layer queries, diagnostics
+@pytest.mark.parametrize("metric", ["sq_euclid", "cosine"])
+def test_knn_query_on_upper_layers_matches_oracle(hnswindex, oracle, tmp_path, metric):
+    # KnnQuery(query, k, layer: L), HNSWIndex.cs:107-124: descent stops above L, the beam search runs on L
+    rng = np.random.default_rng(77)
+    data = rng.random((6000, 48), dtype=np.float32)
+    queries = rng.random((300, 48), dtype=np.float32)
+    ref, path = _oracle_graph(oracle, tmp_path, metric, data, f"layers_{metric}", max_edges=8, distribution_rate=1.0 / math.log(4.0))
+    gpu = hnswindex.Index.deserialize(metric, path)
+    top = gpu.top_layer()
+    assert top >= 3 and gpu.entry_point() == ref.entry_point
+    for layer in range(0, top + 1):
+        for k, min_nn in ((1, 5), (10, 5), (4, 40)):
+            ref.set_min_nn(min_nn)
+            gpu.set_min_nn(min_nn)
+            o_ids, o_d = ref.knn_query_layer(queries, k, layer)
+            g_ids, g_d = gpu.knn_query_layer(queries, k, layer)
+            _assert_identical(g_ids, g_d, o_ids, o_d, explain=(oracle, metric, data, queries))
+            if layer > 0:  # results live on that layer
+                levels, _, _ = gpu.export_layer0()
+                assert (levels[g_ids[g_ids >= 0]] >= layer).all()
+    with pytest.raises(RuntimeError):
+        gpu.knn_query_layer(queries, 3, top + 1)
+
+
+def test_multilayer_knn_query_matches_oracle(hnswindex, oracle, tmp_path):
+    # MultiLayerKnnQuery, HNSWIndex.cs:173-187
+    rng = np.random.default_rng(78)
+    data = rng.random((5000, 32), dtype=np.float32)
+    queries = rng.random((200, 32), dtype=np.float32)
+    ref, path = _oracle_graph(oracle, tmp_path, "sq_euclid", data, "multilayer", max_edges=8, distribution_rate=1.0 / math.log(4.0))
+    gpu = hnswindex.Index.deserialize("sq_euclid", path)
+    top = gpu.top_layer()
+    for k, max_layer, min_layer in ((5, 2 ** 31 - 1, 0), (8, 2, 0), (3, top, 1), (1, 1, 0), (6, 0, 0), (4, 2, 3)):
+        o_ids, o_d = ref.multilayer_knn_query(queries, k, max_layer, min_layer)
+        g_ids, g_d = gpu.multilayer_knn_query(queries, k, max_layer, min_layer)
+        assert g_ids.shape == o_ids.shape == (200, min(top, max_layer) + 1, k)
+        _assert_identical(g_ids.reshape(-1, k), g_d.reshape(-1, k), o_ids.reshape(-1, k), o_d.reshape(-1, k))
+        assert (g_ids[:, :, k - 1] == -1).all()  # the reference drops the first entry of every layer's list
+
+
+def test_get_info_and_connected_components(hnswindex, oracle):
+    # GetInfo (HNSWInfo.cs) and GetConnectedComponentCounts (GraphNavigator.cs:331-419) on a GPU-built graph,
+    # recomputed here from the exported rows
+    rng = np.random.default_rng(79)
+    data = rng.random((4000, 24), dtype=np.float32)
+    ix = hnswindex.Index(24, "sq_euclid")
+    ix.set_max_edges(6)
+    ix.add(data)
+    info = ix.get_info()
+    levels, rows0, _ = ix.export_layer0()
+    top = ix.top_layer()
+    assert len(info) == top + 1 and [li["layerId"] for li in info] == list(range(top + 1))
+    comps = ix.connected_component_counts()
+    assert len(comps) == top + 1
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    for layer in range(top + 1):
+        rows = rows0 if layer == 0 else ix.export_layer(layer)
+        on = np.nonzero(levels >= layer)[0]
+        deg = (rows[on] >= 0).sum(axis=1)
+        li = info[layer]
+        assert li["nodesCount"] == len(on)
+        assert li["maxOutEdges"] == deg.max() and li["minOutEdges"] == deg.min()
+        assert abs(li["avgOutEdges"] - deg.mean()) < 1e-9
+        sd = np.sort(deg)
+        med = (sd[len(sd) // 2 - 1] + sd[len(sd) // 2]) // 2 if len(sd) % 2 == 0 else sd[len(sd) // 2]
+        assert li["outEdgesMedian"] == med
+        src = np.repeat(on, rows.shape[1])
+        dst = rows[on].reshape(-1)
+        keep = dst >= 0
+        indeg = np.bincount(dst[keep], minlength=len(levels))[on]
+        assert li["maxInEdges"] == indeg.max() and li["minInEdges"] == indeg.min()
+        assert li["avgInEdges"] == li["avgOutEdges"]  # GraphTests.cs:151-155: in and out edges are balanced
+        g = sp.coo_matrix((np.ones(keep.sum()), (src[keep], dst[keep])), shape=(len(levels), len(levels)))
+        ncomp, lab = connected_components(g, directed=True, connection="weak")
+        assert comps[layer] == len(np.unique(lab[on]))
+    assert comps[0] >= 1

@@ -188,3 +188,31 @@ def test_frozen_batch_insertion_recall(oracle):
     assert np.array_equal(ids, ids2)
     r1 = oracle.self_recall(fb, v, ids2)
     assert r1 > r0 - 0.02, (r0, r1)
+
+
+def test_layer_queries_of_the_oracle(oracle):
+    # KnnQuery(layer) / MultiLayerKnnQuery (HNSWIndex.cs:107-124, 173-187): results live on the requested layer,
+    # layer 0 equals the plain query, the multi-layer rows drop the first entry of each layer's list
+    import math
+    rng = np.random.default_rng(5)
+    data = rng.random((3000, 16), dtype=np.float32)
+    q = rng.random((50, 16), dtype=np.float32)
+    ix = oracle.OracleIndex("sq_euclid", max_edges=8, distribution_rate=1.0 / math.log(4.0))
+    ix.add(data)
+    ids0, d0 = ix.knn_query(q, 5)
+    idsL, dL = ix.knn_query_layer(q, 5, 0)
+    assert np.array_equal(ids0, idsL) and np.array_equal(d0, dL)
+    levels = np.array([ix.node_level(i) for i in range(ix.count)])
+    top = levels[ix.entry_point]
+    assert top >= 2
+    ids2, _ = ix.knn_query_layer(q, 5, 2)
+    assert (levels[ids2[ids2 >= 0]] >= 2).all()
+    with pytest.raises(RuntimeError):
+        ix.knn_query_layer(q, 5, int(top) + 1)
+    mi, md = ix.multilayer_knn_query(q, 4)
+    assert mi.shape == (50, top + 1, 4) and (mi[:, :, 3] == -1).all()
+    for layer in range(top + 1):
+        v = mi[:, layer, :3]
+        assert (levels[v[v >= 0]] >= layer).all()
+    # layer 0 of the multi-layer query is a width-k search entered from layer 1's best: ascending distances
+    assert (np.diff(md[:, 0, :3], axis=1) >= 0).all()

@@ -1,6 +1,2 @@
-rm -f gpurun_out/build6.log
-for cfg in "vis_global_build=16384 build_batch_max=16384 build_batch_ratio=32" "vis_global_build=16384 build_batch_max=16384 build_batch_ratio=16" "vis_global_build=16384 build_batch_max=8192 build_batch_ratio=8" "vis_global_build=16384 build_batch_max=12288 build_batch_ratio=16" "vis_global_build=0 build_batch_max=8192 build_batch_ratio=16"; do
-  echo "== $cfg" >> gpurun_out/build6.log
-  timeout 300 python tools/build_only.py 1000000 $cfg >> gpurun_out/build6.log 2>&1
-done
-cat gpurun_out/build6.log
+timeout 300 python tools/sweep.py 1000000 48 > gpurun_out/sweep7.log 2>&1; cat gpurun_out/sweep7.log
+timeout 900 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/bench7.json 2> gpurun_out/bench7.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/bench7.json; grep -o '"kernel_ms_avg": [0-9.]*' gpurun_out/bench7.json
