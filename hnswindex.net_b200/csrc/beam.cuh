@@ -109,18 +109,20 @@ __device__ __forceinline__ void stage_issue(const GraphView& g, Stager& stg, con
     const unsigned pitch_bytes = (unsigned)g.pitch * 4u;
     const bool act = lane * 4 < nfl;  // lanes beyond the row length copy nothing
     const int limit = act ? nrows : 0;
+#ifdef HNSW_STAGE_TWO_PATHS
     if (nrows == kStageRows) {        // warp-uniform: the shuffles below stay convergent
 #pragma unroll
         for (int r = 0; r < kStageRows; ++r) {
             const unsigned id = (unsigned)__shfl_sync(FULL, myid, r);
             if (act) cp_async_16s(dst0 + r * (kSegPitch * 4), src0 + (size_t)id * pitch_bytes);
         }
-    } else {
+        return;
+    }
+#endif
 #pragma unroll
-        for (int r = 0; r < kStageRows; ++r) {
-            const unsigned id = (unsigned)__shfl_sync(FULL, myid, r);
-            if (r < limit) cp_async_16s(dst0 + r * (kSegPitch * 4), src0 + (size_t)id * pitch_bytes);
-        }
+    for (int r = 0; r < kStageRows; ++r) {
+        const unsigned id = (unsigned)__shfl_sync(FULL, myid, r);
+        if (r < limit) cp_async_16s(dst0 + r * (kSegPitch * 4), src0 + (size_t)id * pitch_bytes);
     }
 #endif
 }
@@ -153,7 +155,11 @@ __device__ __forceinline__ void compute_staged(const GraphView& g, Stager& stg, 
     __syncwarp();  // staged rows are free again, distances are visible
 }
 
-template <int METRIC>
+// SPEC (compile-time knowledge that lets the hot kernels drop dead code; 0 = generic):
+//   bit 0: rows fit one staging segment (pitch <= kSegFloats);  bit 1: the list never exceeds 64 entries (ef <= 64)
+constexpr int kSpecShortRows = 1, kSpecSmallList = 2;
+
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, const int* ids, float* out,
                                               int m, int lane) {
     constexpr bool SQ = METRIC == SQ_EUCLID;
@@ -162,12 +168,13 @@ __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, c
     const int ntail = g.dim - (nfull << 3);       // scalar remainder
     for (int base = 0; base < m; base += kStageRows) {
         const int nrows = min(kStageRows, m - base);
-        if (g.pitch <= kSegFloats) {
+        if ((SPEC & kSpecShortRows) || g.pitch <= kSegFloats) {
             stage_issue(g, stg, ids, base, nrows, 0, g.pitch, lane);
             stage_complete(stg);
             compute_staged<METRIC>(g, stg, q, q_norm_sqrt, ids, out, base, nrows, lane);
             continue;
         }
+        if (SPEC & kSpecShortRows) continue;  // (unreachable; lets the compiler drop the long-row code)
         // long rows: segments of kSegFloats floats, lane accumulators carried across segments
         const bool active = grp < nrows;
         double an = 0.0;
@@ -191,17 +198,17 @@ __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, c
     }
     __syncwarp();
 }
-template <int METRIC>
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void batch_dist(const GraphView& g, WarpScratch& s, double q_norm_sqrt, int m, int lane) {
-    batch_dist_to<METRIC>(g, s.stg, s.q, q_norm_sqrt, s.cand_id, s.cand_dist, m, lane);
+    batch_dist_to<METRIC, SPEC>(g, s.stg, s.q, q_norm_sqrt, s.cand_id, s.cand_dist, m, lane);
 }
 
-template <int METRIC>
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ float single_dist(const GraphView& g, WarpScratch& s, double q_norm_sqrt, int id, int lane) {
     __syncwarp();
     if (lane == 0) s.cand_id[0] = id;
     __syncwarp();
-    batch_dist<METRIC>(g, s, q_norm_sqrt, 1, lane);
+    batch_dist<METRIC, SPEC>(g, s, q_norm_sqrt, 1, lane);
     const float d = s.cand_dist[0];
     __syncwarp();
     return d;
@@ -239,9 +246,10 @@ __device__ __forceinline__ int list_lower_bound(const u64* list, int n, u64 key,
 
 // Insert `key` (flag bit clear) keeping the list sorted, dropping the last entry when
 // full.  Returns false when the id is already present (duplicate) or falls off the end.
+template <int SPEC = 0>
 __device__ __forceinline__ bool list_insert(u64* list, BeamState& st, u64 key, int lane) {
     const int n = st.n;
-    if (n <= 64) {
+    if ((SPEC & kSpecSmallList) || n <= 64) {
         // whole list in two registers per lane: one pass finds the position, detects duplicates and shifts
         const u64 v0 = lane < n ? list[lane] : ~0ull;
         const u64 v1 = lane + 32 < n ? list[lane + 32] : ~0ull;
@@ -259,6 +267,7 @@ __device__ __forceinline__ bool list_insert(u64* list, BeamState& st, u64 key, i
         if (pos < st.cursor) st.cursor = pos;
         return true;
     }
+    if (SPEC & kSpecSmallList) return false;  // (unreachable)
     if (n <= 1024) {
         // Two-level search (construction: ef = MaxCandidates ~ 100-200): lane c looks at the LAST entry of chunk c
         // (32 entries per chunk), the ballot names the first chunk that is not entirely below the key, a second
@@ -364,7 +373,7 @@ __device__ __forceinline__ bool gvis_test_and_set(const WarpScratch& s, int id) 
 // row of the current node in stored order, move to the strict minimum (first
 // occurrence on ties), repeat until a scan brings no improvement.
 // ----------------------------------------------------------------------------
-template <int METRIC>
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void greedy_layer(const GraphView& g, WarpScratch& s, double qn, int layer, int& cur, float& cur_d,
                                              int lane, WarpCounters& wc) {
     bool changed = true;
@@ -385,7 +394,7 @@ __device__ __forceinline__ void greedy_layer(const GraphView& g, WarpScratch& s,
         wc.row_words += m + 1;
         if (m == 0) break;
         wc.ndist += m;
-        batch_dist<METRIC>(g, s, qn, m, lane);
+        batch_dist<METRIC, SPEC>(g, s, qn, m, lane);
         u64 best = ~0ull;
         for (int j = lane; j < m; j += 32) {
             const u64 k = ((u64)f2ord(s.cand_dist[j]) << 32) | (u64)(uint32_t)j;
@@ -410,6 +419,7 @@ __device__ __forceinline__ void greedy_layer(const GraphView& g, WarpScratch& s,
 
 // Insert candidates [lo, hi) of the current expansion in stored order; a candidate is accepted iff
 // |top| < ef or d < far (strict), re-evaluated after every insertion (GraphNavigator.cs:233-246).
+template <int SPEC = 0>
 __device__ __forceinline__ void insert_candidates(const GraphView& g, WarpScratch& s, BeamState& st, int lo, int hi, int layer, int lane, int flags) {
     for (int jb = lo; jb < hi; jb += 32) {
         const int j = jb + lane;
@@ -423,7 +433,7 @@ __device__ __forceinline__ void insert_candidates(const GraphView& g, WarpScratc
             const int src = __ffs(mk) - 1;
             const u64 kn = __shfl_sync(FULL, mykey, src);
             if (lane == src) pending = false;
-            const bool inserted = list_insert(s.list, st, kn, lane);
+            const bool inserted = list_insert<SPEC>(s.list, st, kn, lane);
             // optional: pull the adjacency row of an accepted candidate into L2 (measured: no gain at C2)
             if (inserted && lane == src && layer == 0 && (flags & kPrefetchRows)) {
                 const char* rp = reinterpret_cast<const char*>(g.adj0 + (size_t)key_id(kn) * g.stride0);
@@ -437,7 +447,7 @@ __device__ __forceinline__ void insert_candidates(const GraphView& g, WarpScratc
 // Beam search of width ef on one layer (GraphNavigator.cs:194-256).  On return
 // s.list[0..st.n) holds the result sorted ascending by (distance, id).
 // ----------------------------------------------------------------------------
-template <int METRIC>
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, double qn, int layer, int entry, float entry_d,
                                             int ef, BeamState& st, int lane, WarpCounters& wc, int flags = kPrefetchRows) {
     st.n = 0;
@@ -446,7 +456,7 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
     st.cursor = 0;
     vis_clear(s, lane);
     if (s.gvis != nullptr) gvis_clear(s, lane);
-    list_insert(s.list, st, make_key(entry_d, entry), lane);
+    list_insert<SPEC>(s.list, st, make_key(entry_d, entry), lane);
     if (lane == 0) {
         vis_test_and_set(s, entry);
         if (s.gvis != nullptr) gvis_test_and_set(s, entry);
@@ -494,7 +504,7 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
         if (m == 0) continue;
         wc.ndist += m;
 
-        if (g.pitch <= kSegFloats) {
+        if ((SPEC & kSpecShortRows) || g.pitch <= kSegFloats) {
             // Software pipeline over passes of 16 rows: the copies of pass p+1 are in flight while the
             // candidates of pass p are inserted (stored order is kept: pass p is inserted before p+1).
             stage_issue(g, s.stg, s.cand_id, 0, min(kStageRows, m), 0, g.pitch, lane);
@@ -517,11 +527,11 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
                     }
                     if (guess_id >= 0) guess_nb = lane < g.stride0 ? __ldg(g.adj0 + (size_t)guess_id * g.stride0 + lane) : -1;
                 }
-                insert_candidates(g, s, st, base, base + nrows, layer, lane, flags);
+                insert_candidates<SPEC>(g, s, st, base, base + nrows, layer, lane, flags);
             }
-        } else {
-            batch_dist<METRIC>(g, s, qn, m, lane);
-            insert_candidates(g, s, st, 0, m, layer, lane, flags);
+        } else if (!(SPEC & kSpecShortRows)) {
+            batch_dist<METRIC, SPEC>(g, s, qn, m, lane);
+            insert_candidates<SPEC>(g, s, st, 0, m, layer, lane, flags);
         }
     }
 }

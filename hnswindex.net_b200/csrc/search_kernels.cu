@@ -18,7 +18,9 @@ namespace hnsw {
 
 // ANY_LAYER = false: the base-layer search of the headline path (layer is the constant 0 throughout);
 // ANY_LAYER = true: KnnQuery(..., layer > 0), a separate instantiation so that the hot kernel stays untouched.
-template <int METRIC, bool ANY_LAYER>
+// SPEC: compile-time facts about the launch (beam.cuh kSpec*), so the C2-shaped hot kernel carries no dead code
+// (its instruction footprint decides whether the loop stays inside the 32 KB L1.5 instruction cache).
+template <int METRIC, bool ANY_LAYER, int SPEC>
 __global__ void __launch_bounds__(kThreads, 5)
 knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int layer, int vis_size, int cand_cap, int flags,
                   int* __restrict__ out_ids, float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats) {
@@ -41,13 +43,13 @@ knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
 
         WarpCounters wc;
         int cur = g.entry;
-        float cur_d = single_dist<METRIC>(g, s, qn, cur, lane);
+        float cur_d = single_dist<METRIC, SPEC>(g, s, qn, cur, lane);
         wc.ndist++;
         const int target = ANY_LAYER ? layer : 0;
-        for (int l = g.top_layer; l > target; --l) greedy_layer<METRIC>(g, s, qn, l, cur, cur_d, lane, wc);
+        for (int l = g.top_layer; l > target; --l) greedy_layer<METRIC, SPEC>(g, s, qn, l, cur, cur_d, lane, wc);
 
         BeamState st;
-        beam_search<METRIC>(g, s, qn, target, cur, cur_d, ef, st, lane, wc, ANY_LAYER ? 0 : flags);
+        beam_search<METRIC, SPEC>(g, s, qn, target, cur, cur_d, ef, st, lane, wc, ANY_LAYER ? 0 : flags);
 
         for (int j = lane; j < k; j += 32) {
             int id = -1;
@@ -190,13 +192,18 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
 #define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
     {                                                                                                                           \
         int warps = 0;                                                                                                          \
-        if (layer == 0) {                                                                                                       \
-            const int grid = configure_persistent(knn_search_kernel<M, false>, per_warp, t, nq, warps);                        \
-            knn_search_kernel<M, false><<<grid, 32 * warps, per_warp * warps, stream>>>(                                       \
+        if (layer == 0 && g.pitch <= kSegFloats && ef <= 64) {                                                                  \
+            constexpr int S = kSpecShortRows | kSpecSmallList;                                                                  \
+            const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
+            knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
+                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
+        } else if (layer == 0) {                                                                                                \
+            const int grid = configure_persistent(knn_search_kernel<M, false, 0>, per_warp, t, nq, warps);                     \
+            knn_search_kernel<M, false, 0><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
                 g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
         } else {                                                                                                                \
-            const int grid = configure_persistent(knn_search_kernel<M, true>, per_warp, t, nq, warps);                         \
-            knn_search_kernel<M, true><<<grid, 32 * warps, per_warp * warps, stream>>>(                                        \
+            const int grid = configure_persistent(knn_search_kernel<M, true, 0>, per_warp, t, nq, warps);                      \
+            knn_search_kernel<M, true, 0><<<grid, 32 * warps, per_warp * warps, stream>>>(                                     \
                 g, d_queries, nq, k, ef, layer, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);              \
         }                                                                                                                       \
     }

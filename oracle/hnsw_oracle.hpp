@@ -28,6 +28,7 @@
 #include <memory>
 #include <mutex>
 #include <random>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -560,33 +561,185 @@ public:
         return (int)v;
     }
 
-    // GraphData.cs:79-118 (no removed-slot reuse: removals are out of scope)
+    // GraphData.cs:79-118
     int AddItem(const float* v, int d) {
         int topLayer = GetRandomLayer();
         if (topLayer < 0) return -1;
         return AddItemWithLevel(v, d, topLayer);
     }
-    int AddItemWithLevel(const float* v, int d, int topLayer) {
-        std::lock_guard<std::mutex> g(indexLock);
-        if (dim < 0) dim = d;
-        if (d != dim) throw std::runtime_error("dimension mismatch");
-        int slotId = Length++;
-        if (Length > Capacity) Capacity *= 2;
-        // NewNode, GraphData.cs:224-242
+    // NewNode, GraphData.cs:224-242
+    std::unique_ptr<Node> NewNode(int index, int topLayer) const {
         auto node = std::make_unique<Node>();
-        node->Id = slotId;
+        node->Id = index;
         node->OutEdges.resize(topLayer + 1);
         if (p.AllowRemovals) node->InEdges.resize(topLayer + 1);
         for (int layer = 0; layer <= topLayer; layer++) {
             node->OutEdges[layer] = EdgeList(MaxEdges(layer) + 1);
             if (p.AllowRemovals) node->InEdges[layer] = EdgeList(MaxEdges(layer) + 1);
         }
+        return node;
+    }
+    int AddItemWithLevel(const float* v, int d, int topLayer) {
+        std::lock_guard<std::mutex> g(indexLock);
+        if (dim < 0) dim = d;
+        if (d != dim) throw std::runtime_error("dimension mismatch");
+        // "Search for empty spot first", GraphData.cs:84-91
+        if (p.AllowRemovals && !RemovedIndexes.empty()) {
+            int vacantId = RemovedIndexes.back();
+            RemovedIndexes.pop_back();
+            Nodes[vacantId] = NewNode(vacantId, topLayer);
+            std::copy(v, v + dim, Items.begin() + (size_t)vacantId * dim);
+            ActiveAdd(vacantId);
+            return vacantId;
+        }
+        int slotId = Length++;
+        if (Length > Capacity) Capacity *= 2;
         if (threaded && (Nodes.size() == Nodes.capacity() || Items.size() + dim > Items.capacity()))
             throw std::runtime_error("threaded add needs reserve()");
-        Nodes.push_back(std::move(node));
+        Nodes.push_back(NewNode(slotId, topLayer));
         Items.insert(Items.end(), v, v + dim);
-        ActiveIds.push_back(slotId);
+        ActiveAdd(slotId);
         return slotId;
+    }
+
+    // ActiveSet.cs:69-93 (dense = ActiveIds, sparse built on first use so that deserialised indexes work too)
+    void ActiveAdd(int id) {
+        if (sparse_valid) {
+            if ((int)ActiveSparse.size() <= id) ActiveSparse.resize((size_t)id + 1, 0);
+            ActiveSparse[id] = (int)ActiveIds.size();
+        }
+        ActiveIds.push_back(id);
+    }
+    void ActiveRemove(int id) {
+        if (!sparse_valid) {
+            ActiveSparse.assign(Nodes.size(), 0);
+            for (size_t i = 0; i < ActiveIds.size(); i++) ActiveSparse[ActiveIds[i]] = (int)i;
+            sparse_valid = true;
+        }
+        int idx = ActiveSparse[id];
+        int lastId = ActiveIds.back();
+        ActiveIds.pop_back();
+        if (idx < (int)ActiveIds.size()) {  // move last into the removed slot
+            ActiveIds[idx] = lastId;
+            ActiveSparse[lastId] = idx;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // Removal, single-threaded restatement (HNSWIndex.cs:83-100, GraphConnector.cs:53-167,
+    // GraphData.cs:124-199).  The neighbourhood locks of GraphLocker.cs and the TryEnterReadLock(0) at
+    // GraphConnector.cs:152 only matter under concurrency and are omitted.
+    // ------------------------------------------------------------------------------------------------
+    std::vector<int> RemovedIndexes;  // ConcurrentStack<int>: back() is the top
+
+    void Remove(int itemIndex, Counters* c = nullptr) {
+        if (!p.AllowRemovals) throw std::runtime_error("Removals are disabled in this index instance.");
+        if (itemIndex < 0 || itemIndex >= (int)Nodes.size()) throw std::out_of_range("item index");
+        RemoveNodeConnections(Nodes[itemIndex].get(), c);
+    }
+
+    // GraphConnector.cs:53-67
+    void RemoveNodeConnections(Node* item, Counters* c) {
+        item->IsRemoved = true;
+        for (int layer = item->MaxLayer(); layer >= 0; layer--) {
+            ReplaceEntryPointIfNeeded(item, layer);
+            RemoveConnectionsAtLayer(item, layer, c);
+            if (layer == 0) {  // GraphData.RemoveItem, GraphData.cs:124-128
+                RemovedIndexes.push_back(item->Id);
+                ActiveRemove(item->Id);
+            }
+        }
+    }
+
+    // GraphConnector.cs:72-85
+    void ReplaceEntryPointIfNeeded(Node* removedNode, int layer) {
+        if (removedNode->Id != EntryPointId) return;
+        if (TryReplaceEntryPoint(layer)) return;
+        if (layer > 0) return;
+        if (Count() == 1) {
+            EntryPointId = -1;
+            return;
+        }
+        ForceReplaceEntryPoint();
+    }
+
+    // GraphData.cs:146-166
+    bool TryReplaceEntryPoint(int layer) {
+        const EdgeList& e = Nodes[EntryPointId]->OutEdges[layer];
+        if (e.Count > 0) {
+            int replacementId = -1, maxConnections = -1;
+            for (int i = 0; i < e.Count; i++) {
+                int neighborId = e.Buffer[i];
+                int cnt = Nodes[neighborId]->OutEdges[layer].Count;
+                if (cnt > maxConnections) {
+                    maxConnections = cnt;
+                    replacementId = neighborId;
+                }
+            }
+            EntryPointId = replacementId;
+            return true;
+        }
+        return false;
+    }
+
+    // GraphData.cs:172-189 (the node being removed is still active here and may be chosen -- as in the reference)
+    void ForceReplaceEntryPoint() {
+        if (Count() == 0) return;
+        int bestLayer = -1, bestId = -1;
+        for (int id : ActiveIds) {
+            int ml = Nodes[id]->MaxLayer();
+            if (ml > bestLayer) {
+                bestLayer = ml;
+                bestId = id;
+            }
+        }
+        EntryPointId = bestId;
+    }
+
+    // GraphConnector.cs:90-167
+    void RemoveConnectionsAtLayer(Node* removedNode, int layer, Counters* c) {
+        int maxEdges = MaxEdges(layer);
+        // DetachOutgoingReferences, GraphConnector.cs:277-288
+        {
+            const EdgeList& e = removedNode->OutEdges[layer];
+            for (int i = 0; i < e.Count; i++) Nodes[e.Buffer[i]]->InEdges[layer].Remove(removedNode->Id);
+        }
+        std::vector<int> affectedNodes(removedNode->InEdges[layer].Buffer.begin(),
+                                       removedNode->InEdges[layer].Buffer.begin() + removedNode->InEdges[layer].Count);
+        auto searchCandidates = SearchLayer<true>(removedNode->Id, layer, p.RemoveMaxCandidates, item(removedNode->Id), c, removedNode->Id);
+        std::vector<NodeDistance> candidateDistances;
+        for (int affectedNodeId : affectedNodes) {
+            Node* affectedNode = Nodes[affectedNodeId].get();
+            affectedNode->OutEdges[layer].Remove(removedNode->Id);  // RemoveOutEdge, :268-272
+            const EdgeList& out = affectedNode->OutEdges[layer];
+            std::vector<int> oldIds(out.Buffer.begin(), out.Buffer.begin() + out.Count);
+            std::set<int> oldSeen, newSeen;
+            candidateDistances.clear();
+            for (int id : oldIds) {
+                candidateDistances.push_back(NodeDistance{id, Distance(id, affectedNodeId, c)});
+                oldSeen.insert(id);
+            }
+            for (const NodeDistance& sc : searchCandidates) {
+                if (sc.Id == affectedNodeId) continue;
+                if (oldSeen.count(sc.Id)) continue;
+                candidateDistances.push_back(NodeDistance{sc.Id, Distance(sc.Id, affectedNodeId, c)});
+            }
+            EdgeList newOut = RelativeNeighborPruning(candidateDistances, maxEdges, c);
+            for (int j = 0; j < newOut.Count; j++) newSeen.insert(newOut.Buffer[j]);
+            for (int oldNeighborId : oldIds) {  // :135-143
+                if (newSeen.count(oldNeighborId)) continue;
+                affectedNode->OutEdges[layer].Remove(oldNeighborId);
+                Nodes[oldNeighborId]->InEdges[layer].Remove(affectedNodeId);
+            }
+            for (int j = 0; j < newOut.Count; j++) {  // :146-164
+                int newNeighborId = newOut.Buffer[j];
+                if (oldSeen.count(newNeighborId)) continue;
+                Node* newNeighbor = Nodes[newNeighborId].get();
+                if (newNeighbor->IsRemoved) continue;
+                affectedNode->OutEdges[layer].Add(newNeighborId);
+                newNeighbor->InEdges[layer].Add(affectedNodeId);
+            }
+        }
     }
 
     // HNSWIndex.cs:55-65
@@ -754,14 +907,17 @@ public:
     }
 
     // GraphNavigator.cs:123-189 (LOCK) / :194-256 (lock-free twin)
+    // `excluded`: the id rejected by the filter delegate of GraphConnector.cs:96 (id => id != removedNode.Id), -1 = no filter
     template <bool LOCK>
-    std::vector<NodeDistance> SearchLayer(int entryPointId, int layer, int k, const float* q, Counters* c) {
+    std::vector<NodeDistance> SearchLayer(int entryPointId, int layer, int k, const float* q, Counters* c, int excluded = -1) {
         BinaryHeap<FartherFirst> topCandidates(k);
         BinaryHeap<CloserFirst> candidates(k * 2);
         NodeDistance entry{entryPointId, Distance(entryPointId, q, c)};
         float farthest = std::numeric_limits<float>::max();
-        topCandidates.Push(entry);
-        farthest = entry.Dist;
+        if (entryPointId != excluded) {  // GraphNavigator.cs:133-137
+            topCandidates.Push(entry);
+            farthest = entry.Dist;
+        }
         candidates.Push(entry);
         VisitedList* visited = GetFreeVisitedList();
         visited->Add(entryPointId);
@@ -783,7 +939,7 @@ public:
                 if (topCandidates.Count() < k || d < farthest) {
                     NodeDistance sel{nb, d};
                     candidates.Push(sel);
-                    topCandidates.Push(sel);
+                    if (nb != excluded) topCandidates.Push(sel);  // GraphNavigator.cs:170-171
                     if (topCandidates.Count() > k) topCandidates.Pop();
                     if (topCandidates.Count() > 0) farthest = topCandidates.Peek().Dist;
                 }
@@ -986,6 +1142,8 @@ private:
     std::mutex indexLock, entryPointLock, rngLock, poolLock;
     DotNetRandom rng;
     bool threaded = false;
+    std::vector<int> ActiveSparse;  // ActiveSet.sparse (id -> position in ActiveIds), valid when sparse_valid
+    bool sparse_valid = false;
     std::vector<std::unique_ptr<VisitedList>> visitedPool;
 
     // VisitedListPool.cs:98-141
