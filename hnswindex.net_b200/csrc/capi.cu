@@ -88,8 +88,15 @@ int hnsw_remove(hnsw_handle handle, const int* ids, int count) {
     if (!handle) return 0;
     HNSW_TRY
     if (ids == nullptr || count <= 0) return 0;
-    if (!get(handle)->params().AllowRemovals) throw std::runtime_error("Removals are disabled in this index instance.");  // HNSWIndex.cs:85-86
-    throw std::runtime_error("Remove is outside the GPU-accelerated path of this engine (Add / KnnQuery / Serialize); not supported.");
+    get(handle)->remove(ids, count);  // throws when AllowRemovals is false (HNSWIndex.cs:85-86)
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_ids(hnsw_handle handle, int* outIds, int capacity) {
+    HNSW_TRY
+    const std::vector<int>& a = get(handle)->active_ids();
+    for (int i = 0; i < (int)a.size() && i < capacity && outIds != nullptr; ++i) outIds[i] = a[i];
+    return (int)a.size();
     HNSW_CATCH(-1)
 }
 

@@ -30,6 +30,7 @@ constexpr int kThreads = 32 * kWarpsPerBlock;
 //   adj0      [capacity][stride0] int32, layer-0 rows, unused slots = -1
 //   upper_off [capacity] int32, index of the node's layer-1 row in adjU, -1 for level-0 nodes
 //   adjU      [rowsU][strideU] int32, rows of layers 1..level of a node are consecutive
+//   rm_index  [capacity] int32 removal state (Node.IsRemoved): nothing points at a removed node, its rows are empty
 struct GraphView {
     const float* vectors;
     const double* norm_sqrt;
@@ -37,6 +38,7 @@ struct GraphView {
     int* adjU;
     const int* upper_off;
     int* locks;
+    const int* rm_index;  // [capacity] -1 alive, >= 0 position in the chunk being removed, -2 removed earlier
     int dim, pitch;
     int stride0, strideU;
     int max_edges;      // M (layer >= 1); layer 0 holds 2M

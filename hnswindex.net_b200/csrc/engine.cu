@@ -98,7 +98,7 @@ Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), par
 Index::~Index() {
     cudaSetDevice(device_);
     cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
-    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_);
+    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -114,6 +114,8 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "zero_copy") zero_copy_ = value != 0;
     else if (key == "build_batch_max") build_batch_max_ = std::max(1, value);
     else if (key == "build_batch_ratio") build_batch_ratio_ = std::max(1, value);
+    else if (key == "remove_batch_max") remove_batch_max_ = std::max(1, value);
+    else if (key == "remove_batch_ratio") remove_batch_ratio_ = std::max(1, value);
     else throw std::invalid_argument("unknown tuning key: " + key);
 }
 
@@ -125,6 +127,7 @@ GraphView Index::view() const {
     g.adjU = d_adjU_;
     g.upper_off = d_upper_off_;
     g.locks = d_locks_;
+    g.rm_index = d_rm_index_;
     g.dim = dim_;
     g.pitch = pitch_;
     g.stride0 = stride0_;
@@ -163,6 +166,7 @@ void Index::ensure_capacity(int needed) {
     grow_device(d_adj0_, o * stride0_, n * stride0_, 0xFF, stream_);
     grow_device(d_upper_off_, o, n, 0xFF, stream_);
     grow_device(d_locks_, o, n, 0, stream_);
+    grow_device(d_rm_index_, o, n, 0xFF, stream_);
     grow_device(d_levels_, o, n, 0, stream_);
     dev_capacity_ = capacity_;
 }
@@ -208,53 +212,82 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     std::lock_guard<std::mutex> lock(mu_);
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
-    std::vector<int> lv;
-    lv.reserve(count);
-    int nnew = 0;
-    bool all = true;
+    std::vector<int> lv, ids_new, src_row;
+    lv.reserve(count); ids_new.reserve(count); src_row.reserve(count);
+    int nfresh = 0, nreused = 0;
     for (int i = 0; i < count; ++i) {
         // GraphData.GetRandomLayer, GraphData.cs:211-219
         const float r = rng_.NextSingle();
         const double x = -std::log((double)r) * params_.DistributionRate;
         if (!(x < 2147483648.0) || x < 0.0) {  // r == 0: the reference's cast goes negative and the item is dropped (:81-82)
             out_ids[i] = -1;
-            all = false;
             continue;
         }
         int level = (int)x;
         if (level > 30) level = 30;
-        out_ids[i] = length_ + nnew++;
+        int id;
+        if (params_.AllowRemovals && !removed_stack_.empty()) {  // "Search for empty spot first", GraphData.cs:84-91
+            id = removed_stack_.back();
+            removed_stack_.pop_back();
+            ++nreused;
+        } else {
+            id = length_ + nfresh++;
+        }
+        out_ids[i] = id;
+        ids_new.push_back(id);
         lv.push_back(level);
+        src_row.push_back(i);
     }
+    const int nnew = (int)ids_new.size();
     if (nnew == 0) return count;
     const int first = length_;
-    ensure_capacity(first + nnew);
+    ensure_capacity(first + nfresh);
 
-    // vectors -> slab rows [first, first+nnew)
-    if (all) {
+    // vectors -> slab rows
+    if (nreused == 0 && nnew == count) {
         HNSW_CUDA_CHECK(cudaMemcpy2DAsync(d_vectors_ + (size_t)first * pitch_, (size_t)pitch_ * 4, vectors, (size_t)dim * 4, (size_t)dim * 4,
                                           (size_t)nnew, cudaMemcpyHostToDevice, stream_));
     } else {
-        int j = 0;
-        for (int i = 0; i < count; ++i)
-            if (out_ids[i] >= 0) {
-                HNSW_CUDA_CHECK(cudaMemcpyAsync(d_vectors_ + (size_t)(first + j) * pitch_, vectors + (size_t)i * dim, (size_t)dim * 4,
-                                                cudaMemcpyHostToDevice, stream_));
-                ++j;
-            }
+        for (int j = 0; j < nnew; ++j)
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_vectors_ + (size_t)ids_new[j] * pitch_, vectors + (size_t)src_row[j] * dim, (size_t)dim * 4,
+                                            cudaMemcpyHostToDevice, stream_));
     }
-    // NewNode (GraphData.cs:224-242): rows for layers 0..level
-    levels_.resize(first + nnew);
-    upper_off_.resize(first + nnew);
+    // NewNode (GraphData.cs:224-242): rows for layers 0..level.  A reused slot gets fresh upper rows; its layer-0 row was
+    // emptied when the old item was removed.
+    levels_.resize(first + nfresh);
+    upper_off_.resize(first + nfresh);
+    removed_.resize(first + nfresh, 0);
     for (int j = 0; j < nnew; ++j) {
-        levels_[first + j] = lv[j];
-        upper_off_[first + j] = lv[j] > 0 ? upper_rows_ : -1;
+        const int id = ids_new[j];
+        levels_[id] = lv[j];
+        upper_off_[id] = lv[j] > 0 ? upper_rows_ : -1;
         upper_rows_ += lv[j];
+        removed_[id] = 0;
+        active_add(id);
     }
     ensure_upper_rows(upper_rows_);
-    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_levels_ + first, levels_.data() + first, (size_t)nnew * 4, cudaMemcpyHostToDevice, stream_));
-    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_ + first, upper_off_.data() + first, (size_t)nnew * 4, cudaMemcpyHostToDevice, stream_));
-    if (metric_ == COSINE) launch_item_norms(d_vectors_, pitch_, dim_, first, nnew, d_norms_, stream_);
+    if ((size_t)nnew > new_ids_cap_) {
+        cudaFree(d_new_ids_); d_new_ids_ = nullptr; new_ids_cap_ = 0;
+        HNSW_CUDA_CHECK(cudaMalloc(&d_new_ids_, (size_t)nnew * sizeof(int)));
+        new_ids_cap_ = nnew;
+    }
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_new_ids_, ids_new.data(), (size_t)nnew * 4, cudaMemcpyHostToDevice, stream_));
+    if (nreused == 0) {
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_levels_ + first, levels_.data() + first, (size_t)nfresh * 4, cudaMemcpyHostToDevice, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_ + first, upper_off_.data() + first, (size_t)nfresh * 4, cudaMemcpyHostToDevice, stream_));
+        if (metric_ == COSINE) launch_item_norms(d_vectors_, pitch_, dim_, first, nfresh, d_norms_, stream_);
+    } else {
+        const size_t n = levels_.size();
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_levels_, levels_.data(), n * 4, cudaMemcpyHostToDevice, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_, upper_off_.data(), n * 4, cudaMemcpyHostToDevice, stream_));
+        launch_set_rm_index(d_rm_index_, d_new_ids_, nnew, false, -1, stream_);  // alive again
+        if (metric_ == COSINE) {
+            if (nfresh > 0) launch_item_norms(d_vectors_, pitch_, dim_, first, nfresh, d_norms_, stream_);
+            for (int j = 0; j < nnew; ++j)
+                if (ids_new[j] < first) launch_item_norms(d_vectors_, pitch_, dim_, ids_new[j], 1, d_norms_, stream_);
+        }
+    }
+    length_ = first + nfresh;
 
     if (tuning_.vis_global_build > 0) {  // room for 16 warps per SM
         int slots = 1024;
@@ -268,33 +301,33 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     }
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     int done = 0;
+    int linked = this->count() - nnew;  // nodes a new node can reach (everything active before this call, then batch by batch)
     while (done < nnew) {
-        const int v = first + done;
+        const int v = ids_new[done];
         if (entry_ < 0) {  // GraphConnector.cs:28-33: the first node becomes the entry point, no links
             entry_ = v;
             top_ = levels_[v];
-            length_ = v + 1;
             ++done;
+            ++linked;
             continue;
         }
         int batch = 1;
         const bool new_top = levels_[v] > top_;
         if (!new_top) {
-            const int b = std::max(1, std::min(build_batch_max_, v / build_batch_ratio_));
-            while (done + batch < nnew && batch < b && levels_[v + batch] <= top_) ++batch;
+            const int b = std::max(1, std::min(build_batch_max_, linked / build_batch_ratio_));
+            while (done + batch < nnew && batch < b && levels_[ids_new[done + batch]] <= top_) ++batch;
         }
-        length_ = v;  // nodes visible to this batch
-        launch_build_batch((int)metric_, view(), d_levels_, v, batch, params_.MaxCandidates, d_counters_, d_build_prof_, d_gvis_, gvis_words_, tuning_,
-                           stream_);
+        // nodes of the same batch cannot reach each other: nothing points at them before the link kernel runs
+        launch_build_batch((int)metric_, view(), d_levels_, d_new_ids_ + done, batch, params_.MaxCandidates, d_counters_, d_build_prof_, d_gvis_,
+                           gvis_words_, tuning_, stream_);
         stats_.build_launches += 2;
         if (new_top) {  // GraphConnector.cs:36-41
             entry_ = v;
             top_ = levels_[v];
         }
         done += batch;
-        length_ = v + batch;
+        linked += batch;
     }
-    length_ = first + nnew;
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     int err = 0;
     HNSW_CUDA_CHECK(cudaMemcpyAsync(&err, d_counters_ + 2, sizeof(int), cudaMemcpyDeviceToHost, stream_));
@@ -307,6 +340,144 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
         throw std::runtime_error("build: a node lock could not be acquired (index may be inconsistent)");
     }
     return count;
+}
+
+// ActiveSet.cs:69-93
+void Index::active_add(int id) {
+    if ((int)active_sparse_.size() <= id) active_sparse_.resize((size_t)id + 1, -1);
+    active_sparse_[id] = (int)active_dense_.size();
+    active_dense_.push_back(id);
+}
+void Index::active_remove(int id) {
+    const int idx = active_sparse_[id];
+    const int last_id = active_dense_.back();
+    active_dense_.pop_back();
+    if (idx < (int)active_dense_.size()) {  // move last into the removed slot
+        active_dense_[idx] = last_id;
+        active_sparse_[last_id] = idx;
+    }
+    active_sparse_[id] = -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Remove (HNSWIndex.cs:83-100, GraphConnector.cs:53-167, GraphData.cs:124-199) in chunks; see remove_kernels.cu
+// ---------------------------------------------------------------------------------------------
+std::vector<int> Index::read_row(int id, int layer) {
+    const int stride = layer == 0 ? stride0_ : strideU_;
+    const int* src = layer == 0 ? d_adj0_ + (size_t)id * stride0_ : d_adjU_ + ((size_t)upper_off_[id] + (layer - 1)) * strideU_;
+    std::vector<int> row(stride);
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(row.data(), src, (size_t)stride * 4, cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    int n = 0;
+    while (n < stride && row[n] >= 0) ++n;
+    row.resize(n);
+    return row;
+}
+
+// ReplaceEntryPointIfNeeded (GraphConnector.cs:72-85) for an entry point that is part of the chunk: walk its layers from
+// the top; the first layer with a surviving neighbour hands the role to the neighbour with most links on that layer
+// (GraphData.TryReplaceEntryPoint, :146-166); otherwise the highest active node takes over (ForceReplaceEntryPoint,
+// :172-189 -- the reference may pick the node being removed there; the chunk is excluded here).
+void Index::replace_entry_point(const std::vector<unsigned char>& in_chunk, int chunk_size) {
+    const int ep = entry_;
+    for (int layer = levels_[ep]; layer >= 0; --layer) {
+        int best = -1, best_deg = -1;
+        for (int nb : read_row(ep, layer)) {
+            if (in_chunk[nb]) continue;
+            const int deg = (int)read_row(nb, layer).size();
+            if (deg > best_deg) { best_deg = deg; best = nb; }
+        }
+        if (best >= 0) {
+            entry_ = best;
+            top_ = levels_[best];
+            return;
+        }
+    }
+    if (count() - chunk_size <= 0) {
+        entry_ = -1;
+        top_ = -1;
+        return;
+    }
+    int best = -1, best_layer = -1;
+    for (int id : active_dense_)
+        if (!in_chunk[id] && levels_[id] > best_layer) { best_layer = levels_[id]; best = id; }
+    entry_ = best;
+    top_ = best_layer;
+}
+
+void Index::remove_chunk(const int* ids, int n) {
+    std::vector<unsigned char> in_chunk(length_, 0);
+    for (int i = 0; i < n; ++i) in_chunk[ids[i]] = 1;
+    if (in_chunk[entry_]) replace_entry_point(in_chunk, n);
+
+    // work items: (node, layer) for every layer of every removed node, a node's items consecutive from layer 0
+    std::vector<int> item_node, item_layer, item_first(n);
+    for (int i = 0; i < n; ++i) {
+        item_first[i] = (int)item_node.size();
+        for (int l = 0; l <= levels_[ids[i]]; ++l) { item_node.push_back(ids[i]); item_layer.push_back(l); }
+    }
+    const int nitems = (int)item_node.size();
+    const int rmc = std::max(1, params_.RemoveMaxCandidates);
+    const size_t max_rows = (size_t)length_ + (size_t)upper_rows_;
+    int *d_ids = nullptr, *d_item_node = nullptr, *d_item_layer = nullptr, *d_item_first = nullptr, *d_cand = nullptr;
+    int2* d_aff = nullptr;
+    auto free_all = [&]() { cudaFree(d_ids); cudaFree(d_item_node); cudaFree(d_item_layer); cudaFree(d_item_first); cudaFree(d_cand); cudaFree(d_aff); };
+    try {
+        HNSW_CUDA_CHECK(cudaMalloc(&d_ids, (size_t)n * 4));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_item_node, (size_t)nitems * 4));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_item_layer, (size_t)nitems * 4));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_item_first, (size_t)n * 4));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_cand, (size_t)nitems * rmc * 4));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_aff, max_rows * sizeof(int2)));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_ids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_node, item_node.data(), (size_t)nitems * 4, cudaMemcpyHostToDevice, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_layer, item_layer.data(), (size_t)nitems * 4, cudaMemcpyHostToDevice, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_first, item_first.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+        launch_set_rm_index(d_rm_index_, d_ids, n, true, 0, stream_);
+        const GraphView g = view();
+        launch_remove_search((int)metric_, g, d_item_node, d_item_layer, nitems, rmc, d_cand, d_counters_ + 4, stream_);
+        launch_find_affected(g, d_levels_, length_, d_aff, d_counters_ + 5, stream_);
+        unsigned naff = 0;
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(&naff, d_counters_ + 5, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
+        HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        launch_relink((int)metric_, g, d_aff, (int)naff, d_item_first, d_cand, rmc, d_counters_ + 4, stream_);
+        launch_clear_rows(g, d_item_node, d_item_layer, nitems, stream_);
+        launch_set_rm_index(d_rm_index_, d_ids, n, false, -2, stream_);
+        HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        stats_.remove_launches += 6;
+    } catch (...) {
+        free_all();
+        throw;
+    }
+    free_all();
+    for (int i = 0; i < n; ++i) {  // GraphData.RemoveItem, GraphData.cs:124-128
+        removed_[ids[i]] = 1;
+        removed_stack_.push_back(ids[i]);
+        active_remove(ids[i]);
+    }
+}
+
+void Index::remove(const int* ids, int count) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (!params_.AllowRemovals) throw std::runtime_error("Removals are disabled in this index instance.");  // HNSWIndex.cs:85-86
+    if (count <= 0) return;
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    {
+        std::vector<unsigned char> seen(length_, 0);
+        for (int i = 0; i < count; ++i) {
+            const int id = ids[i];
+            if (id < 0 || id >= length_) throw std::out_of_range("remove: item index " + std::to_string(id) + " is out of range");
+            if (removed_[id]) throw std::invalid_argument("remove: item " + std::to_string(id) + " has already been removed");
+            if (seen[id]) throw std::invalid_argument("remove: item " + std::to_string(id) + " is listed twice");
+            seen[id] = 1;
+        }
+    }
+    int done = 0;
+    while (done < count) {
+        const int chunk = std::max(1, std::min(std::min(remove_batch_max_, this->count() / remove_batch_ratio_), count - done));
+        remove_chunk(ids + done, chunk);
+        done += chunk;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -341,7 +512,7 @@ static T* pinned_alias(const T* host) {
 void Index::knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists, int layer) {
     std::lock_guard<std::mutex> lock(mu_);
     if (count <= 0 || k < 1) return;
-    if (length_ <= 0) {  // HNSWIndex.cs:109
+    if (this->count() <= 0) {  // HNSWIndex.cs:109
         fill_empty(out_ids, out_dists, (size_t)count * k);
         return;
     }
@@ -379,7 +550,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
 void Index::knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists) {
     std::lock_guard<std::mutex> lock(mu_);
     if (count <= 0 || k < 1) return;
-    if (length_ <= 0) throw std::runtime_error("knn_query_device on an empty index");
+    if (this->count() <= 0) throw std::runtime_error("knn_query_device on an empty index");
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
     if (collect_stats_) ensure_stats(count);
@@ -400,7 +571,7 @@ void Index::knn_query_device(const float* d_queries, int count, int dim, int k, 
 // outputs are [count][L][k] (pass null pointers to query L only).
 int Index::multilayer_knn_query(const float* queries, int count, int dim, int k, int max_layer, int min_layer, int* out_ids, float* out_dists) {
     std::lock_guard<std::mutex> lock(mu_);
-    if (length_ <= 0 || k < 1) return 0;  // HNSWIndex.cs:176
+    if (this->count() <= 0 || k < 1) return 0;  // HNSWIndex.cs:176
     if (max_layer < 0) throw std::out_of_range("maxLayer must not be negative");
     const int top_l = std::min(top_, max_layer);
     const int layers = top_l + 1;
@@ -421,7 +592,7 @@ int Index::multilayer_knn_query(const float* queries, int count, int dim, int k,
 void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
     std::lock_guard<std::mutex> lock(mu_);
     if (count <= 0 || k < 1) return;
-    if (length_ <= 0) {
+    if (this->count() <= 0) {
         fill_empty(out_ids, out_dists, (size_t)count * k);
         return;
     }
@@ -455,7 +626,7 @@ void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_
 void Index::range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out) {
     std::lock_guard<std::mutex> lock(mu_);
     out.assign((size_t)std::max(count, 0), {});
-    if (count <= 0 || length_ <= 0) return;  // HNSWIndex.cs:146
+    if (count <= 0 || this->count() <= 0) return;  // HNSWIndex.cs:146
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
     ensure_query_scratch(count, 1);
@@ -532,6 +703,13 @@ void Index::export_graph(HostGraph& g, bool with_vectors) {
     g.strideU = strideU_;
     g.levels.assign(levels_.begin(), levels_.begin() + length_);
     g.upper_off.assign(upper_off_.begin(), upper_off_.begin() + length_);
+    if (count() != length_ || !removed_stack_.empty()) {  // removal state travels only when there is any
+        g.removed.assign(removed_.begin(), removed_.begin() + length_);
+        g.removed_stack = removed_stack_;
+    }
+    bool identity = (int)active_dense_.size() == length_;
+    for (int i = 0; identity && i < length_; ++i) identity = active_dense_[i] == i;
+    if (!identity) g.active = active_dense_;
     if (with_vectors) g.vectors.resize((size_t)length_ * g.dim);
     g.adj0.resize((size_t)length_ * stride0_);
     g.adjU.resize((size_t)upper_rows_ * strideU_);
@@ -564,14 +742,14 @@ int median_like_reference(std::vector<int>& v) {  // HNSWInfo.cs:45-51
 std::vector<Index::LayerInfo> Index::get_info() {
     std::lock_guard<std::mutex> lock(mu_);
     std::vector<LayerInfo> out;
-    if (length_ <= 0) return out;
+    if (count() <= 0) return out;
     HostGraph g;
     export_graph(g, false);
     const bool has_in = params_.AllowRemovals;
     for (int layer = 0; layer <= top_; ++layer) {
         std::vector<int> outdeg, indeg_all(g.length, 0), ids;
         for (int i = 0; i < g.length; ++i) {
-            if (g.levels[i] < layer) continue;
+            if (g.levels[i] < layer || removed_[i]) continue;  // data.ActiveIds only (HNSWIndex.cs:194)
             int stride;
             const int* row = host_row(g, i, layer, stride);
             int d = 0;
@@ -603,7 +781,7 @@ std::vector<Index::LayerInfo> Index::get_info() {
 std::vector<int> Index::connected_component_counts() {
     std::lock_guard<std::mutex> lock(mu_);
     std::vector<int> counts;
-    if (length_ <= 0) return counts;
+    if (count() <= 0) return counts;
     HostGraph g;
     export_graph(g, false);
     counts.assign(top_ + 1, 0);
@@ -615,7 +793,7 @@ std::vector<int> Index::connected_component_counts() {
             return x;
         };
         for (int i = 0; i < g.length; ++i) {
-            if (g.levels[i] < layer) continue;
+            if (g.levels[i] < layer || removed_[i]) continue;
             int stride;
             const int* row = host_row(g, i, layer, stride);
             for (int j = 0; j < stride && row[j] >= 0; ++j) {
@@ -626,7 +804,7 @@ std::vector<int> Index::connected_component_counts() {
         }
         int c = 0;
         for (int i = 0; i < g.length; ++i)
-            if (g.levels[i] >= layer && find(i) == i) ++c;
+            if (g.levels[i] >= layer && !removed_[i] && find(i) == i) ++c;
         counts[layer] = c;
     }
     return counts;
@@ -642,6 +820,7 @@ void Index::serialize(const std::string& path, bool packed) {
 void Index::upload_graph(const HostGraph& g) {
     const int n = g.length;
     if (n == 0) return;
+    if (g.entry < 0 && g.active.empty() && g.removed.empty()) throw std::runtime_error("snapshot: no entry point");
     ensure_dim(g.dim);
     capacity_ = std::max(capacity_, std::max(g.capacity, 1));
     ensure_capacity(n);
@@ -671,7 +850,31 @@ void Index::upload_graph(const HostGraph& g) {
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
     length_ = n;
     entry_ = g.entry;
-    top_ = levels_[entry_];
+    top_ = entry_ >= 0 ? levels_[entry_] : -1;
+    // removal state
+    removed_.assign(n, 0);
+    if (!g.removed.empty()) removed_.assign(g.removed.begin(), g.removed.end());
+    removed_stack_ = g.removed_stack;
+    active_dense_.clear();
+    active_sparse_.assign(n, -1);
+    if (!g.active.empty() || !g.removed.empty()) {
+        for (int id : g.active) {
+            if (id < 0 || id >= n || removed_[id] || active_sparse_[id] >= 0) throw std::runtime_error("snapshot: inconsistent ActiveNodes");
+            active_add(id);
+        }
+    } else {
+        for (int i = 0; i < n; ++i) active_add(i);
+    }
+    std::vector<int> rm_index(n, -1);
+    int nremoved = 0;
+    for (int i = 0; i < n; ++i)
+        if (removed_[i]) { rm_index[i] = -2; ++nremoved; }
+    if (nremoved + (int)active_dense_.size() != n) throw std::runtime_error("snapshot: ActiveNodes and IsRemoved flags disagree");
+    if (nremoved > 0) {
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_rm_index_, rm_index.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+        HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+    if (entry_ >= 0 && removed_[entry_]) throw std::runtime_error("snapshot: the entry point is a removed node");
 }
 
 Index* Index::from_snapshot(MetricKind metric, const std::string& path) {

@@ -43,6 +43,7 @@ struct IndexStats {
     unsigned long long nexp = 0;
     unsigned long long row_words = 0;
     unsigned long long search_launches = 0, build_launches = 0;  // kernels launched since creation
+    unsigned long long remove_launches = 0;
 };
 
 class Index {
@@ -55,6 +56,10 @@ public:
     static Index* from_snapshot(MetricKind metric, const std::string& path);
 
     int add(const float* vectors, int count, int dim, int* out_ids);
+    // HNSWIndex.Remove(List<int>) (HNSWIndex.cs:83-100); throws when AllowRemovals is false
+    void remove(const int* ids, int count);
+    // HNSWIndex.Ids() (HNSWIndex.cs:242-245): active ids in ActiveSet order
+    const std::vector<int>& active_ids() const { return active_dense_; }
     // `layer`: HNSWIndex.cs:107/129 optional argument (0 = base layer)
     void knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists, int layer = 0);
     // MultiLayerKnnQuery (HNSWIndex.cs:173-187), batched; returns the layer count, outputs [count][layers][k]
@@ -68,7 +73,8 @@ public:
     void range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out);
     void serialize(const std::string& path, bool packed);
 
-    int count() const { return length_; }
+    int count() const { return (int)active_dense_.size(); }  // GraphData.Count: active (not removed) items
+    int length() const { return length_; }                     // GraphData.Length: slots in use
     int dim() const { return dim_; }
     const Parameters& params() const { return params_; }
     void set_min_nn(int v) { params_.MinNN = v; }
@@ -100,6 +106,11 @@ private:
     void upload_graph(const HostGraph& g);
     GraphView view() const;
     void fetch_query_stats(int count);
+    void active_add(int id);
+    void active_remove(int id);
+    void remove_chunk(const int* ids, int n);
+    void replace_entry_point(const std::vector<unsigned char>& in_chunk, int chunk_size);
+    std::vector<int> read_row(int id, int layer);
 
     MetricKind metric_;
     Parameters params_;
@@ -117,6 +128,13 @@ private:
     int build_batch_ratio_ = 16;   // ... and at most 1/ratio of the nodes already linked
 
     std::vector<int> levels_, upper_off_;
+    // removal state (GraphData.RemovedIndexes, ActiveSet, Node.IsRemoved)
+    std::vector<unsigned char> removed_;
+    std::vector<int> active_dense_, active_sparse_, removed_stack_;
+    int remove_batch_max_ = 4096, remove_batch_ratio_ = 16;
+    int* d_rm_index_ = nullptr;   // [capacity] see GraphView::rm_index
+    int* d_new_ids_ = nullptr;    // ids of the nodes of the running add()
+    size_t new_ids_cap_ = 0;
     int upper_rows_ = 0, upper_rows_cap_ = 0;
 
     float* d_vectors_ = nullptr;

@@ -81,6 +81,7 @@ exact_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
         }
         double an = 0.0;
         if (METRIC == COSINE && active) an = __ldg(g.norm_sqrt + id);
+        const bool live = active && __ldg(g.rm_index + id) == -1;  // removed items (HNSWIndex.Remove) are not candidates
 #pragma unroll
         for (int t = 0; t < TQ; ++t) {
             const float s0 = __fadd_rn(acc[t][0], __shfl_xor_sync(FULL, acc[t][0], 1));
@@ -106,7 +107,7 @@ exact_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
             u64* list = mylists + (size_t)t * k;
             st.far_ord = st.n == k ? key_ord(list[k - 1]) : 0xFFFFFFFFu;
             const u64 mykey = make_key(r, id);
-            bool pending = active && h == 0 && (q0 + t < nq);
+            bool pending = live && h == 0 && (q0 + t < nq);
             for (;;) {
                 const bool want = pending && (st.n < k || mykey < list[k - 1]);
                 const unsigned mk = __ballot_sync(FULL, want);

@@ -37,11 +37,11 @@ void launch_multilayer_search(int metric, const GraphView& g, const float* d_que
 // per-item sqrt((double)normA) in the cosine metric's accumulation order
 void launch_item_norms(const float* d_vectors, int pitch, int dim, int first, int count, double* d_norm_sqrt, cudaStream_t stream);
 
-// K4+K5: for new nodes [first, first+count): descent, per-layer beam search (ef = MaxCandidates) against the
+// K4+K5: for the new nodes d_new_ids[0..count): descent, per-layer beam search (ef = MaxCandidates) against the
 // graph as it stands, relative-neighbour selection, write the node's own rows.
 // K6: reverse links with per-node locks and overflow pruning.
 // d_build_prof: 16 u64 cycle / work counters accumulated by the kernels (build_kernels.cu BuildProf).
-void launch_build_batch(int metric, const GraphView& g, const int* d_levels, int first, int count, int ef_construction,
+void launch_build_batch(int metric, const GraphView& g, const int* d_levels, const int* d_new_ids, int count, int ef_construction,
                         unsigned* d_work_counter, u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream);
 
 // RangeQuery (HNSWIndex.cs:144-168): traversal of all in-range nodes reachable from the layer-0 entry.  Work item w handles
@@ -55,6 +55,19 @@ void launch_range_search(int metric, const GraphView& g, const float* d_queries,
 void launch_exact_knn(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists,
                       void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t exact_knn_scratch_bytes(int nq, int k, int count);
+
+// Remove (GraphConnector.cs:53-167) for one chunk of removed nodes, see remove_kernels.cu.
+//   rm_index[id] = position of id in the chunk (use_index) or `value`
+void launch_set_rm_index(int* d_rm_index, const int* d_ids, int n, bool use_index, int value, cudaStream_t stream);
+//   per (removed node, layer) item: beam search from the node, width RemoveMaxCandidates + 1 -> d_cand [nitems][rmc] (-1 padded)
+void launch_remove_search(int metric, const GraphView& g, const int* d_item_node, const int* d_item_layer, int nitems, int rmc, int* d_cand,
+                          unsigned* d_work_counter, cudaStream_t stream);
+//   every live row naming a node of the chunk -> d_affected (node, layer), count in *d_n_affected
+void launch_find_affected(const GraphView& g, const int* d_levels, int length, int2* d_affected, unsigned* d_n_affected, cudaStream_t stream);
+//   rewrite each affected row: remaining neighbours + search results of its removed neighbours, heuristic
+void launch_relink(int metric, const GraphView& g, const int2* d_affected, int naffected, const int* d_item_first, const int* d_cand, int rmc,
+                   unsigned* d_work_counter, cudaStream_t stream);
+void launch_clear_rows(const GraphView& g, const int* d_item_node, const int* d_item_layer, int nitems, cudaStream_t stream);
 
 // K7: merge `parts` sorted top-k lists per query: in_* are [parts][nq][k], out_* [nq][k]
 void launch_merge_topk(const int* d_in_ids, const float* d_in_dists, int parts, int nq, int k, int* d_out_ids, float* d_out_dists,

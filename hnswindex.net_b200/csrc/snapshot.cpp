@@ -189,9 +189,12 @@ void write_snapshot(const HostGraph& g, const std::string& path, bool packed) {
         cnt = row_count(row, stride);
         return row;
     };
+    const bool any_removed = !g.removed.empty();
+    auto is_removed = [&](int i) { return any_removed && g.removed[i] != 0; };
     auto node_body = [&](int i) -> uint64_t {
         uint64_t b = 0;
         if (i != 0) b += 1 + vsize(sx(i));
+        if (is_removed(i)) b += 2;  // IsRemoved = true (Node.cs:18-19)
         for (int l = 0; l <= g.levels[i]; l++) {
             int cnt; const int* row = out_row(i, l, cnt);
             const uint64_t eb = edge_list_body(row, cnt, packed);
@@ -218,18 +221,24 @@ void write_snapshot(const HostGraph& g, const std::string& path, bool packed) {
     if (p.RandomSeed) params_body += 1 + vsize(sx(p.RandomSeed));
     if (p.AllowRemovals) params_body += 2;
 
-    std::vector<int> active(n);
-    for (int i = 0; i < n; i++) active[i] = i;  // ActiveSet.dense[..count] in insertion order (no removals)
+    // ActiveSet.dense[..count]: insertion order, a removal moves the last entry into the hole (ActiveSet.cs:79-93)
+    std::vector<int> active;
+    if (!g.active.empty() || any_removed) active = g.active;
+    else { active.resize(n); for (int i = 0; i < n; i++) active[i] = i; }
+    const int nactive = (int)active.size();
+    // GraphData.RemovedIndexes: a ConcurrentStack enumerates from its top [inferred: protobuf-net writes in enumeration order]
+    std::vector<int> removed_top_first(g.removed_stack.rbegin(), g.removed_stack.rend());
 
     uint64_t data_body = 0;
     for (int i = 0; i < n; i++) { const uint64_t nb = node_body(i); data_body += 1 + vsize(nb) + nb; }
-    data_body += int32s_size(1, active.data(), n, packed);
+    data_body += int32s_size(1, active.data(), nactive, packed);
+    data_body += int32s_size(1, removed_top_first.data(), (int)removed_top_first.size(), packed);
     const uint64_t ib = item_body(g.dim, packed);
     data_body += (uint64_t)n * (1 + vsize(ib) + ib);
     if (g.entry != 0) data_body += 1 + vsize(sx(g.entry));
     if (g.capacity) data_body += 1 + vsize(sx(g.capacity));
     if (g.length) data_body += 1 + vsize(sx(g.length));
-    if (n) data_body += 1 + vsize(sx(n));
+    if (nactive) data_body += 1 + vsize(sx(nactive));
 
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) throw std::runtime_error("snapshot: cannot create " + path);
@@ -252,6 +261,7 @@ void write_snapshot(const HostGraph& g, const std::string& path, bool packed) {
             s.tag(1, 2);
             s.varint(node_body(i));
             if (i != 0) { s.tag(1, 0); s.varint(sx(i)); }
+            if (is_removed(i)) { s.tag(2, 0); s.varint(1); }
             for (int l = 0; l <= g.levels[i]; l++) {
                 int cnt; const int* row = out_row(i, l, cnt);
                 emit_edge_list(s, 3, row, cnt, packed);
@@ -262,7 +272,7 @@ void write_snapshot(const HostGraph& g, const std::string& path, bool packed) {
                     emit_edge_list(s, 4, ie.ids.data() + ie.off[i], (int)(ie.off[i + 1] - ie.off[i]), packed);
                 }
         }
-        emit_int32s(s, 2, active.data(), n, packed);
+        emit_int32s(s, 2, active.data(), nactive, packed);
         for (int i = 0; i < n; i++) {
             const float* v = g.vectors.data() + (size_t)i * g.dim;
             s.tag(3, 2);
@@ -276,10 +286,11 @@ void write_snapshot(const HostGraph& g, const std::string& path, bool packed) {
                 for (int d = 0; d < g.dim; d++) { s.byte(0x0D); s.put(v + d, 4); }
             }
         }
+        emit_int32s(s, 4, removed_top_first.data(), (int)removed_top_first.size(), packed);
         if (g.entry != 0) { s.tag(5, 0); s.varint(sx(g.entry)); }
         if (g.capacity) { s.tag(6, 0); s.varint(sx(g.capacity)); }
         if (g.length) { s.tag(7, 0); s.varint(sx(g.length)); }
-        if (n) { s.tag(8, 0); s.varint(sx(n)); }
+        if (nactive) { s.tag(8, 0); s.varint(sx(nactive)); }
         s.flush();
     } catch (...) {
         std::fclose(f);
@@ -334,7 +345,8 @@ void read_snapshot(const std::string& path, HostGraph& g) {
     g.strideU = stride_for(p.MaxEdges);
 
     int count_field = 0;
-    std::vector<int> row, active;
+    std::vector<int> row, active, removed_top_first;
+    std::vector<int> removed_nodes;
     {
         Reader root(bytes.data(), bytes.data() + bytes.size());
         int field, wt;
@@ -381,8 +393,8 @@ void read_snapshot(const std::string& path, HostGraph& g) {
                         } else if (f3 == 4 && w3 == 2) { any_in = true; nr.skip(w3); }
                         else nr.skip(w3);
                     }
-                    if (removed) throw std::runtime_error("snapshot: removed nodes are not supported by this engine");
-                    if (id != idx) throw std::runtime_error("snapshot: node ids must be dense (no removed slots)");
+                    if (removed) removed_nodes.push_back(idx);
+                    if (id != idx) throw std::runtime_error("snapshot: node ids must equal their slot");
                     if (nout < 1) throw std::runtime_error("snapshot: node without layer-0 edge list");
                     g.levels.push_back(nout - 1);
                 } else if (f2 == 2) read_int32s(r, w2, active);
@@ -405,7 +417,7 @@ void read_snapshot(const std::string& path, HostGraph& g) {
                     if (items_seen == 0) g.dim = d;
                     else if (d != g.dim) throw std::runtime_error("snapshot: items have different lengths");
                     items_seen++;
-                } else if (f2 == 4) { std::vector<int> rem; read_int32s(r, w2, rem); if (!rem.empty()) throw std::runtime_error("snapshot: removed indexes are not supported by this engine"); }
+                } else if (f2 == 4) read_int32s(r, w2, removed_top_first);
                 else if (f2 == 5 && w2 == 0) { g.entry = (int32_t)r.varint(); have_entry = true; }
                 else if (f2 == 6 && w2 == 0) g.capacity = (int32_t)r.varint();
                 else if (f2 == 7 && w2 == 0) g.length = (int32_t)r.varint();
@@ -423,9 +435,27 @@ void read_snapshot(const std::string& path, HostGraph& g) {
     if (!have_allow) p.AllowRemovals = any_in || n == 0;
     if (g.length == 0) g.length = n;
     if (g.length != n) throw std::runtime_error("snapshot: Length does not match the number of nodes");
-    if (count_field != 0 && count_field != n) throw std::runtime_error("snapshot: Count does not match the number of nodes");
+    // removal state: the reference leaves the rows of a removed node stale (nothing points at it); they are emptied here
+    if (!removed_nodes.empty() || !removed_top_first.empty()) {
+        g.removed.assign((size_t)n, 0);
+        for (int i : removed_nodes) {
+            g.removed[i] = 1;
+            for (int j = 0; j < g.stride0; j++) g.adj0[(size_t)i * g.stride0 + j] = -1;
+            for (int l = 1; l <= g.levels[i]; l++)
+                for (int j = 0; j < g.strideU; j++) g.adjU[((size_t)g.upper_off[i] + (l - 1)) * g.strideU + j] = -1;
+        }
+        g.removed_stack.assign(removed_top_first.rbegin(), removed_top_first.rend());
+        g.active = active;
+        if ((int)active.size() + (int)removed_nodes.size() != n) throw std::runtime_error("snapshot: ActiveNodes and IsRemoved flags disagree");
+    } else if ((int)active.size() == n) {
+        bool identity = true;
+        for (int i = 0; identity && i < n; i++) identity = active[i] == i;
+        if (!identity) g.active = active;
+    }
+    const int nactive = n - (int)removed_nodes.size();
+    if (count_field != 0 && count_field != nactive) throw std::runtime_error("snapshot: Count does not match the number of active nodes");
     if (g.capacity < n) g.capacity = std::max(n, p.CollectionSize);
-    if (n > 0 && (g.entry < 0 || g.entry >= n)) throw std::runtime_error("snapshot: EntryPointId out of range");
+    if (nactive > 0 && (g.entry < 0 || g.entry >= n)) throw std::runtime_error("snapshot: EntryPointId out of range");
     for (int v : g.adj0) if (v >= n) throw std::runtime_error("snapshot: edge to a node that does not exist");
     for (int v : g.adjU) if (v >= n) throw std::runtime_error("snapshot: edge to a node that does not exist");
 }

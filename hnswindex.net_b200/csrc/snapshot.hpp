@@ -48,6 +48,10 @@ struct HostGraph {
     std::vector<int> adj0;        // [length][stride0], -1 padded
     std::vector<int> upper_off;   // [length] first upper row of the node or -1
     std::vector<int> adjU;        // [rowsU][strideU], -1 padded
+    // removal state (all empty when nothing was ever removed)
+    std::vector<unsigned char> removed;  // [length] Node.IsRemoved
+    std::vector<int> active;             // ActiveSet.dense[..count] in its own order; empty = 0..length-1
+    std::vector<int> removed_stack;      // GraphData.RemovedIndexes, bottom first (back() is handed out next)
 };
 
 inline int stride_for(int max_edges) { return ((max_edges < 1 ? 1 : max_edges) + 3) & ~3; }

@@ -73,6 +73,7 @@ def _load():
         "hnsw_get_stats": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
         "hnsw_knn_query_layer": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
         "hnsw_multilayer_knn_query": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
+        "hnsw_ids": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
         "hnsw_top_layer": (ct.c_int, [ct.c_void_p]),
         "hnsw_entry_point": (ct.c_int, [ct.c_void_p]),
         "hnsw_get_info": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
@@ -292,6 +293,16 @@ class Index:
         if layers > 0 and n > 0:
             _check(lib.hnsw_multilayer_knn_query(self._h, _fp(q), n, self.dim, int(k), int(max_layer), int(min_layer), _ip(ids), _fp(dists)))
         return ids, dists
+
+    def ids(self) -> np.ndarray:
+        """Ids() (HNSWIndex.cs:242-245): active ids in the reference's ActiveSet order."""
+        if not self._h:
+            return np.zeros(0, dtype=np.int32)
+        n = lib.hnsw_ids(self._h, None, 0)
+        _check(n)
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        _check(lib.hnsw_ids(self._h, _ip(out), n))
+        return out[:n]
 
     def top_layer(self) -> int:
         return lib.hnsw_top_layer(self._h) if self._h else -1

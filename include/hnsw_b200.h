@@ -54,10 +54,14 @@ HNSW_API void hnsw_free(hnsw_handle handle);
  * -1 on error.  The dimension is fixed by the first call. */
 HNSW_API int hnsw_add(hnsw_handle handle, const float* vectors, int count, int dim, int* outIds);
 
-/* HNSWIndexExports.cs:102-117 -> HNSWIndex.Remove (HNSWIndex.cs:83-100).  Removal is outside the
- * accelerated path: returns 0 for NULL handle / NULL ids / count <= 0 like the
- * reference, otherwise -1 with an explanatory error. */
+/* HNSWIndexExports.cs:102-117 -> HNSWIndex.Remove(List<int>) (HNSWIndex.cs:83-100, GraphConnector.cs:53-167).
+ * Returns 0 (also for NULL handle / NULL ids / count <= 0, like the reference), -1 on error: AllowRemovals is
+ * false, an id is out of range, already removed or listed twice.  Removed slots are handed out again by later
+ * hnsw_add calls, most recently removed first (GraphData.cs:84-91). */
 HNSW_API int hnsw_remove(hnsw_handle handle, const int* ids, int count);
+/* HNSWIndex.Ids() (HNSWIndex.cs:242-245): the active ids in the reference's ActiveSet order.  Returns their number
+ * (= hnsw_count) and writes at most `capacity` of them. */
+HNSW_API int hnsw_ids(hnsw_handle handle, int* outIds, int capacity);
 
 /* HNSWIndexExports.cs:119-149 -> HNSWIndex.BatchKnnQuery (HNSWIndex.cs:129-137).  outIds/outDists:
  * caller-owned row-major [count][k]; each row ascending by distance, padded with id -1 / NaN when

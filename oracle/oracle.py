@@ -59,6 +59,9 @@ def lib():
     L.orc_add_frozen_batches.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, i32p, ct.c_int, ct.c_int]
     L.orc_knn_query.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, ct.c_int, u64p]
     L.orc_knn_query_counters.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, u64p]
+    L.orc_remove.argtypes = [ct.c_void_p, i32p, ct.c_int]
+    L.orc_active_ids.argtypes = [ct.c_void_p, i32p, ct.c_int]
+    L.orc_is_removed.argtypes = [ct.c_void_p, ct.c_int]
     L.orc_knn_query_layer.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, ct.c_int]
     L.orc_multilayer_knn_query.argtypes = [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, i32p, f32p]
     L.orc_range_query.restype = ct.c_longlong
@@ -226,6 +229,21 @@ class OracleIndex:
         if rc < 0:
             raise RuntimeError(lib().orc_last_error().decode())
         return (ids, dists, c) if counters else (ids, dists)
+
+    def remove(self, ids):
+        """HNSWIndex.Remove for each id in order (HNSWIndex.cs:83-100), single-threaded."""
+        a = np.ascontiguousarray(np.asarray(ids, dtype=np.int32).reshape(-1))
+        if lib().orc_remove(self._h, _ip(a), a.shape[0]) < 0:
+            raise RuntimeError(lib().orc_last_error().decode())
+
+    def active_ids(self):
+        n = lib().orc_active_ids(self._h, None, 0)
+        out = np.empty(max(n, 1), dtype=np.int32)
+        lib().orc_active_ids(self._h, _ip(out), n)
+        return out[:n]
+
+    def is_removed(self, i):
+        return bool(lib().orc_is_removed(self._h, int(i)))
 
     def knn_query_layer(self, queries, k, layer, threads=1):
         """BatchKnnQuery(..., layer) -- HNSWIndex.cs:107-137."""

@@ -95,6 +95,21 @@ int orc_add_frozen_batches(void* h, const float* v, int count, int dim, int* out
     try { ((Index*)h)->AddBatchFrozen(v, count, dim, outIds, ratio, bmax); return count; }
     catch (std::exception& e) { g_err = e.what(); return -1; }
 }
+// HNSWIndex.Remove(int) applied to ids in order (HNSWIndex.cs:83-100, single-threaded)
+int orc_remove(void* h, const int* ids, int count) {
+    try {
+        Index* ix = (Index*)h;
+        for (int i = 0; i < count; i++) ix->Remove(ids[i]);
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+int orc_active_ids(void* h, int* out, int cap) {
+    Index* ix = (Index*)h;
+    int n = (int)ix->ActiveIds.size();
+    for (int i = 0; i < n && i < cap; i++) out[i] = ix->ActiveIds[i];
+    return n;
+}
+int orc_is_removed(void* h, int id) { return ((Index*)h)->Nodes[id]->IsRemoved ? 1 : 0; }
 int orc_knn_query(void* h, const float* q, int count, int dim, int k, int* outIds, float* outDists, int threads, uint64_t* counters /*3 or null*/) {
     try {
         Index* ix = (Index*)h;

@@ -146,7 +146,14 @@ inline void serialize(const Index& ix, const std::string& path, bool packed = fa
         }
         data.bytes_field(3, it.buf);
     }
-    // 4: RemovedIndexes -- empty
+    // 4: RemovedIndexes -- ConcurrentStack<int> enumerates from the top of the stack down [inferred: protobuf-net
+    // writes a collection in enumeration order]
+    if (packed) {
+        pb::Writer a; for (auto it = ix.RemovedIndexes.rbegin(); it != ix.RemovedIndexes.rend(); ++it) a.varint((uint64_t)(int64_t)*it);
+        if (!ix.RemovedIndexes.empty()) data.bytes_field(4, a.buf);
+    } else {
+        for (auto it = ix.RemovedIndexes.rbegin(); it != ix.RemovedIndexes.rend(); ++it) data.int32_field(4, *it);
+    }
     data.int32_field_nz(5, ix.EntryPointId);
     data.int32_field_nz(6, ix.Capacity);
     data.int32_field_nz(7, ix.Length);
@@ -194,7 +201,7 @@ inline std::unique_ptr<Index> deserialize(Metric metric, const std::string& path
     bool haveParams = false, haveData = false, anyInEdges = false, haveAllow = false, haveEp = false;
     int ep = -1, capacity = 0, length = 0, count = 0;
     std::vector<std::unique_ptr<Node>> nodes;
-    std::vector<int> active;
+    std::vector<int> active, removedTopFirst;
     std::vector<std::vector<float>> items;
 
     pb::Reader root(bytes.data(), bytes.data() + bytes.size());
@@ -241,7 +248,8 @@ inline std::unique_ptr<Index> deserialize(Metric metric, const std::string& path
                         if (f3 == 1) pb::read_floats(ir, w3, v); else ir.skip(w3);
                     }
                     items.push_back(std::move(v));
-                } else if (f2 == 5 && w2 == 0) { ep = (int32_t)r.varint(); haveEp = true; }
+                } else if (f2 == 4) pb::read_int32s(r, w2, removedTopFirst);
+                else if (f2 == 5 && w2 == 0) { ep = (int32_t)r.varint(); haveEp = true; }
                 else if (f2 == 6 && w2 == 0) capacity = (int32_t)r.varint();
                 else if (f2 == 7 && w2 == 0) length = (int32_t)r.varint();
                 else if (f2 == 8 && w2 == 0) count = (int32_t)r.varint();
@@ -261,12 +269,13 @@ inline std::unique_ptr<Index> deserialize(Metric metric, const std::string& path
     auto ix = std::make_unique<Index>(metric, p);
     ix->dim = items.empty() ? -1 : (int)items[0].size();
     for (size_t i = 0; i < nodes.size(); i++) {
-        if (nodes[i]->Id != (int)i) throw std::runtime_error("snapshot: removed slots are not supported");
+        if (nodes[i]->Id != (int)i) throw std::runtime_error("snapshot: node ids must equal their slot");
         if ((int)items[i].size() != ix->dim) throw std::runtime_error("snapshot: ragged items");
         ix->Items.insert(ix->Items.end(), items[i].begin(), items[i].end());
     }
     ix->Nodes = std::move(nodes);
     ix->ActiveIds = std::move(active);
+    ix->RemovedIndexes.assign(removedTopFirst.rbegin(), removedTopFirst.rend());
     ix->EntryPointId = ep;
     ix->Capacity = capacity > 0 ? capacity : std::max<int>(p.CollectionSize, (int)ix->Nodes.size());
     ix->Length = length > 0 ? length : (int)ix->Nodes.size();

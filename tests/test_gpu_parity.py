@@ -461,3 +461,126 @@ def test_get_info_and_connected_components(hnswindex, oracle):
         ncomp, lab = connected_components(g, directed=True, connection="weak")
         assert comps[layer] == len(np.unique(lab[on]))
     assert comps[0] >= 1
+
+
+# ------------------------------------------------------------------------------------------ Remove
+def _rows_as_sets(ix_rows):
+    return [frozenset(int(x) for x in r if x >= 0) for r in ix_rows]
+
+
+def _gpu_layer_sets(gpu, layer):
+    rows = gpu.export_layer0()[1] if layer == 0 else gpu.export_layer(layer)
+    return _rows_as_sets(rows)
+
+
+@pytest.mark.parametrize("metric", ["sq_euclid", "ucosine"])
+def test_remove_one_by_one_matches_oracle(hnswindex, oracle, tmp_path, metric):
+    # one id per call = the reference's sequential Remove (GraphConnector.cs:53-167): same link SETS in every row,
+    # same entry point, same query answers
+    rng = np.random.default_rng(11)
+    data = rng.random((1500, 32), dtype=np.float32)
+    if metric == "ucosine":
+        data /= np.linalg.norm(data, axis=1, keepdims=True)
+    ref, path = _oracle_graph(oracle, tmp_path, metric, data, f"rm_{metric}", max_edges=8)
+    gpu = hnswindex.Index.deserialize(metric, path)
+    victims = [int(v) for v in rng.permutation(1500)[:120] if int(v) != ref.entry_point]
+    levels = gpu.export_layer0()[0]
+    for step, v in enumerate(victims):
+        ref.remove([v])
+        gpu.remove([v])
+        if step % 20 == 19 or step == len(victims) - 1:
+            assert gpu.count == ref.count and gpu.entry_point() == ref.entry_point
+            for layer in range(gpu.top_layer() + 1):
+                g_sets = _gpu_layer_sets(gpu, layer)
+                diff = 0
+                for i in range(1500):
+                    if levels[i] < layer or ref.is_removed(i):
+                        continue
+                    o = frozenset(int(x) for x in ref.row(i, layer, 0))
+                    diff += o != g_sets[i]
+                assert diff == 0, (step, layer, diff)
+    live = np.array([i for i in range(1500) if not ref.is_removed(i)])
+    assert sorted(gpu.ids().tolist()) == live.tolist() and np.array_equal(gpu.ids(), ref.active_ids())
+    o_ids, o_d = ref.knn_query(data[:300], 5)
+    g_ids, g_d = gpu.knn_query(data[:300], 5)
+    _assert_identical(g_ids, g_d, o_ids, o_d, min_same=0.98)
+    assert not (set(g_ids.ravel().tolist()) & set(victims))
+    # removed slots are handed out again most-recent-first by both (GraphData.cs:84-91)
+    fresh = rng.random((10, 32), dtype=np.float32)
+    if metric == "ucosine":
+        fresh /= np.linalg.norm(fresh, axis=1, keepdims=True)
+    a = np.concatenate([ref.add(fresh[i:i + 1]) for i in range(10)])
+    b = np.concatenate([gpu.add(fresh[i:i + 1]) for i in range(10)])
+    assert a.tolist() == b.tolist() == victims[::-1][:10]
+    g_ids, _ = gpu.knn_query(fresh, 1)
+    assert (g_ids[:, 0] == b).all()
+
+
+def test_remove_half_in_one_call_like_reference_tests(hnswindex, oracle):
+    # GraphTests.cs:194-225 RemoveNodesBatchTest (+ bindings recall_test.py:18-34): unit-cosine, 2000 normalised vectors,
+    # Remove(odd ids) in one call: recall of the rest > 0.98 x the insert recall, in/out edges balanced
+    v = oracle.normalize_rows_like_reference(oracle.random_vectors(128, 2000))
+    ix = hnswindex.Index(128, "ucosine")
+    ids = ix.add(v)
+    assert ids.tolist() == list(range(2000))
+    insert_recall = float((ix.knn_query(v, 1)[0][:, 0] == ids).mean())
+    assert insert_recall > 0.85
+    ix.remove(ids[1::2])
+    assert ix.count == 1000 and sorted(ix.ids().tolist()) == ids[0::2].tolist()
+    res = ix.knn_query(v[0::2], 1)[0][:, 0]
+    removal_recall = float((res == ids[0::2]).mean())
+    assert insert_recall * 0.98 < removal_recall, (insert_recall, removal_recall)
+    assert (res % 2 == 0).all()
+    for li in ix.get_info():
+        assert li["avgOutEdges"] == li["avgInEdges"]
+    et, _ = ix.exact_knn(v[:50], 3)
+    assert (et % 2 == 0).all()
+    # python binding test of the reference: |remove_recall - add_recall| < 0.02
+    assert abs(removal_recall - insert_recall) < 0.02 or removal_recall > insert_recall
+
+
+def test_remove_entry_point_everything_and_errors(hnswindex, oracle, tmp_path):
+    rng = np.random.default_rng(3)
+    v = rng.random((400, 16), dtype=np.float32)
+    ix = hnswindex.Index(16, "sq_euclid")
+    ix.set_max_edges(4)
+    ids = ix.add(v)
+    ep = ix.entry_point()
+    ix.remove([ep])
+    assert ix.entry_point() not in (ep, -1) and ix.count == 399
+    res = ix.knn_query(v, 1)[0][:, 0]
+    assert (res != ep).all() and (res == ids)[ids != ep].mean() > 0.85
+    with pytest.raises(RuntimeError):
+        ix.remove([ep])            # already removed
+    with pytest.raises(RuntimeError):
+        ix.remove([5, 5])          # listed twice
+    with pytest.raises(RuntimeError):
+        ix.remove([100000])        # out of range
+    # snapshot with removal state: GPU -> file -> oracle and back
+    path = tmp_path / "rm_state.hnsw"
+    ix.serialize(path)
+    ref = oracle.OracleIndex.deserialize("sq_euclid", path)
+    assert ref.count == 399 and ref.is_removed(ep) and np.array_equal(ref.active_ids(), ix.ids())
+    o_ids, o_d = ref.knn_query(v[:100], 3)
+    g_ids, g_d = ix.knn_query(v[:100], 3)
+    _assert_identical(g_ids, g_d, o_ids, o_d)
+    ref.remove([7, 9])
+    path2 = tmp_path / "rm_state2.hnsw"
+    ref.serialize(path2)
+    back = hnswindex.Index.deserialize("sq_euclid", path2)
+    assert back.count == 397 and np.array_equal(back.ids(), ref.active_ids())
+    assert back.add(v[:3]).tolist() == ref.add(v[:3]).tolist() == [9, 7, ep]
+    # remove everything
+    rest = [i for i in ids.tolist() if i != ep]
+    ix.remove(rest)
+    assert ix.count == 0 and ix.entry_point() == -1
+    r, d = ix.knn_query(v[:3], 2)
+    assert (r == -1).all() and np.isnan(d).all()
+    again = ix.add(v[:5])
+    assert ix.count == 5 and set(again.tolist()) <= set(ids.tolist())
+    assert (ix.knn_query(v[:5], 1)[0][:, 0] == again).all()
+    noremove = hnswindex.Index(16, "sq_euclid")
+    noremove.set_allow_removals(False)
+    noremove.add(v[:10])
+    with pytest.raises(RuntimeError):
+        noremove.remove([1])

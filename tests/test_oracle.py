@@ -216,3 +216,64 @@ def test_layer_queries_of_the_oracle(oracle):
         assert (levels[v[v >= 0]] >= layer).all()
     # layer 0 of the multi-layer query is a width-k search entered from layer 1's best: ascending distances
     assert (np.diff(md[:, 0, :3], axis=1) >= 0).all()
+
+
+# ---------------------------------------------------------------- removal
+def test_remove_nodes_like_reference_test(oracle, tmp_path):
+    # GraphTests.cs:122-156 RemoveNodesTest: unit-cosine, 2000 normalised vectors, remove the odd-indexed ones one by one;
+    # recall on the remaining ones stays above 0.98 x the insert recall and in/out edges stay balanced
+    v = _fixture(oracle, "v2000")
+    ix = oracle.OracleIndex("ucosine")
+    ids = ix.add(v)
+    insert_recall = oracle.self_recall(ix, v, ids)
+    odd = ids[1::2]
+    even = ids[0::2]
+    ix.remove(odd)
+    assert ix.count == 1000
+    assert sorted(ix.active_ids().tolist()) == sorted(even.tolist())
+    res, _ = ix.knn_query(v[0::2], 1)
+    removal_recall = float((res[:, 0] == even).mean())
+    assert insert_recall * 0.98 < removal_recall, (insert_recall, removal_recall)
+    # no live row points at a removed node; in == out over the live nodes
+    removed = set(odd.tolist())
+    tot_out = tot_in = 0
+    for i in even.tolist():
+        for layer in range(ix.node_level(i) + 1):
+            out = ix.row(i, layer, 0)
+            assert not (set(out.tolist()) & removed)
+            tot_out += len(out)
+            tot_in += len(ix.row(i, layer, 1))
+    assert tot_out == tot_in
+    assert not ix.is_removed(int(even[0])) and ix.is_removed(int(odd[0]))
+    # removed slots are handed out again, most recently removed first (GraphData.cs:84-91)
+    new_ids = ix.add(v[1:7:2])
+    assert new_ids.tolist() == odd[::-1][:3].tolist()
+    assert ix.count == 1003
+    # snapshot round trip keeps the removal state
+    path = tmp_path / "removed.hnsw"
+    ix.serialize(path)
+    ix2 = oracle.OracleIndex.deserialize("ucosine", path)
+    assert ix2.count == ix.count and np.array_equal(ix2.active_ids(), ix.active_ids())
+    a, _ = ix.knn_query(v[:200], 5)
+    b, _ = ix2.knn_query(v[:200], 5)
+    assert np.array_equal(a, b)
+    assert ix2.add(v[7:9:2]).tolist() == ix.add(v[7:9:2]).tolist()
+
+
+def test_remove_entry_point_and_everything(oracle):
+    rng = np.random.default_rng(3)
+    v = rng.random((300, 16), dtype=np.float32)
+    ix = oracle.OracleIndex("sq_euclid", max_edges=4)
+    ids = ix.add(v)
+    ep = ix.entry_point
+    ix.remove([ep])
+    assert ix.entry_point != ep and ix.count == 299
+    res, _ = ix.knn_query(v, 1)
+    assert (res[:, 0] != ep).all()
+    rest = [i for i in ids.tolist() if i != ep]
+    ix.remove(rest)
+    assert ix.count == 0 and ix.entry_point == -1
+    res, d = ix.knn_query(v[:3], 2)
+    assert (res == -1).all() and np.isnan(d).all()
+    with pytest.raises(RuntimeError):
+        oracle.OracleIndex("sq_euclid", allow_removals=False).remove([0])
