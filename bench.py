@@ -37,23 +37,37 @@ sys.path.insert(0, str(ROOT / "hnswindex.net_b200"))
 EF_GRID = [10, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096]
 DIM, RANK, K = 128, 16, 10
 M, EFC = 16, 200
+# the BASELINE configs that fit one GPU.  c2 is the one the metric is quoted on (the default).
+WORKLOADS = {
+    "c2": dict(tag="C2", dim=128, rank=16, metric="sq_euclid", M=16, efc=200, k=10, dist_rate=None,
+               metric_name="QPS at recall@10>=0.95, 1M x 128 sq_euclid", shape="SIFT-shaped (rank-16 + 0.25 noise)"),
+    "c2u": dict(tag="C2-uniform", dim=128, rank=0, metric="sq_euclid", M=16, efc=200, k=10, dist_rate=None,
+                metric_name="QPS at recall@10>=0.95, 1M x 128 sq_euclid, U[0,1) data (hard case of SURVEY 8d)",
+                shape="uniform U[0,1)^128 (the reference tests' distribution; intrinsic dimension 128)"),
+    "c3": dict(tag="C3", dim=960, rank=32, metric="cosine", M=32, efc=200, k=100, dist_rate=1.0 / math.log(32.0),
+               metric_name="QPS at recall@100>=0.95, 1M x 960 cosine (C3, GIST-shaped)", shape="GIST-shaped (rank-32 + 0.25 noise, not normalised)"),
+}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_data(n, nq_total, seed_data=1234, seed_q=4321):
-    """SIFT-shaped x = zA + 0.25 eps, z~N(0,I16); queries from the same distribution, held out."""
+def make_data(n, nq_total, seed_data=1234, seed_q=4321, dim=DIM, rank=RANK):
+    """x = zA + 0.25 eps, z~N(0,I_rank) (low intrinsic dimension); queries from the same
+    distribution, held out."""
     rng = np.random.default_rng(seed_data)
-    A = rng.standard_normal((RANK, DIM)).astype(np.float32)
-    data = np.empty((n, DIM), dtype=np.float32)
+    if rank <= 0:  # uniform hard case
+        data = rng.random((n, dim), dtype=np.float32)
+        return data, np.random.default_rng(seed_q).random((nq_total, dim), dtype=np.float32)
+    A = rng.standard_normal((rank, dim)).astype(np.float32)
+    data = np.empty((n, dim), dtype=np.float32)
     for s in range(0, n, 131072):
         e = min(n, s + 131072)
-        z = rng.standard_normal((e - s, RANK)).astype(np.float32)
-        data[s:e] = z @ A + 0.25 * rng.standard_normal((e - s, DIM)).astype(np.float32)
+        z = rng.standard_normal((e - s, rank)).astype(np.float32)
+        data[s:e] = z @ A + 0.25 * rng.standard_normal((e - s, dim)).astype(np.float32)
     rq = np.random.default_rng(seed_q)
-    q = (rq.standard_normal((nq_total, RANK)).astype(np.float32) @ A + 0.25 * rq.standard_normal((nq_total, DIM)).astype(np.float32))
+    q = (rq.standard_normal((nq_total, rank)).astype(np.float32) @ A + 0.25 * rq.standard_normal((nq_total, dim)).astype(np.float32))
     return data, np.ascontiguousarray(q.astype(np.float32))
 
 
@@ -111,10 +125,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def pick_ef(search, truth, grid=EF_GRID, target=0.95):
+def pick_ef(search, truth, grid=EF_GRID, target=0.95, k=K):
+    grid = [k] * (k not in grid) + [e for e in grid if e >= k]  # ef = max(MinNN, k): values below k are all k
+    grid.sort()
     for ef in grid:
         r = recall_at_k(search(ef), truth)
-        log(f"  ef={ef}: recall@10={r:.4f}")
+        log(f"  ef={ef}: recall@{k}={r:.4f}")
         if r >= target:
             return ef, r
     return grid[-1], r
@@ -140,27 +156,41 @@ def run_b200(args):
     from hnswindex import bindings as hb
     hb.set_device(local)
 
+    W = WORKLOADS[args.workload]
+    DIM, RANK, K, M, EFC, METRIC = W["dim"], W["rank"], W["k"], W["M"], W["efc"], W["metric"]
     n, nq, nb = args.n, args.nq, args.query_batches
-    data, queries = make_data(n, nq * nb, seed_q=4321 + 1000 * rank)
-    snap = Path(args.snapshot_dir) / f"bench_c2_{n}.hnsw"
+    data, queries = make_data(n, nq * nb, seed_q=4321 + 1000 * rank, dim=DIM, rank=RANK)
+    snap = Path(args.snapshot_dir) / f"bench_{args.workload}_{n}.hnsw"
+
+    def new_index():
+        ix = hnswindex.Index(DIM, METRIC)
+        ix.set_collection_size(n); ix.set_max_edges(M); ix.set_max_candidates(EFC); ix.set_allow_removals(False)
+        if W["dist_rate"]:
+            ix.set_distribution_rate(W["dist_rate"])
+        return ix
 
     # ---- setup (untimed): build once on rank 0, replicate through the serialized snapshot
     t0 = time.time()
     build_info = {}
     if rank == 0:
-        ix = hnswindex.Index(DIM, "sq_euclid")
-        ix.set_collection_size(n); ix.set_max_edges(M); ix.set_max_candidates(EFC); ix.set_allow_removals(False)
+        ix = new_index()
         tb = time.time()
         ix.add(data)
         build_s = time.time() - tb
-        build_info = {"inserts_per_s": round(n / build_s), "build_s": round(build_s, 3), "build_kernel_ms": round(ix.stats()["last_build_ms"], 1)}
-        log(f"[bench] GPU build: {n} inserts in {build_s:.2f}s ({n / build_s:.0f}/s)")
+        bp = ix.build_profile()
+        kms_build = ix.stats()["last_build_ms"]
+        nd = bp["ndist_search"] + bp["ndist_select"] + bp["ndist_prune"]
+        build_info = {"inserts_per_s": round(n / build_s), "build_s": round(build_s, 3), "build_kernel_ms": round(kms_build, 1),
+                      "build_kernel_inserts_per_s": round(n / (kms_build / 1e3)),
+                      "build_ndist_per_insert": round(nd / max(1, bp["inserts"]), 1),
+                      "build_gathered_GBps": round(nd * DIM * 4 / (kms_build / 1e3) / 1e9, 1)}
+        log(f"[bench] GPU build: {n} inserts in {build_s:.2f}s ({n / build_s:.0f}/s), kernels {kms_build:.0f} ms")
         if world > 1 or not args.no_cpu_baseline:
             ts = time.time(); ix.serialize(snap, packed=True); log(f"[bench] serialize {time.time() - ts:.1f}s")
     if world > 1:
         dist.barrier()
         if rank != 0:
-            ix = hnswindex.Index.deserialize("sq_euclid", snap)
+            ix = hnswindex.Index.deserialize(METRIC, snap)
     del data
 
     # ---- ef = smallest grid value with recall@10 >= 0.95 (GPU search == oracle search on the same graph: tests/)
@@ -171,7 +201,7 @@ def run_b200(args):
         ix.set_min_nn(ef)
         return ix.knn_query(queries[:ns], K)[0]
     if rank == 0:
-        ef, rec = pick_ef(search_ef, truth)
+        ef, rec = pick_ef(search_ef, truth, k=K)
         sel = torch.tensor([ef], dtype=torch.int32, device="cuda")
     else:
         sel = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -180,7 +210,7 @@ def run_b200(args):
     ef = int(sel.item())
     ix.set_min_nn(ef)
     recall = recall_at_k(ix.knn_query(queries[:ns], K)[0], truth)
-    log(f"[bench] rank {rank}: ef={ef} recall@10={recall:.4f} setup {time.time() - t0:.1f}s")
+    log(f"[bench] rank {rank}: ef={ef} recall@{K}={recall:.4f} setup {time.time() - t0:.1f}s")
 
     # ---- device-resident buffers, engine runs on torch's current stream so torch events bracket it
     stream = torch.cuda.Stream()
@@ -256,31 +286,33 @@ def run_b200(args):
     if not args.no_cpu_baseline:
         from oracle import oracle as O
         ts = time.time()
-        ref = O.OracleIndex.deserialize("sq_euclid", snap)
+        ref = O.OracleIndex.deserialize(METRIC, snap)
         ref.set_min_nn(ef)
         log(f"[bench] oracle loaded the GPU-built snapshot in {time.time() - ts:.1f}s")
         cores = os.cpu_count() or 1
-        o_ids, o_d, cnt = ref.knn_query(queries[:nq], K, threads=cores, counters=True)
+        ncheck = nq if args.workload == "c2" else min(nq, 2000)   # wide rows: count the work on a sample, scale to the batch
+        o_ids, o_d, cnt = ref.knn_query(queries[:ncheck], K, threads=cores, counters=True)
         ix.set_stream(0)
-        g_ids, g_d = ix.knn_query(queries[:nq], K)
+        g_ids, g_d = ix.knn_query(queries[:ncheck], K)
         same = float((g_ids == o_ids).all(axis=1).mean())
+        cnt = [int(c) * nq // ncheck for c in cnt]
         bytes_vec = int(cnt[0]) * DIM * 4
         bytes_adj = int(cnt[2]) * 4
-        alg = bytes_vec + bytes_adj            # per launch (one 10k batch; batches are i.i.d.)
+        alg = bytes_vec + bytes_adj            # per launch (one batch; batches are i.i.d.)
         ach = alg / (kernel_ms / 1e3) / 1e9
         roof.update({"achieved": round(ach, 1), "peak": peak, "frac": round(ach / peak, 4), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "gathered_vector_GBps": round(bytes_vec / (kernel_ms / 1e3) / 1e9, 1),
                      "ndist_per_query": round(int(cnt[0]) / nq, 1), "nexp_per_query": round(int(cnt[1]) / nq, 1),
-                     "kernel": "knn_search_kernel<SQ_EUCLID>", "kernel_ms_avg": round(kernel_ms, 4)})
+                     "kernel": f"knn_search_kernel<{METRIC}>", "kernel_ms_avg": round(kernel_ms, 4)})
         prof = ROOT / "profiles" / "search_kernel_traffic.json"
-        if prof.exists():
+        if prof.exists() and args.workload == "c2":
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
         # CPU baseline (N=1 only): repeat the 10k batch until ~10 s of work (max 5 passes)
         t_cpu, passes = 0.0, 0
         while world == 1 and t_cpu < 10.0 and passes < 5:
-            tc = time.perf_counter(); ref.knn_query(queries[:nq], K, threads=cores); t_cpu += time.perf_counter() - tc; passes += 1
-        cpu = None if world > 1 else {"value": round(nq * passes / t_cpu, 1), "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": f"{passes} x {nq} queries of batch 0 on the same GPU-built 1M graph, ef={ef}, all host threads "
+            tc = time.perf_counter(); ref.knn_query(queries[:ncheck], K, threads=cores); t_cpu += time.perf_counter() - tc; passes += 1
+        cpu = None if world > 1 else {"value": round(ncheck * passes / t_cpu, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{passes} x {ncheck} queries of batch 0 on the same GPU-built {n}-node graph, ef={ef}, all host threads "
                          f"(C++ restatement of the reference's Parallel.For BatchKnnQuery, not the .NET runtime)",
                "id_lists_identical_to_gpu": round(same, 5)}
         del ref
@@ -290,12 +322,12 @@ def run_b200(args):
         pass
 
     line = {
-        "metric": "QPS at recall@10>=0.95, 1M x 128 sq_euclid", "value": round(value, 1), "unit": "queries/s",
+        "metric": W["metric_name"], "value": round(value, 1), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2: {n} x {DIM} fp32 sq_euclid SIFT-shaped (rank-16 + 0.25 noise), M={M}, efConstruction={EFC}, "
-                               f"{nq}-query batch per GPU per step, k={K}, MinNN(ef)={ef} = smallest grid value with recall@10>=0.95",
-                   "recall_at_10": round(recall, 4), "ef": ef, "index_nodes": n, "queries_per_step_per_gpu": nq,
+        "config": {"workload": f"{W['tag']}: {n} x {DIM} fp32 {METRIC} {W['shape']}, M={M}, efConstruction={EFC}, "
+                               f"{nq}-query batch per GPU per step, k={K}, MinNN(ef)={ef} = smallest grid value with recall@{K}>=0.95",
+                   f"recall_at_{K}": round(recall, 4), "ef": ef, "index_nodes": n, "queries_per_step_per_gpu": nq,
                    "parallelism": f"graph replicated x{world}, query batches sharded, no collective",
                    "l2_policy": f"inputs larger than L2: {n * (DIM * 4 + 2 * M * 4) / 1e6:.0f} MB graph vs 126 MB L2, "
                                 f"{nb} distinct query batches rotated", "graph_built_by": "GPU engine (hnsw_add)", **build_info},
@@ -322,10 +354,13 @@ def run_reference(args):
     from oracle import oracle as O
     O.build()
     cores = os.cpu_count() or 1
+    W = WORKLOADS[args.workload]
+    DIM, RANK, K, M, EFC, METRIC = W["dim"], W["rank"], W["k"], W["M"], W["efc"], W["metric"]
     n, nq = args.n, args.nq
-    data, queries = make_data(n, nq)
+    data, queries = make_data(n, nq, dim=DIM, rank=RANK)
     t0 = time.time()
-    ref = O.OracleIndex("sq_euclid", max_edges=M, max_candidates=EFC, collection_size=n, allow_removals=False)
+    okw = {"distribution_rate": W["dist_rate"]} if W["dist_rate"] else {}
+    ref = O.OracleIndex(METRIC, max_edges=M, max_candidates=EFC, collection_size=n, allow_removals=False, **okw)
     # probe the insert rate, then decide who builds the (untimed) graph
     probe = min(n, 20000)
     ref.add(data[:probe], threads=cores)
@@ -338,13 +373,15 @@ def run_reference(args):
         import __graft_entry__ as ge
         ge.build()
         import hnswindex
-        ix = hnswindex.Index(DIM, "sq_euclid")
+        ix = hnswindex.Index(DIM, METRIC)
         ix.set_collection_size(n); ix.set_max_edges(M); ix.set_max_candidates(EFC); ix.set_allow_removals(False)
+        if W["dist_rate"]:
+            ix.set_distribution_rate(W["dist_rate"])
         ix.add(data)
         snap = Path(args.snapshot_dir) / f"bench_ref_{n}.hnsw"
         ix.serialize(snap, packed=True)
         del ix
-        ref = O.OracleIndex.deserialize("sq_euclid", snap)
+        ref = O.OracleIndex.deserialize(METRIC, snap)
         snap.unlink()
         built_by = "GPU engine snapshot (setup only; timed path is the oracle)"
     elif n > probe:
@@ -357,7 +394,7 @@ def run_reference(args):
     def search_ef(ef):
         ref.set_min_nn(ef)
         return ref.knn_query(queries[:ns], K, threads=cores)[0]
-    ef, rec = pick_ef(search_ef, truth)
+    ef, rec = pick_ef(search_ef, truth, k=K)
     ref.set_min_nn(ef)
     sample = min(nq, args.reference_sample)
     for _ in range(args.warmup):
@@ -369,12 +406,12 @@ def run_reference(args):
     value = sample * args.steps / el
     line = {
         "impl": "reference",
-        "metric": "QPS at recall@10>=0.95, 1M x 128 sq_euclid", "value": round(value, 1), "unit": "queries/s",
+        "metric": W["metric_name"], "value": round(value, 1), "unit": "queries/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2: {n} x {DIM} fp32 sq_euclid SIFT-shaped (rank-16 + 0.25 noise), M={M}, efConstruction={EFC}, "
-                               f"k={K}, MinNN(ef)={ef} = smallest grid value with recall@10>=0.95; each step = {sample} queries",
-                   "recall_at_10": round(rec, 4), "ef": ef, "index_nodes": n, "graph_built_by": built_by},
+        "config": {"workload": f"{W['tag']}: {n} x {DIM} fp32 {METRIC} {W['shape']}, M={M}, efConstruction={EFC}, "
+                               f"k={K}, MinNN(ef)={ef} = smallest grid value with recall@{K}>=0.95; each step = {sample} queries",
+                   f"recall_at_{K}": round(rec, 4), "ef": ef, "index_nodes": n, "graph_built_by": built_by},
         "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} queries per step on the {n}-node graph; C++ restatement of the reference "
                                    f"(the .NET runtime is not available), Parallel.For stand-in on all host threads"},
@@ -473,6 +510,99 @@ def run_partitioned(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- construction (C5)
+def run_build(args):
+    """BASELINE config C5: batched GPU construction (hnsw_add) of the C2 data set vs the reference's Parallel.For Add
+    (oracle port on all host threads, bounded sample), with a recall-parity check.  Secondary workload, own metric name.
+    A step = one complete build of the n-node index."""
+    import torch
+    import __graft_entry__ as ge
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    ge.build()
+    import hnswindex
+    W = WORKLOADS[args.workload]
+    DIM, RANK, K, M, EFC, METRIC = W["dim"], W["rank"], W["k"], W["M"], W["efc"], W["metric"]
+    n = args.n
+    data, queries = make_data(n, 2000, dim=DIM, rank=RANK)
+    pinned = torch.from_numpy(data).pin_memory()
+    f32p, i32p = ct.POINTER(ct.c_float), ct.POINTER(ct.c_int)
+    out_ids = np.empty(n, dtype=np.int32)
+
+    def new_index(size):
+        ix = hnswindex.Index(DIM, METRIC)
+        ix.set_collection_size(size); ix.set_max_edges(M); ix.set_max_candidates(EFC); ix.set_allow_removals(False)
+        if W["dist_rate"]:
+            ix.set_distribution_rate(W["dist_rate"])
+        ix._create()
+        return ix
+
+    steps = max(1, min(args.steps, 5))
+    walls, kms, prof = [], [], None
+    sampler = ClockSampler(0)
+    for i in range(1 + steps):           # first build = warm-up (context, allocator)
+        ix = new_index(n)
+        if i == 1:
+            sampler.start()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        rc = hnswindex.lib.hnsw_add(ix._h, ct.cast(pinned.data_ptr(), f32p), n, DIM, out_ids.ctypes.data_as(i32p))
+        el = time.perf_counter() - t
+        assert rc == n, hnswindex.last_error()
+        if i > 0:
+            walls.append(el); kms.append(ix.stats()["last_build_ms"])
+            prof = ix.build_profile()
+        if i < steps:
+            del ix
+    clocks = sampler.stop()
+    wall, kernel_ms = float(np.mean(walls)), float(np.mean(kms))
+    nd = prof["ndist_search"] + prof["ndist_select"] + prof["ndist_prune"]
+    peak, peak_src = measured_peak()
+    ach = nd * DIM * 4 / (kernel_ms / 1e3) / 1e9
+    truth, _ = ix.exact_knn(queries, K)
+    ef, rec = pick_ef(lambda e: (ix.set_min_nn(e), ix.knn_query(queries, K)[0])[1], truth, k=K)
+    # CPU baseline + recall parity on a bounded sample: both engines build the first `sample` vectors
+    cpu, parity = None, None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        cores = os.cpu_count() or 1
+        sample = min(n, args.build_sample)
+        okw = {"distribution_rate": W["dist_rate"]} if W["dist_rate"] else {}
+        ref = O.OracleIndex(METRIC, max_edges=M, max_candidates=EFC, collection_size=sample, allow_removals=False, **okw)
+        t = time.perf_counter(); oids = ref.add(data[:sample], threads=cores); t_cpu = time.perf_counter() - t
+        small = new_index(sample)
+        gids = small.add(data[:sample])
+        st, _ = small.exact_knn(queries, K)
+        small.set_min_nn(ef); ref.set_min_nn(ef)
+        r_gpu = recall_at_k(small.knn_query(queries, K)[0], st)
+        inv = np.empty(sample, dtype=np.int64); inv[oids] = np.arange(sample)   # threaded Add hands out ids in completion order
+        o_res = ref.knn_query(queries, K, threads=cores)[0]
+        r_cpu = recall_at_k(np.where(o_res >= 0, inv[np.maximum(o_res, 0)], -1), st)
+        cpu = {"value": round(sample / t_cpu, 1), "unit": "inserts/s", "cores": cores, "kind": "port",
+               "sample": f"the first {sample} vectors of the same data set built by the oracle's threaded Add (Parallel.For stand-in, "
+                         f"all host threads); insert cost grows ~log n, so the full-size CPU rate is lower still"}
+        parity = {"nodes": sample, "ef": ef, f"recall_at_{K}_gpu_built": round(r_gpu, 4), f"recall_at_{K}_oracle_built": round(r_cpu, 4)}
+    print(json.dumps({
+        "metric": f"build inserts/s, {n} x {DIM} {METRIC}, M={M}, efConstruction={EFC} (C5)", "value": round(n / (kernel_ms / 1e3), 1),
+        "unit": "inserts/s", "n_gpus": 1, "steps": steps, "warmup": 1, "ms_per_step": round(kernel_ms, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C5: batched GPU construction of {n} x {DIM} fp32 {METRIC} {W['shape']}, M={M}, efConstruction={EFC}; "
+                               f"value = device time of all insertion batches (vectors resident), e2e = hnsw_add from pinned host memory",
+                   f"recall_at_{K}": round(rec, 4), "ef": ef, "recall_parity": parity,
+                   "l2_policy": "every step builds a fresh index: 640 MB of vectors + adjacency vs 126 MB L2"},
+        "e2e": {"value": round(n / wall, 1), "unit": "inserts/s", "h2d_bytes_per_step": n * DIM * 4, "d2h_bytes_per_step": n * 4,
+                "ms_per_step": round(wall * 1e3, 1), "api": "hnsw_add (C ABI, pinned host buffer)"},
+        "gpu_launches": int(ix.stats()["build_launches"]), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                     "peak_source": peak_src, "kernel": "build_select_kernel + build_link_kernel (all batches)",
+                     "bytes_model": "GPU-counted distance evaluations (search + heuristic + overflow prune) x dim x 4",
+                     "ndist_per_insert": {"search": round(prof["ndist_search"] / n, 1), "heuristic": round(prof["ndist_select"] / n, 1),
+                                          "overflow_prune": round(prof["ndist_prune"] / n, 1)}},
+        "cpu_baseline": cpu}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -486,7 +616,10 @@ def main():
     ap.add_argument("--snapshot-dir", default="/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
     ap.add_argument("--reference-sample", type=int, default=10_000)
     ap.add_argument("--reference-build-budget-s", type=float, default=150.0)
-    ap.add_argument("--mode", default="replicated", choices=["replicated", "partitioned"], help="partitioned = BASELINE config C4 (secondary workload)")
+    ap.add_argument("--mode", default="replicated", choices=["replicated", "partitioned", "build"],
+                    help="partitioned = BASELINE config C4, build = C5 (secondary workloads, own metric names)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="replicated mode: c2 (the metric's config) or c3")
+    ap.add_argument("--build-sample", type=int, default=100_000, help="build mode: nodes the CPU oracle builds (bounded sample)")
     ap.add_argument("--n-per-rank", type=int, default=1_250_000)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -495,6 +628,8 @@ def main():
         run_reference(args)
     elif args.mode == "partitioned":
         run_partitioned(args)
+    elif args.mode == "build":
+        run_build(args)
     else:
         run_b200(args)
 

@@ -27,7 +27,7 @@ enum BuildProf : int {
     BP_CYC_LINK, BP_CYC_PRUNE, BP_PRUNES, BP_NDIST_PRUNE, BP_CYC_LOCK, BP_CYC_SELECT_KERNEL, BP_LINKS, BP_WORDS
 };
 
-template <int METRIC>
+template <int METRIC, int SPEC>
 __global__ void __launch_bounds__(kThreads, 4)
 build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int efc, int list_cap, int vis_size, int cand_cap,
                     int sel_cap, unsigned* work_counter, u64* prof, uint32_t* gvis, int gvis_slots) {
@@ -65,7 +65,7 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
         for (int layer = min(level, g.top_layer); layer >= 0; --layer) {
             BeamState st;
             t0 = clock64();
-            beam_search<METRIC>(g, s, qn, layer, cur, cur_d, efc, st, lane, wc);
+            beam_search<METRIC, SPEC>(g, s, qn, layer, cur, cur_d, efc, st, lane, wc);
             t1 = clock64();
             cyc_search += t1 - t0;
             const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
@@ -249,6 +249,10 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
     // small table: shared memory per warp decides the occupancy of this latency-bound kernel (see search_kernels.cu)
     int vis = t.vis_size_build > 0 ? std::max(64, pow2_ge(t.vis_size_build)) : std::min(2048, std::max(256, pow2_ge(2 * efc)));
     if (t.vis_size_build <= 0 && d_gvis != nullptr && t.vis_global_build > 0) vis = 256;  // first-level filter only
+    // 16-bit tags (beam.cuh vis16_test_and_set) hold two entries per word: half the words keep the same filter and let a
+    // fourth block fit on the SM
+    if (t.vis_size_build <= 0 && vis > 256 && (long long)g.count <= ((long long)(vis / 2) << 16)) vis /= 2;
+    const bool vis16 = (long long)g.count <= ((long long)vis << 16);
     const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap);   // per warp
     const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap);  // per warp
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, 2 * sizeof(unsigned), stream));
@@ -256,17 +260,24 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
 #define HNSW_LAUNCH_BUILD(M)                                                                                                    \
     {                                                                                                                           \
         int w1 = 0, w2 = 0;                                                                                                     \
-        const int g1 = persistent_grid(build_select_kernel<M>, smem_sel, t, count, w1);                                        \
-        const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                        \
-        build_select_kernel<M><<<g1, 32 * w1, smem_sel * w1, stream>>>(g, d_levels, d_new_ids, count, efc, list_cap_sel, vis,  \
-                                                                       cand_cap, sel_cap, d_work_counter, d_build_prof,        \
-                                                                       d_gvis, gslots);                                        \
+        if (vis16) {                                                                                                            \
+            const int g1 = persistent_grid(build_select_kernel<M, kSpecVis16>, smem_sel, t, count, w1);                        \
+            const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
+            build_select_kernel<M, kSpecVis16><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                        \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
+        } else {                                                                                                                \
+            const int g1 = persistent_grid(build_select_kernel<M, 0>, smem_sel, t, count, w1);                                 \
+            const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
+            build_select_kernel<M, 0><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                 \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
+        }                                                                                                                       \
         const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, count, w2);                                         \
         build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, stream>>>(g, d_levels, d_new_ids, count, list_cap_link, cand_cap,  \
                                                                       sel_cap, d_work_counter + 1, err, d_build_prof);         \
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_BUILD(SQ_EUCLID) break;
+        case EUCLID: HNSW_LAUNCH_BUILD(EUCLID) break;
         case COSINE: HNSW_LAUNCH_BUILD(COSINE) break;
         default: HNSW_LAUNCH_BUILD(UCOSINE) break;
     }

@@ -68,7 +68,7 @@ __device__ __forceinline__ int select_neighbors_long(const GraphView& g, BuildSc
 // distance between one staged row (this lane pair's) and a vector in shared memory; both lanes of the pair get it
 template <int METRIC>
 __device__ __forceinline__ float staged_row_dist(const GraphView& g, const float* row, const float* q, double an, double qn, bool active, int h) {
-    constexpr bool SQ = METRIC == SQ_EUCLID;
+    constexpr bool SQ = metric_is_sq(METRIC);
     const int nfull = g.dim >> 3, ntail = g.dim - (nfull << 3);
     PairAcc acc = {0.f, 0.f, 0.f, 0.f};
     if (active) pair_accumulate<SQ>(acc, row, q, nfull, h);

@@ -27,6 +27,7 @@ MetricKind parse_metric(const char* m) {
     if (s == "sq_euclid") return SQ_EUCLID;
     if (s == "cosine") return COSINE;
     if (s == "ucosine") return UCOSINE;
+    if (s == "euclid") return EUCLID;  // addition: EuclideanMetric.Compute of the C# library (the reference's native shim stops at three names)
     throw std::invalid_argument("Unsupported distance metric: " + s);  // HNSWIndexExports.cs:59
 }
 Index* get(hnsw_handle h) {

@@ -10,7 +10,10 @@ namespace hnsw {
 
 typedef unsigned long long u64;
 
-enum MetricKind : int { SQ_EUCLID = 0, COSINE = 1, UCOSINE = 2 };
+// EUCLID = sqrt of the squared Euclidean distance (EuclideanMetric.Compute, Metrics/EuclideanMetric.cs:103-109): same
+// accumulation as SQ_EUCLID, the root taken once per distance
+enum MetricKind : int { SQ_EUCLID = 0, COSINE = 1, UCOSINE = 2, EUCLID = 3 };
+__host__ __device__ constexpr bool metric_is_sq(int m) { return m == SQ_EUCLID || m == EUCLID; }
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kWarpsPerBlock = 4;     // independent warps (one query / one insert each)

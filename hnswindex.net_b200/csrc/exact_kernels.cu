@@ -64,7 +64,7 @@ exact_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
 #pragma unroll
                 for (int t = 0; t < TQ; ++t) {
                     const float4 b = reinterpret_cast<const float4*>(qs + (size_t)t * pitch4)[2 * c + h];
-                    if (METRIC == SQ_EUCLID) {
+                    if (metric_is_sq(METRIC)) {
                         float d;
                         d = __fsub_rn(a.x, b.x); acc[t][0] = __fmaf_rn(d, d, acc[t][0]);
                         d = __fsub_rn(a.y, b.y); acc[t][1] = __fmaf_rn(d, d, acc[t][1]);
@@ -88,16 +88,17 @@ exact_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
             const float s1 = __fadd_rn(acc[t][1], __shfl_xor_sync(FULL, acc[t][1], 1));
             const float s2 = __fadd_rn(acc[t][2], __shfl_xor_sync(FULL, acc[t][2], 1));
             const float s3 = __fadd_rn(acc[t][3], __shfl_xor_sync(FULL, acc[t][3], 1));
-            float r = METRIC == SQ_EUCLID ? __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)) : __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
+            float r = metric_is_sq(METRIC) ? __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)) : __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
             if (active) {
                 const float* qt = qs + (size_t)t * pitch4;
                 for (int i = nch << 3; i < g.dim; ++i) {
                     const float a = __ldg(vec + i), b = qt[i];
-                    if (METRIC == SQ_EUCLID) { const float d = __fsub_rn(a, b); r = __fadd_rn(r, __fmul_rn(d, d)); }
+                    if (metric_is_sq(METRIC)) { const float d = __fsub_rn(a, b); r = __fadd_rn(r, __fmul_rn(d, d)); }
                     else r = __fadd_rn(r, __fmul_rn(a, b));
                 }
                 if (METRIC == COSINE) r = cosine_finish(r, an, qn[t]);
                 else if (METRIC == UCOSINE) r = __fsub_rn(1.0f, r);
+                else if (METRIC == EUCLID) r = __fsqrt_rn(r);
             }
             // insert into this warp's list of query t
             BeamState st;
@@ -219,6 +220,7 @@ void launch_exact_knn(int metric, const GraphView& g, const float* d_queries, in
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_EXACT(SQ_EUCLID) break;
+        case EUCLID: HNSW_LAUNCH_EXACT(EUCLID) break;
         case COSINE: HNSW_LAUNCH_EXACT(COSINE) break;
         default: HNSW_LAUNCH_EXACT(UCOSINE) break;
     }

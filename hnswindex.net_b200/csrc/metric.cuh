@@ -118,6 +118,7 @@ __device__ __forceinline__ float cosine_finish(float dot, double sqrt_na, double
 template <int METRIC>
 __device__ __forceinline__ float metric_finish(float r, double sqrt_na, double sqrt_nb) {
     if (METRIC == SQ_EUCLID) return r;
+    if (METRIC == EUCLID) return __fsqrt_rn(r);  // (float)Math.Sqrt(x): the double root rounded to float is the correctly rounded float root
     if (METRIC == COSINE) return cosine_finish(r, sqrt_na, sqrt_nb);
     return __fsub_rn(1.0f, r);  // CosineMetric.cs:141
 }

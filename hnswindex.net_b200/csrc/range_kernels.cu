@@ -129,6 +129,7 @@ void launch_range_search(int metric, const GraphView& g, const float* d_queries,
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_RANGE(SQ_EUCLID) break;
+        case EUCLID: HNSW_LAUNCH_RANGE(EUCLID) break;
         case COSINE: HNSW_LAUNCH_RANGE(COSINE) break;
         default: HNSW_LAUNCH_RANGE(UCOSINE) break;
     }

@@ -223,6 +223,7 @@ void launch_remove_search(int metric, const GraphView& g, const int* d_item_node
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_RS(SQ_EUCLID) break;
+        case EUCLID: HNSW_LAUNCH_RS(EUCLID) break;
         case COSINE: HNSW_LAUNCH_RS(COSINE) break;
         default: HNSW_LAUNCH_RS(UCOSINE) break;
     }
@@ -259,6 +260,7 @@ void launch_relink(int metric, const GraphView& g, const int2* d_affected, int n
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_RL(SQ_EUCLID) break;
+        case EUCLID: HNSW_LAUNCH_RL(EUCLID) break;
         case COSINE: HNSW_LAUNCH_RL(COSINE) break;
         default: HNSW_LAUNCH_RL(UCOSINE) break;
     }

@@ -192,8 +192,8 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
 #define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
     {                                                                                                                           \
         int warps = 0;                                                                                                          \
-        if (layer == 0 && g.pitch <= kSegFloats && ef <= 64) {                                                                  \
-            constexpr int S = kSpecShortRows | kSpecSmallList;                                                                  \
+        if (layer == 0 && g.pitch <= kSegFloats && ef <= 64 && (long long)g.count <= ((long long)vis << 16)) {                  \
+            constexpr int S = kSpecShortRows | kSpecSmallList | kSpecVis16;                                                     \
             const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
                 g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
@@ -209,6 +209,7 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_SEARCH(SQ_EUCLID) break;
+        case EUCLID: HNSW_LAUNCH_SEARCH(EUCLID) break;
         case COSINE: HNSW_LAUNCH_SEARCH(COSINE) break;
         default: HNSW_LAUNCH_SEARCH(UCOSINE) break;
     }
@@ -232,6 +233,7 @@ void launch_multilayer_search(int metric, const GraphView& g, const float* d_que
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_ML(SQ_EUCLID) break;
+        case EUCLID: HNSW_LAUNCH_ML(EUCLID) break;
         case COSINE: HNSW_LAUNCH_ML(COSINE) break;
         default: HNSW_LAUNCH_ML(UCOSINE) break;
     }

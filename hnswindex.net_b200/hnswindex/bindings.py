@@ -21,7 +21,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-_METRICS = ("sq_euclid", "cosine", "ucosine")
+_METRICS = ("sq_euclid", "cosine", "ucosine", "euclid")  # "euclid" = EuclideanMetric.Compute (C# only in the reference)
 
 
 def _runtime_id() -> str:
@@ -143,7 +143,7 @@ def _check(status):
 class Index:
     """HNSW index over float32 vectors of one dimensionality, resident on one B200.
 
-    Parameters mirror the reference: ``Index(dim, metric="sq_euclid" | "cosine" | "ucosine")``.
+    Parameters mirror the reference: ``Index(dim, metric="sq_euclid" | "cosine" | "ucosine")`` (+ ``"euclid"``, the C# library's EuclideanMetric).
     The native index is created lazily by the first ``add`` (or by ``deserialize``); the
     ``set_*`` methods configure that creation and therefore must be called before it.
     """

@@ -111,7 +111,7 @@ struct DotNetRandom {
 // and AVX intrinsics (fast, used for the CPU baseline).  tests/ check that the
 // two agree bit for bit.  Build with -ffp-contract=off.
 // -----------------------------------------------------------------------------
-enum Metric { SQ_EUCLID = 0, COSINE = 1, UCOSINE = 2 };
+enum Metric { SQ_EUCLID = 0, COSINE = 1, UCOSINE = 2, EUCLID = 3 };
 
 inline float hsum_sq(const float* L) {
     // lower+upper (EuclideanMetric.cs:45-47), then two hadd (:48-49)
@@ -252,6 +252,7 @@ inline float ucosine_avx(const float* a, const float* b, int len) {
 inline float metric_scalar(Metric m, const float* a, const float* b, int len) {
     switch (m) {
         case SQ_EUCLID: return sq_euclid_scalar(a, b, len);
+        case EUCLID: return (float)std::sqrt((double)sq_euclid_scalar(a, b, len));  // EuclideanMetric.cs:103-109
         case COSINE: return cosine_scalar(a, b, len);
         default: return ucosine_scalar(a, b, len);
     }
@@ -260,6 +261,7 @@ inline float metric_fast(Metric m, const float* a, const float* b, int len) {
 #if ORACLE_HAVE_AVX
     switch (m) {
         case SQ_EUCLID: return sq_euclid_avx(a, b, len);
+        case EUCLID: return (float)std::sqrt((double)sq_euclid_avx(a, b, len));
         case COSINE: return cosine_avx(a, b, len);
         default: return ucosine_avx(a, b, len);
     }

@@ -20,6 +20,7 @@ static Metric parse_metric(const char* m) {
     if (s == "sq_euclid") return SQ_EUCLID;
     if (s == "cosine") return COSINE;
     if (s == "ucosine") return UCOSINE;
+    if (s == "euclid") return EUCLID;
     throw std::runtime_error("Unsupported distance metric: " + s);
 }
 

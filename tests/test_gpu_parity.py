@@ -66,6 +66,7 @@ def _assert_identical(g_ids, g_d, o_ids, o_d, min_same=0.995, explain=None):
     ("sq_euclid", 128, False), ("cosine", 128, False), ("ucosine", 128, True),
     ("sq_euclid", 127, False), ("cosine", 100, False), ("ucosine", 96, True), ("cosine", 960, False), ("sq_euclid", 20, False),
     ("sq_euclid", 3, False), ("cosine", 5, False), ("ucosine", 260, True),
+    ("euclid", 128, False), ("euclid", 37, False),   # EuclideanMetric.Compute = (float)Math.Sqrt(squared), EuclideanMetric.cs:103-109
 ])
 def test_knn_query_matches_oracle_on_same_graph(hnswindex, oracle, tmp_path, metric, dim, normalize):
     n = 3000 if dim < 900 else 1200
@@ -157,7 +158,7 @@ def test_results_do_not_depend_on_visited_table_size(hnswindex, oracle, tmp_path
 
 
 def test_exact_knn_matches_oracle(hnswindex, oracle, tmp_path):
-    for metric, dim in (("sq_euclid", 128), ("cosine", 100), ("ucosine", 96)):
+    for metric, dim in (("sq_euclid", 128), ("cosine", 100), ("ucosine", 96), ("euclid", 64)):
         rng = np.random.default_rng(5)
         data = rng.standard_normal((5000, dim)).astype(np.float32)
         q = rng.standard_normal((64, dim)).astype(np.float32)
@@ -197,7 +198,7 @@ def _rows_as_sets(rows):
     return [frozenset(int(x) for x in r if x >= 0) for r in rows]
 
 
-@pytest.mark.parametrize("metric", ["sq_euclid", "cosine"])
+@pytest.mark.parametrize("metric", ["sq_euclid", "cosine", "euclid"])
 def test_one_by_one_insertion_builds_the_oracle_graph(hnswindex, oracle, metric):
     # Adding items one call at a time is the reference's serial Add: the GPU must produce the same
     # levels, entry point and link sets (row order is free only where the reference's is: the

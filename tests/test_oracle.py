@@ -277,3 +277,16 @@ def test_remove_entry_point_and_everything(oracle):
     assert (res == -1).all() and np.isnan(d).all()
     with pytest.raises(RuntimeError):
         oracle.OracleIndex("sq_euclid", allow_removals=False).remove([0])
+
+
+def test_euclidean_metric_is_the_rounded_root_of_the_squared_one(oracle):
+    # EuclideanMetric.Compute = (float)Math.Sqrt(SquaredEuclideanMetric.Compute(a, b)), EuclideanMetric.cs:103-109
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((500, 77)).astype(np.float32)
+    b = rng.standard_normal((500, 77)).astype(np.float32)
+    sq = oracle.metric_many("sq_euclid", a, b)
+    eu = oracle.metric_many("euclid", a, b)
+    assert np.array_equal(eu, np.sqrt(sq.astype(np.float64)).astype(np.float32))
+    assert np.array_equal(eu, oracle.metric_many("euclid", a, b, impl=1))
+    ref = np.sqrt(((a.astype(np.float64) - b.astype(np.float64)) ** 2).sum(axis=1))
+    assert np.allclose(eu, ref, rtol=1e-5, atol=1e-5)   # bindings/__tests__/metric_test.py tolerance
