@@ -267,6 +267,65 @@ int hnsw_merge_topk_device(const int* dInIds, const float* dInDists, int parts, 
     return 0;
     HNSW_CATCH(-1)
 }
+// ---- partitioned index: CUDA IPC buffers + fused search/scatter (partition_kernels.cu)
+int hnsw_ipc_alloc(size_t bytes, void** devPtr, unsigned char* handle64) {
+    HNSW_TRY
+    if (!devPtr || !handle64 || bytes == 0) throw std::invalid_argument("null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    HNSW_CUDA_CHECK(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); HNSW_CUDA_CHECK(e); }
+    std::memcpy(handle64, &h, 64);
+    *devPtr = p;
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_ipc_open(const unsigned char* handle64, void** devPtr) {
+    HNSW_TRY
+    if (!devPtr || !handle64) throw std::invalid_argument("null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    HNSW_CUDA_CHECK(cudaIpcOpenMemHandle(devPtr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_ipc_close(void* devPtr) {
+    HNSW_TRY
+    if (devPtr) HNSW_CUDA_CHECK(cudaIpcCloseMemHandle(devPtr));
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_ipc_free(void* devPtr) {
+    HNSW_TRY
+    if (devPtr) HNSW_CUDA_CHECK(cudaFree(devPtr));
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_knn_query_scatter(hnsw_handle handle, const float* dQueries, int count, int dim, int k, const hnsw_scatter* sc) {
+    HNSW_TRY
+    if (!sc || !dQueries) throw std::invalid_argument("null argument");
+    if (sc->world < 1 || sc->world > HNSW_MAX_PEERS || sc->rank < 0 || sc->rank >= sc->world) throw std::invalid_argument("bad world / rank");
+    ScatterArgs a{};
+    a.world = sc->world; a.rank = sc->rank; a.id_offset = sc->idOffset; a.epoch = sc->epoch;
+    for (int p = 0; p < sc->world; ++p) {
+        if (!sc->ids[p] || !sc->dists[p] || !sc->flags[p]) throw std::invalid_argument("null peer pointer");
+        a.ids[p] = sc->ids[p]; a.dists[p] = sc->dists[p]; a.flags[p] = sc->flags[p];
+    }
+    get(handle)->knn_query_scatter(dQueries, count, dim, k, a);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_wait_and_merge_device(hnsw_handle handle, const unsigned* dFlags, int world, unsigned epoch, const int* dInIds, const float* dInDists,
+                               int count, int k, int* dOutIds, float* dOutDists) {
+    HNSW_TRY
+    if (world < 1 || k < 1) throw std::invalid_argument("world and k must be positive");
+    get(handle)->wait_and_merge(dFlags, world, epoch, dInIds, dInDists, count, k, dOutIds, dOutDists);
+    return 0;
+    HNSW_CATCH(-1)
+}
 int hnsw_enable_stats(hnsw_handle handle, int on) {
     HNSW_TRY
     get(handle)->enable_stats(on != 0);

@@ -589,6 +589,34 @@ int Index::multilayer_knn_query(const float* queries, int count, int dim, int k,
     return layers;
 }
 
+void Index::knn_query_scatter(const float* d_queries, int count, int dim, int k, const ScatterArgs& sc) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (count <= 0 || k < 1) return;
+    if (this->count() <= 0) throw std::runtime_error("knn_query_scatter on an empty shard");
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    const int ef = std::max(params_.MinNN, k);
+    launch_knn_scatter((int)metric_, view(), d_queries, count, k, ef, sc, d_counters_ + 3, d_counters_ + 6, tuning_, stream_);
+    stats_.search_launches += 1;
+}
+
+void Index::wait_and_merge(const unsigned* d_flags, int world, unsigned epoch, const int* d_in_ids, const float* d_in_dists, int count, int k,
+                           int* d_out_ids, float* d_out_dists) {
+    std::lock_guard<std::mutex> lock(mu_);
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    int* d_err = reinterpret_cast<int*>(d_counters_ + 7);
+    launch_wait_flags(d_flags, world, epoch, d_err, stream_);
+    launch_merge_topk(d_in_ids, d_in_dists, world, count, k, d_out_ids, d_out_dists, stream_);
+    int err = 0;
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    stats_.search_launches += 2;
+    if (err != 0) {
+        HNSW_CUDA_CHECK(cudaMemset(d_err, 0, sizeof(int)));
+        throw std::runtime_error("partitioned query: a peer GPU did not deliver its results in time");
+    }
+}
+
 void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
     std::lock_guard<std::mutex> lock(mu_);
     if (count <= 0 || k < 1) return;

@@ -69,6 +69,21 @@ void launch_relink(int metric, const GraphView& g, const int2* d_affected, int n
                    unsigned* d_work_counter, cudaStream_t stream);
 void launch_clear_rows(const GraphView& g, const int* d_item_node, const int* d_item_layer, int nitems, cudaStream_t stream);
 
+// Partitioned index (partition_kernels.cu): search whose epilogue stores each query's top-k (global ids) into slot
+// `rank` of every peer's gather buffer [world][nq][k] (peer pointers from CUDA IPC), then raises flags[peer][rank].
+constexpr int kMaxPeers = 16;
+struct ScatterArgs {
+    int world, rank, id_offset;
+    unsigned epoch;
+    int* ids[kMaxPeers];
+    float* dists[kMaxPeers];
+    unsigned* flags[kMaxPeers];
+};
+void launch_knn_scatter(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, const ScatterArgs& sc,
+                        unsigned* d_work_counter, unsigned* d_done_counter, const Tuning& t, cudaStream_t stream);
+// one warp spins (bounded) until d_flags[0..world) have all reached `epoch`; *d_error = 1 on timeout
+void launch_wait_flags(const unsigned* d_flags, int world, unsigned epoch, int* d_error, cudaStream_t stream);
+
 // K7: merge `parts` sorted top-k lists per query: in_* are [parts][nq][k], out_* [nq][k]
 void launch_merge_topk(const int* d_in_ids, const float* d_in_dists, int parts, int nq, int k, int* d_out_ids, float* d_out_dists,
                        cudaStream_t stream);

@@ -1,0 +1,159 @@
+// partition_kernels.cu -- partitioned index (SURVEY 8e mode 2): search fused with the exchange of the per-shard top-k.
+//
+// Every GPU owns one sub-graph and searches ALL queries on it.  Instead of "search, then ncclAllGather, then merge",
+// the search kernel's epilogue stores a query's local top-k (ids shifted to global ids) straight into EVERY peer's
+// gather buffer over NVLink (peer pointers obtained with CUDA IPC), so the transfer of query i overlaps the search
+// of query i+1 and no collective is launched.  Completion is signalled with one flag per (peer, source rank):
+//   every warp:   result stores to all peers -> __threadfence_system() -> atomicAdd(done)
+//   last warp:    flags[peer][rank] = epoch  (system-scope release) for every peer
+//   wait kernel:  spins (bounded) until flags[rank][*] >= epoch (acquire), then the merge kernel runs in stream order.
+// Buffers are double-buffered by epoch parity; a rank cannot run two epochs ahead of a peer because each epoch's wait
+// needs that peer's flag of the same epoch, which the peer raises only after finishing the previous epoch's merge
+// (stream order).
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "beam.cuh"
+#include "kernels.hpp"
+
+namespace hnsw {
+
+template <int METRIC, int SPEC>
+__global__ void __launch_bounds__(kThreads, 5)
+knn_scatter_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int vis_size, int cand_cap, int flags,
+                   ScatterArgs sc, unsigned* work_counter, unsigned* done_counter) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis_size, cand_cap);
+    WarpScratch s = carve_scratch(smem + warp * per_warp, g.pitch, ef, vis_size, cand_cap, lane);
+
+    for (;;) {
+        unsigned qi = 0;
+        if (lane == 0) qi = atomicAdd(work_counter, 1u);
+        qi = __shfl_sync(FULL, qi, 0);
+        if (qi >= (unsigned)nq) break;
+
+        const float* qsrc = queries + (size_t)qi * g.dim;
+        for (int i = lane; i < g.pitch; i += 32) s.q[i] = i < g.dim ? __ldg(qsrc + i) : 0.f;
+        __syncwarp();
+        double qn = 0.0;
+        if (METRIC == COSINE) qn = pair_norm_sqrt(s.q, g.dim, lane & 1);
+
+        WarpCounters wc;
+        int cur = g.entry;
+        float cur_d = single_dist<METRIC, SPEC>(g, s, qn, cur, lane);
+        for (int l = g.top_layer; l > 0; --l) greedy_layer<METRIC, SPEC>(g, s, qn, l, cur, cur_d, lane, wc);
+        BeamState st;
+        beam_search<METRIC, SPEC>(g, s, qn, 0, cur, cur_d, ef, st, lane, wc, flags);
+
+        // epilogue: this shard's top-k of query qi, global ids, into slot `rank` of every peer's gather buffer
+        const size_t row = ((size_t)sc.rank * nq + qi) * k;
+        for (int j = lane; j < k; j += 32) {
+            int id = -1;
+            float d = CUDART_NAN_F;
+            if (j < st.n) {
+                const u64 e = s.list[j];
+                id = key_id(e) + sc.id_offset;
+                d = key_dist(e);
+            }
+            for (int p = 0; p < sc.world; ++p) {
+                sc.ids[p][row + j] = id;
+                sc.dists[p][row + j] = d;
+            }
+        }
+        __syncwarp();
+    }
+    // signal: all of this warp's peer stores are ordered before its arrival; the last warp raises the flags
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned total = gridDim.x * (blockDim.x >> 5);
+        if (atomicAdd(done_counter, 1u) == total - 1u) {
+            *done_counter = 0u;  // ready for the next launch (stream-ordered)
+            __threadfence_system();
+            for (int p = 0; p < sc.world; ++p) {
+                volatile unsigned* f = sc.flags[p] + sc.rank;
+                *f = sc.epoch;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
+// One warp: lane p waits for rank p's flag of this epoch.  Bounded: a peer that never arrives sets *error instead of
+// hanging the GPU.
+__global__ void wait_flags_kernel(const unsigned* flags, int world, unsigned epoch, int* error) {
+    const int lane = threadIdx.x;
+    if (lane < world) {
+        const volatile unsigned* f = flags + lane;
+        unsigned spins = 0;
+        while ((int)(*f - epoch) < 0) {  // a fast peer may already have raised the next epoch
+            __nanosleep(200);
+            if (++spins > (1u << 24)) {  // ~ 3+ s
+                atomicExch(error, 1);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+template <typename Kern>
+static int scatter_grid(Kern kern, size_t smem_per_warp, const Tuning& t, int work_items, int& warps) {
+    int dev = 0, max_optin = 0, sms = 0, per_sm = 0;
+    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    warps = kWarpsPerBlock;
+    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) warps >>= 1;
+    const size_t smem = smem_per_warp * warps;
+    if (smem > (size_t)max_optin) throw std::runtime_error("search width too large for shared memory");
+    HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);
+    const int need = (work_items + warps - 1) / warps;
+    return std::max(1, std::min(need, sms * per_sm));
+}
+
+int pick_vis_size(int requested, int ef);  // search_kernels.cu
+
+void launch_knn_scatter(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, const ScatterArgs& sc,
+                        unsigned* d_work_counter, unsigned* d_done_counter, const Tuning& t, cudaStream_t stream) {
+    if (nq <= 0) return;
+    if (sc.world < 1 || sc.world > kMaxPeers) throw std::invalid_argument("scatter: world size out of range");
+    const int vis = pick_vis_size(t.vis_size_search, ef);
+    const int cand_cap = ((std::max(g.stride0, g.strideU) + 31) / 32) * 32;
+    const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis, cand_cap);
+    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
+#define HNSW_LAUNCH_SCATTER(M)                                                                                                 \
+    {                                                                                                                          \
+        int warps = 0;                                                                                                         \
+        if (g.pitch <= kSegFloats && ef <= 64 && (long long)g.count <= ((long long)vis << 16)) {                               \
+            constexpr int S = kSpecShortRows | kSpecSmallList | kSpecVis16;                                                    \
+            const int grid = scatter_grid(knn_scatter_kernel<M, S>, per_warp, t, nq, warps);                                  \
+            knn_scatter_kernel<M, S><<<grid, 32 * warps, per_warp * warps, stream>>>(g, d_queries, nq, k, ef, vis, cand_cap,  \
+                                                                                    t.flags, sc, d_work_counter, d_done_counter); \
+        } else {                                                                                                               \
+            const int grid = scatter_grid(knn_scatter_kernel<M, 0>, per_warp, t, nq, warps);                                  \
+            knn_scatter_kernel<M, 0><<<grid, 32 * warps, per_warp * warps, stream>>>(g, d_queries, nq, k, ef, vis, cand_cap,  \
+                                                                                    t.flags, sc, d_work_counter, d_done_counter); \
+        }                                                                                                                      \
+    }
+    switch (metric) {
+        case SQ_EUCLID: HNSW_LAUNCH_SCATTER(SQ_EUCLID) break;
+        case EUCLID: HNSW_LAUNCH_SCATTER(EUCLID) break;
+        case COSINE: HNSW_LAUNCH_SCATTER(COSINE) break;
+        default: HNSW_LAUNCH_SCATTER(UCOSINE) break;
+    }
+#undef HNSW_LAUNCH_SCATTER
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_wait_flags(const unsigned* d_flags, int world, unsigned epoch, int* d_error, cudaStream_t stream) {
+    wait_flags_kernel<<<1, 32, 0, stream>>>(d_flags, world, epoch, d_error);
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace hnsw

@@ -74,6 +74,13 @@ def _load():
         "hnsw_knn_query_layer": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
         "hnsw_multilayer_knn_query": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
         "hnsw_ids": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
+        "hnsw_ipc_alloc": (ct.c_int, [ct.c_size_t, ct.c_void_p, ct.c_void_p]),
+        "hnsw_ipc_open": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
+        "hnsw_ipc_close": (ct.c_int, [ct.c_void_p]),
+        "hnsw_ipc_free": (ct.c_int, [ct.c_void_p]),
+        "hnsw_knn_query_scatter": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p]),
+        "hnsw_wait_and_merge_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_uint, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int,
+                                                  ct.c_void_p, ct.c_void_p]),
         "hnsw_top_layer": (ct.c_int, [ct.c_void_p]),
         "hnsw_entry_point": (ct.c_int, [ct.c_void_p]),
         "hnsw_get_info": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
@@ -93,6 +100,12 @@ def _load():
 
 
 lib = _load()
+
+
+class Scatter(ct.Structure):
+    """hnsw_scatter of include/hnsw_b200.h (partitioned index, fused search + exchange)."""
+    _fields_ = [("world", ct.c_int), ("rank", ct.c_int), ("idOffset", ct.c_int), ("epoch", ct.c_uint),
+                ("ids", ct.POINTER(ct.c_int) * 16), ("dists", ct.POINTER(ct.c_float) * 16), ("flags", ct.POINTER(ct.c_uint) * 16)]
 
 
 class _LayerInfo(ct.Structure):

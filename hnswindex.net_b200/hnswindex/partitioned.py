@@ -2,7 +2,10 @@
 Partitioned index (mode 2): for graphs that exceed one GPU the data set is cut into
 `world` contiguous id ranges, every rank (one process per GPU) builds / loads an independent
 sub-HNSW over its range, all ranks see all queries, and the per-rank top-k lists are exchanged with
-ONE all-gather (NCCL over NVLink on GPUs) and merged by `merge_keys_kernel` (K7).
+ONE all-gather (NCCL over NVLink on GPUs) and merged by `merge_keys_kernel` (K7) -- or, after `enable_fused()`, with
+no collective at all: the search kernel's epilogue stores each query's top-k straight into every peer's gather buffer
+(CUDA IPC peer pointers, NVLink stores overlapping the search of the next queries) and raises a per-rank flag; a wait
+kernel + the merge kernel follow in stream order (csrc/partition_kernels.cu).
 
 The reference has no distributed mode; parity for this mode is defined against the oracle running the
 same sub-graphs + the same merge, and against brute force for recall (tests/test_partitioned_cpu.py,
@@ -64,6 +67,7 @@ class PartitionedIndex:
         self.rank, self.world, self.total = rank, world, total
         self.start, self.end = shard_range(total, rank, world)
         self.index, self.local_search, self.group = index, local_search, group
+        self._fused = None
 
     # ---- device-independent pieces ------------------------------------------------------------
     def to_global(self, local_ids: np.ndarray) -> np.ndarray:
@@ -93,12 +97,80 @@ class PartitionedIndex:
         g_ids, g_d = self._gather(ids_t, d_t)
         return merge_topk_numpy(g_ids.numpy(), g_d.numpy(), k)
 
+    # ---- fused search + exchange (no collective in the data path) ----------------------------------------
+    def enable_fused(self, nq_max: int, k: int) -> None:
+        """Allocate this rank's double-buffered gather buffer + flags, exchange the CUDA IPC handles with the other ranks
+        (a one-off all_gather_object) and map every peer's buffer.  All ranks must call it with the same arguments."""
+        import ctypes as ct
+        import torch
+        import torch.distributed as dist
+        from . import bindings as hb
+        w = self.world
+        half = w * nq_max * k                       # elements of one parity of ids (and of dists)
+        flags_off = 2 * half * 4 * 2                # bytes: ids[2][half] int32, dists[2][half] fp32, then flags[world] u32
+        nbytes = flags_off + 256
+        ptr = ct.c_void_p()
+        handle = (ct.c_ubyte * 64)()
+        hb._check(hb.lib.hnsw_ipc_alloc(ct.c_size_t(nbytes), ct.byref(ptr), handle))
+        handles = [None] * w
+        if w > 1:
+            dist.all_gather_object(handles, bytes(handle), group=self.group)
+        else:
+            handles[0] = bytes(handle)
+        base = []
+        for p in range(w):
+            if p == self.rank:
+                base.append(ptr.value)
+            else:
+                pp = ct.c_void_p()
+                hb._check(hb.lib.hnsw_ipc_open((ct.c_ubyte * 64).from_buffer_copy(handles[p]), ct.byref(pp)))
+                base.append(pp.value)
+        self._fused = dict(nq_max=nq_max, k=k, base=base, half=half, flags_off=flags_off, epoch=0, own=ptr.value,
+                           out_ids=torch.empty((nq_max, k), dtype=torch.int32, device="cuda"),
+                           out_d=torch.empty((nq_max, k), dtype=torch.float32, device="cuda"))
+        if w > 1:
+            dist.barrier(group=self.group)          # every buffer is mapped before anybody writes into it
+
+    def _knn_query_fused(self, q_dev, nq: int, k: int):
+        import ctypes as ct
+        from . import bindings as hb
+        f = self._fused
+        if nq > f["nq_max"] or k != f["k"]:
+            raise ValueError("fused partitioned query: batch larger than the buffers of enable_fused(), or a different k")
+        f["epoch"] += 1
+        par = f["epoch"] & 1
+        sc = hb.Scatter()
+        sc.world, sc.rank, sc.idOffset, sc.epoch = self.world, self.rank, self.start, f["epoch"]
+        # layout of a buffer: ids[2][world][nq_max][k] | dists[2][world][nq_max][k] | flags[world]; a query batch of nq rows
+        # uses the first nq rows of every rank's slot, so the slot pitch is nq (the kernel indexes [rank][nq][k])
+        ids_off = par * f["half"] * 4
+        d_off = 2 * f["half"] * 4 + par * f["half"] * 4
+        for p in range(self.world):
+            sc.ids[p] = ct.cast(ct.c_void_p(f["base"][p] + ids_off), ct.POINTER(ct.c_int))
+            sc.dists[p] = ct.cast(ct.c_void_p(f["base"][p] + d_off), ct.POINTER(ct.c_float))
+            sc.flags[p] = ct.cast(ct.c_void_p(f["base"][p] + f["flags_off"]), ct.POINTER(ct.c_uint))
+        hb._check(hb.lib.hnsw_knn_query_scatter(self.index._h, ct.c_void_p(q_dev.data_ptr()), nq, self.index.dim, k, ct.byref(sc)))
+        hb._check(hb.lib.hnsw_wait_and_merge_device(self.index._h, ct.c_void_p(f["own"] + f["flags_off"]), self.world, f["epoch"],
+                                                   ct.c_void_p(f["own"] + ids_off), ct.c_void_p(f["own"] + d_off), nq, k,
+                                                   ct.c_void_p(f["out_ids"].data_ptr()), ct.c_void_p(f["out_d"].data_ptr())))
+        return f["out_ids"][:nq], f["out_d"][:nq]
+
+    def knn_query_device(self, q_dev, k: int):
+        """Queries already on this GPU (torch tensor [nq, dim] fp32) -> merged (ids, dists) torch tensors on the GPU."""
+        nq = int(q_dev.shape[0])
+        if self._fused is not None:
+            return self._knn_query_fused(q_dev, nq, k)
+        return self._knn_query_gather(q_dev, nq, k)
+
     def _knn_query_cuda(self, q: np.ndarray, k: int):
+        import torch
+        ids, d = self.knn_query_device(torch.from_numpy(q).cuda(), k)
+        return ids.cpu().numpy(), d.cpu().numpy()
+
+    def _knn_query_gather(self, q_dev, nq: int, k: int):
         import ctypes as ct
         import torch
         from . import bindings as hb
-        nq = q.shape[0]
-        q_dev = torch.from_numpy(q).cuda()
         ids_dev = torch.empty((nq, k), dtype=torch.int32, device="cuda")
         d_dev = torch.empty((nq, k), dtype=torch.float32, device="cuda")
         self.index.knn_query_device(q_dev.data_ptr(), nq, k, ids_dev.data_ptr(), d_dev.data_ptr())
@@ -111,4 +183,4 @@ class PartitionedIndex:
                                            ct.c_void_p(out_ids.data_ptr()), ct.c_void_p(out_d.data_ptr()), None)
         if rc < 0:
             raise RuntimeError(hb.last_error())
-        return out_ids.cpu().numpy(), out_d.cpu().numpy()
+        return out_ids, out_d

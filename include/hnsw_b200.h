@@ -23,6 +23,7 @@
 #include <stdbool.h>
 #include <stdint.h>
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -147,6 +148,32 @@ HNSW_API int hnsw_exact_knn(hnsw_handle handle, const float* queries, int count,
  * -1 padded) into [count][k] on the current device. */
 HNSW_API int hnsw_merge_topk_device(const int* dInIds, const float* dInDists, int parts, int count, int k, int* dOutIds, float* dOutDists,
                                     void* cudaStream);
+
+/* Partitioned index (one sub-graph per GPU, SURVEY 8e mode 2) without a collective in the data path: buffers shared
+ * between the ranks of one node through CUDA IPC, and a search whose epilogue writes every query's local top-k (ids +
+ * idOffset) into slot `rank` of EVERY peer's gather buffer over NVLink, then raises flags[peer][rank] = epoch.
+ *   hnsw_ipc_alloc   cudaMalloc (zeroed) + cudaIpcGetMemHandle -> 64-byte handle to send to the other ranks
+ *   hnsw_ipc_open    map a peer's buffer (cudaIpcOpenMemHandle); hnsw_ipc_close / hnsw_ipc_free undo them
+ *   hnsw_knn_query_scatter      stream-ordered, does not synchronise; ids[p] / dists[p] are [world][count][k], flags[p] is
+ *                               [world] unsigned; p = 0..world-1 includes this rank's own buffer
+ *   hnsw_wait_and_merge_device  waits (bounded, on the device) until all `world` flags of this rank reached `epoch`,
+ *                               merges its gather buffer into [count][k], synchronises; -1 if a peer never arrived
+ * Epochs must increase by one per query; alternate two gather buffers by epoch parity. */
+#define HNSW_MAX_PEERS 16
+typedef struct hnsw_scatter {
+    int world, rank, idOffset;
+    unsigned epoch;
+    int* ids[HNSW_MAX_PEERS];
+    float* dists[HNSW_MAX_PEERS];
+    unsigned* flags[HNSW_MAX_PEERS];
+} hnsw_scatter;
+HNSW_API int hnsw_ipc_alloc(size_t bytes, void** devPtr, unsigned char* handle64);
+HNSW_API int hnsw_ipc_open(const unsigned char* handle64, void** devPtr);
+HNSW_API int hnsw_ipc_close(void* devPtr);
+HNSW_API int hnsw_ipc_free(void* devPtr);
+HNSW_API int hnsw_knn_query_scatter(hnsw_handle handle, const float* dQueries, int count, int dim, int k, const hnsw_scatter* sc);
+HNSW_API int hnsw_wait_and_merge_device(hnsw_handle handle, const unsigned* dFlags, int world, unsigned epoch, const int* dInIds,
+                                        const float* dInDists, int count, int k, int* dOutIds, float* dOutDists);
 
 /* Measurement hooks. */
 typedef struct hnsw_stats {

@@ -96,3 +96,35 @@ def test_partitioned_index_world1_cuda_path(hnswindex):
     a = pix.knn_query(data[:100], 5)
     b = ix.knn_query(data[:100], 5)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_partitioned_fused_world1_matches_plain_query(hnswindex):
+    # the fused search + scatter path (CUDA IPC buffer, flags, wait + merge) with a single rank: same answers as knn_query
+    from hnswindex import partitioned as P
+    rng = np.random.default_rng(6)
+    data = rng.random((5000, 48), dtype=np.float32)
+    ix = hnswindex.Index(48, "sq_euclid")
+    ix.set_collection_size(5000)
+    ix.add(data)
+    ix.set_min_nn(40)
+    pix = P.PartitionedIndex(0, 1, 5000, index=ix)
+    pix.enable_fused(600, 7)
+    for n in (600, 1, 333, 600, 17):
+        a = pix.knn_query(data[:n], 7)
+        b = ix.knn_query(data[:n], 7)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    with pytest.raises(ValueError):
+        pix.knn_query(data[:601], 7)
+
+
+def test_partitioned_fused_two_gpus_matches_all_gather_path(hnswindex):
+    import subprocess
+    import sys
+    from pathlib import Path
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(root / "tools" / "partition_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "partition_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -1,6 +1,4 @@
-rm -f gpurun_out/sweep13.log gpurun_out/build9.log
-timeout 300 python tools/sweep.py 1000000 48 >> gpurun_out/sweep13.log 2>&1
-timeout 300 python tools/sweep.py 1000000 48 >> gpurun_out/sweep13.log 2>&1
-cat gpurun_out/sweep13.log
-timeout 300 python tools/build_only.py 1000000 >> gpurun_out/build9.log 2>&1
-cut -c1-200 gpurun_out/build9.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+timeout 600 $TR bench.py --gpus 2 --mode partitioned --steps 20 --warmup 3 > gpurun_out/bench_c4_n2.json 2> gpurun_out/bench_c4_n2.err; echo "c4 rc=$?"; cat gpurun_out/bench_c4_n2.json | cut -c1-1500
+timeout 300 python tools/partition_check.py 2>&1 | tail -2
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/partition_check.py 2>&1 | tail -3

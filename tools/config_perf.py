@@ -33,6 +33,6 @@ def run(name, metric, n, dim, rank, M, efc, k, efs, nq=10000, rate=None, normali
         print(json.dumps({"cfg": name, "ef": max(ef, k), "recall@k": round(rec, 4), "kernel_ms": round(min(ms), 3), "qps": round(nq / min(ms) * 1e3),
                           "ndist_per_q": round(st["ndist"] / nq, 1), "gathered_GBps": round(st["ndist"] * dim * 4 / min(ms) / 1e6, 1), "exact_1000q_s": round(te, 2)}), flush=True)
 
-which = sys.argv[1] if len(sys.argv) > 1 else "all"
+which = (sys.argv[1] if len(sys.argv) > 1 else "all") if __name__ == "__main__" else "none"
 if which in ("c3", "all"): run("C3-like 200k x 960 cosine M=32 k=100", "cosine", 200000, 960, 32, 32, 200, 100, [100, 200], rate=1 / np.log(32))
 if which in ("c4", "all"): run("C4-shard 1.25M x 96 ucosine M=16 k=10", "ucosine", 1250000, 96, 16, 16, 200, 10, [32, 48, 64], normalize=True)
