@@ -217,7 +217,7 @@ static int persistent_grid(Kern kern, size_t smem_per_warp, const Tuning& t, int
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     warps = kWarpsPerBlock;
-    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) warps >>= 1;
+    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) --warps;  // as many independent warps as fit (4, 3, 2 or 1)
     const size_t smem = smem_per_warp * warps;
     if (smem > (size_t)max_optin)
         throw std::runtime_error("MaxCandidates / MaxEdges too large for shared memory: need " + std::to_string(smem) + " B per warp");

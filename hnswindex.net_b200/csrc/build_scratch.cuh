@@ -49,12 +49,16 @@ __device__ __forceinline__ int select_neighbors_long(const GraphView& g, BuildSc
             load_vector(g, c, b.cvec, lane);
             double cn = 0.0;
             if (METRIC == COSINE) cn = __ldg(g.norm_sqrt + c);
-            batch_dist_to<METRIC>(g, b.s.stg, b.cvec, cn, b.sel, b.s.cand_dist, nsel, lane);
-            ndist += nsel;
-            bool rej = false;
-            for (int j = lane; j < nsel; j += 32) rej |= b.s.cand_dist[j] < cd;  // strict, Heuristic.cs:34
-            ok = !__any_sync(FULL, rej);
-            __syncwarp();
+            // 16 selected neighbours per pass, closest first; stop at the first pass that rejects the candidate
+            // (most rejections come from the closest neighbours, so the later passes are rarely needed)
+            for (int s0 = 0; s0 < nsel && ok; s0 += kStageRows) {
+                const int m = min(kStageRows, nsel - s0);
+                batch_dist_to<METRIC>(g, b.s.stg, b.cvec, cn, b.sel + s0, b.s.cand_dist, m, lane);
+                ndist += m;
+                const bool rej = lane < m && b.s.cand_dist[lane] < cd;  // strict, Heuristic.cs:34
+                ok = !__any_sync(FULL, rej);
+                __syncwarp();
+            }
         }
         if (ok) {
             if (lane == 0) b.sel[nsel] = c;

@@ -167,7 +167,7 @@ static int configure_persistent(Kern kern, size_t smem_per_warp, const Tuning& t
     HNSW_CUDA_CHECK(cudaGetDevice(&dev));
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     warps = kWarpsPerBlock;
-    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) warps >>= 1;
+    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) --warps;  // as many independent warps as fit (4, 3, 2 or 1)
     const size_t smem = smem_per_warp * warps;
     if (smem > (size_t)max_optin)
         throw std::runtime_error("search width (max(MinNN, k)) too large for shared memory: need " + std::to_string(smem) +

@@ -198,15 +198,16 @@ def _rows_as_sets(rows):
     return [frozenset(int(x) for x in r if x >= 0) for r in rows]
 
 
-@pytest.mark.parametrize("metric", ["sq_euclid", "cosine", "euclid"])
-def test_one_by_one_insertion_builds_the_oracle_graph(hnswindex, oracle, metric):
+@pytest.mark.parametrize("metric,dim", [("sq_euclid", 32), ("cosine", 32), ("euclid", 32), ("cosine", 200), ("sq_euclid", 131)])
+def test_one_by_one_insertion_builds_the_oracle_graph(hnswindex, oracle, metric, dim):
     # Adding items one call at a time is the reference's serial Add: the GPU must produce the same
     # levels, entry point and link sets (row order is free only where the reference's is: the
     # unsorted early return of Heuristic.cs:13-18).
-    v = oracle.random_vectors(32, 700)
+    # dims above 128 take the long-row (segmented) staging path and the candidate-by-candidate heuristic
+    v = oracle.random_vectors(dim, 700)
     ref = oracle.OracleIndex(metric, max_edges=8, max_candidates=40, collection_size=64, allow_removals=False)
     ref.add(v)
-    gpu = hnswindex.Index(32, metric)
+    gpu = hnswindex.Index(dim, metric)
     gpu.set_max_edges(8); gpu.set_max_candidates(40); gpu.set_collection_size(64); gpu.set_allow_removals(False)
     ids = [int(gpu.add(v[i])[0]) for i in range(len(v))]
     assert ids == list(range(700))
