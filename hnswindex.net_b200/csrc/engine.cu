@@ -215,6 +215,7 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     std::vector<int> lv, ids_new, src_row;
     lv.reserve(count); ids_new.reserve(count); src_row.reserve(count);
     int nfresh = 0, nreused = 0;
+    size_t stack_top = removed_stack_.size();  // slots are taken from the stack only once nothing below can fail
     for (int i = 0; i < count; ++i) {
         // GraphData.GetRandomLayer, GraphData.cs:211-219
         const float r = rng_.NextSingle();
@@ -226,9 +227,8 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
         int level = (int)x;
         if (level > 30) level = 30;
         int id;
-        if (params_.AllowRemovals && !removed_stack_.empty()) {  // "Search for empty spot first", GraphData.cs:84-91
-            id = removed_stack_.back();
-            removed_stack_.pop_back();
+        if (params_.AllowRemovals && stack_top > 0) {  // "Search for empty spot first", GraphData.cs:84-91
+            id = removed_stack_[--stack_top];
             ++nreused;
         } else {
             id = length_ + nfresh++;
@@ -242,6 +242,7 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     if (nnew == 0) return count;
     const int first = length_;
     ensure_capacity(first + nfresh);
+    removed_stack_.resize(stack_top);
 
     // vectors -> slab rows
     if (nreused == 0 && nnew == count) {

@@ -121,6 +121,29 @@ def test_codec_roundtrip_against_oracle(hnswindex, oracle, tmp_path, packed_in, 
     assert np.array_equal(ia, ib) and np.array_equal(da.view(np.uint32), db.view(np.uint32))
 
 
+@pytest.mark.parametrize("packed", [False, True])
+def test_codec_keeps_removal_state(hnswindex, oracle, tmp_path, packed):
+    # a snapshot with removed nodes (IsRemoved, ActiveNodes in ActiveSet order, RemovedIndexes) survives the product codec
+    v = oracle.random_vectors(16, 400)
+    ix = oracle.OracleIndex("sq_euclid", max_edges=6)
+    ids = ix.add(v)
+    ix.remove(ids[5:120:3])
+    a, b = tmp_path / "a.bin", tmp_path / "b.bin"
+    ix.serialize(a, packed=packed)
+    assert hnswindex.lib.hnsw_snapshot_transcode(str(a).encode(), str(b).encode(), int(packed)) == 400, hnswindex.last_error()
+    ix2 = oracle.OracleIndex.deserialize("sq_euclid", b)
+    assert ix2.count == ix.count == 400 - len(ids[5:120:3])
+    assert np.array_equal(ix2.active_ids(), ix.active_ids())
+    assert [ix2.is_removed(i) for i in range(400)] == [ix.is_removed(i) for i in range(400)]
+    assert ix2.entry_point == ix.entry_point
+    q = oracle.random_vectors(16, 40, seed=3)
+    ia, da = ix.knn_query(q, 6)
+    ib, db = ix2.knn_query(q, 6)
+    assert np.array_equal(ia, ib) and np.array_equal(da.view(np.uint32), db.view(np.uint32))
+    # the removed-slot stack comes back in the same order: both hand out the same ids next
+    assert ix2.add(v[:4]).tolist() == ix.add(v[:4]).tolist()
+
+
 def test_codec_byte_identical_to_oracle_writer_when_no_stale_slots(hnswindex, oracle, tmp_path):
     # Two independent writers of the same layout must agree byte for byte once the oracle's stale
     # Buffer slots are removed (AllowRemovals=false, transcode of a transcode is a fixed point).
