@@ -72,3 +72,53 @@ def test_c2_oracle_on_the_gpu_written_snapshot(built, oracle, tmp_path):
     e_ids, e_d = ix.exact_knn(sample[:32], 10)
     b_ids, b_d = ref.exact_knn(sample[:32], 10, threads=16)
     assert np.array_equal(e_ids, b_ids) and np.array_equal(e_d.view(np.uint32), b_d.view(np.uint32))
+
+
+def test_c2_remove_and_reuse_at_full_size():
+    # Remove at the C2 size (AllowRemovals = true): 100k of 1M removed in one call, then 50k slots reused.
+    # Size-independent properties: nothing live points at a removed node, removed ids never come back from a query or
+    # from the exact scan, recall of the remaining items stays above 0.98 x the recall before (the reference's own bar,
+    # GraphTests.cs:148; its sequential algorithm loses ~1 pt when 10 % are removed, and so does this one -- see
+    # test_remove_in_one_call_keeps_the_recall_of_the_sequential_reference), reused slots are the removed ones.
+    import time
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as ge
+    ge.build()
+    import bench
+    import hnswindex
+    n = 1_000_000
+    data, queries = bench.make_data(n, 2_000)
+    ix = hnswindex.Index(128, "sq_euclid")
+    ix.set_collection_size(n); ix.set_max_edges(16); ix.set_max_candidates(200)
+    ix.add(data)
+    ix.set_min_nn(48)
+    truth0, _ = ix.exact_knn(queries, 10)
+    rec0 = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ix.knn_query(queries, 10)[0], truth0)])
+    rng = np.random.default_rng(1)
+    victims = rng.permutation(n)[:100_000].astype(np.int32)
+    t = time.time()
+    ix.remove(victims)
+    t_remove = time.time() - t
+    assert ix.count == n - 100_000
+    gone = np.zeros(n, dtype=bool); gone[victims] = True
+    levels, rows0, ep = ix.export_layer0()
+    assert not gone[ep]
+    live_rows = rows0[~gone]
+    assert not gone[live_rows[live_rows >= 0]].any()                 # no live layer-0 row names a removed node
+    assert (rows0[gone] == -1).all()
+    g_ids, g_d = ix.knn_query(queries, 10)
+    assert not gone[g_ids[g_ids >= 0]].any()
+    truth1, _ = ix.exact_knn(queries, 10)
+    assert not gone[truth1].any()
+    rec1 = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(g_ids, truth1)])
+    assert rec1 > 0.98 * rec0, (rec0, rec1)
+    for li in ix.get_info():
+        assert li["avgOutEdges"] == li["avgInEdges"]                 # GraphTests.cs:151-155
+    new_ids = ix.add(data[victims[:50_000]])
+    assert set(new_ids.tolist()) == set(victims[-50_000:].tolist())  # the most recently removed slots come back first
+    assert ix.count == n - 50_000
+    s_ids, _ = ix.knn_query(data[victims[:2000]], 1)
+    assert (s_ids[:, 0] == new_ids[:2000]).mean() > 0.99
+    print(f"remove 100k of 1M: {t_remove:.2f}s ({100_000 / t_remove:.0f} removals/s), recall {rec0:.4f} -> {rec1:.4f}")

@@ -541,6 +541,25 @@ def test_remove_half_in_one_call_like_reference_tests(hnswindex, oracle):
     assert abs(removal_recall - insert_recall) < 0.02 or removal_recall > insert_recall
 
 
+def test_remove_in_one_call_keeps_the_recall_of_the_sequential_reference(hnswindex, oracle, tmp_path):
+    # 10 % of a 20k SIFT-shaped index removed: the oracle removes one by one (the reference's algorithm), the GPU in one
+    # call (chunks); recall@10 of the survivors must agree within 0.5 pt (north_star bar for GPU-modified graphs)
+    full = sift_like(21000)
+    data, q = full[:20000], full[20000:]          # held-out queries from the same distribution
+    ref, path = _oracle_graph(oracle, tmp_path, "sq_euclid", data, "rm_recall", max_candidates=200, collection_size=20000)
+    gpu = hnswindex.Index.deserialize("sq_euclid", path)
+    victims = np.random.default_rng(2).permutation(20000)[:2000].astype(np.int32)
+    ref.remove(victims)
+    gpu.remove(victims)
+    assert gpu.count == ref.count == 18000
+    ref.set_min_nn(32); gpu.set_min_nn(32)
+    truth, _ = gpu.exact_knn(q, 10)
+    assert not np.isin(truth, victims).any()
+    rg = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(gpu.knn_query(q, 10)[0], truth)])
+    ro = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ref.knn_query(q, 10, threads=8)[0], truth)])
+    assert rg >= ro - 0.005, (rg, ro)
+
+
 def test_remove_entry_point_everything_and_errors(hnswindex, oracle, tmp_path):
     rng = np.random.default_rng(3)
     v = rng.random((400, 16), dtype=np.float32)
