@@ -150,7 +150,8 @@ __device__ __forceinline__ void compute_staged(const GraphView& g, Stager& stg, 
 // SPEC (compile-time knowledge that lets the hot kernels drop dead code; 0 = generic):
 //   bit 0: rows fit one staging segment (pitch <= kSegFloats);  bit 1: the list never exceeds 64 entries (ef <= 64)
 //   bit 2: the visited table holds 16-bit tags (vis16_test_and_set): every id of the index is below vis_size * 65536
-constexpr int kSpecShortRows = 1, kSpecSmallList = 2, kSpecVis16 = 4;
+//   bit 3: the list never exceeds 1024 entries (ef <= 1024): the binary-search insertion path is dead code
+constexpr int kSpecShortRows = 1, kSpecSmallList = 2, kSpecVis16 = 4, kSpecMidList = 8;
 
 template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, const int* ids, float* out,
@@ -300,6 +301,7 @@ __device__ __forceinline__ bool list_insert(u64* list, BeamState& st, u64 key, i
         if (pos < st.cursor) st.cursor = pos;
         return true;
     }
+    if (SPEC & kSpecMidList) return false;  // (unreachable)
     const int pos = list_lower_bound(list, n, key, lane);
     if (pos < n && (list[pos] >> 1) == (key >> 1)) return false;  // same distance bits + id
     if (pos >= st.ef) return false;

@@ -186,8 +186,11 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
                        unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream) {
     if (nq <= 0) return;
     const int vis = pick_vis_size(t.vis_size_search, ef);
+    // 16-bit tags hold two entries per word: for the mid-size lists the same filter fits half the words (more warps per SM)
+    const int vis_mid = std::max(256, vis / 2);
     const int cand_cap = ((std::max(g.stride0, g.strideU) + 31) / 32) * 32;
     const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis, cand_cap);
+    const size_t per_warp_mid = warp_scratch_bytes(g.pitch, ef, vis_mid, cand_cap);
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
 #define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
     {                                                                                                                           \
@@ -197,6 +200,11 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
             const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
                 g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
+        } else if (layer == 0 && g.pitch <= kSegFloats && ef <= 1024 && (long long)g.count <= ((long long)vis_mid << 16)) {     \
+            constexpr int S = kSpecShortRows | kSpecMidList | kSpecVis16;                                                       \
+            const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);                 \
+            knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                                \
+                g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);              \
         } else if (layer == 0) {                                                                                                \
             const int grid = configure_persistent(knn_search_kernel<M, false, 0>, per_warp, t, nq, warps);                     \
             knn_search_kernel<M, false, 0><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
