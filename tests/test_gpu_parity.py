@@ -475,7 +475,7 @@ def _gpu_layer_sets(gpu, layer):
     return _rows_as_sets(rows)
 
 
-@pytest.mark.parametrize("metric", ["sq_euclid", "ucosine"])
+@pytest.mark.parametrize("metric", ["sq_euclid", "ucosine", "cosine"])
 def test_remove_one_by_one_matches_oracle(hnswindex, oracle, tmp_path, metric):
     # one id per call = the reference's sequential Remove (GraphConnector.cs:53-167): same link SETS in every row,
     # same entry point, same query answers
@@ -605,3 +605,37 @@ def test_remove_entry_point_everything_and_errors(hnswindex, oracle, tmp_path):
     noremove.add(v[:10])
     with pytest.raises(RuntimeError):
         noremove.remove([1])
+
+
+def test_remove_and_layer_queries_on_tiny_indexes(hnswindex, oracle):
+    # edge cases: 1-3 items, removals down to empty, layer queries on a single-layer graph, range query after removal
+    rng = np.random.default_rng(8)
+    v = rng.random((3, 8), dtype=np.float32)
+    ix = hnswindex.Index(8, "sq_euclid")
+    ref = oracle.OracleIndex("sq_euclid")
+    for i in range(3):
+        assert ix.add(v[i:i + 1]).tolist() == ref.add(v[i:i + 1]).tolist() == [i]
+    assert ix.entry_point() == ref.entry_point
+    top = ix.top_layer()
+    a = ix.knn_query_layer(v, 3, top)
+    b = ref.knn_query_layer(v, 3, top)
+    assert np.array_equal(a[0], b[0])
+    m_ids, _ = ix.multilayer_knn_query(v, 2)
+    o_ids, _ = ref.multilayer_knn_query(v, 2)
+    assert np.array_equal(m_ids, o_ids)
+    r_ids, r_d = ix.range_query(v, 100.0)
+    assert all(len(x) == 3 for x in r_ids)
+    for victim in (1, ref.entry_point if ref.entry_point != 1 else 0):
+        ix.remove([victim]); ref.remove([victim])
+        assert ix.count == ref.count and ix.entry_point() == ref.entry_point
+        g, o = ix.knn_query(v, 3), ref.knn_query(v, 3)
+        assert np.array_equal(g[0], o[0]) and np.array_equal(np.isnan(g[1]), np.isnan(o[1]))
+        r_ids, _ = ix.range_query(v, 100.0)
+        assert all(len(x) == ix.count for x in r_ids)
+    last = int(ix.ids()[0])
+    ix.remove([last]); ref.remove([last])
+    assert ix.count == 0 == ref.count and ix.entry_point() == -1 == ref.entry_point
+    assert (ix.knn_query(v, 2)[0] == -1).all()
+    assert ix.get_info() == [] and len(ix.connected_component_counts()) == 0
+    assert sorted(ix.add(v).tolist()) == sorted(ref.add(v).tolist()) == [0, 1, 2]
+    assert ix.count == 3
