@@ -366,14 +366,17 @@ __device__ __forceinline__ void gvis_clear(const WarpScratch& s, int lane) {
     __syncwarp();
 }
 __device__ __forceinline__ bool gvis_test_and_set(const WarpScratch& s, int id) {
+    // 2-way buckets read with ONE 64-bit load that bypasses L1 (the table lives in L2), updated with a plain store:
+    // only this warp touches its table, and two lanes of one instruction landing in the same bucket merely lose one
+    // of the two records (that node may be evaluated again later -- harmless)
     const uint32_t tag = (uint32_t)id + 1u;
-    uint32_t slot = (tag * 0x9E3779B1u) >> s.gvis_shift;
-    for (int p = 0; p < 16; ++p) {
-        const uint32_t old = atomicCAS(s.gvis + slot, 0u, tag);
-        if (old == 0u) return true;
-        if (old == tag) return false;
-        slot = (slot + 1u) & (uint32_t)(s.gvis_size - 1);
-    }
+    const uint32_t b = (tag * 0x9E3779B1u) >> (s.gvis_shift + 1);
+    uint2* bucket = reinterpret_cast<uint2*>(s.gvis) + b;
+    const uint2 v = __ldcg(bucket);
+    if (v.x == tag || v.y == tag) return false;
+    if (v.x == 0u) __stcg(&bucket->x, tag);
+    else if (v.y == 0u) __stcg(&bucket->y, tag);
+    else __stcg(bucket, make_uint2(tag, v.x));  // full bucket: the older record is dropped
     return true;
 }
 
