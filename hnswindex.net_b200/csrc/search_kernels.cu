@@ -205,6 +205,13 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
             const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);                 \
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                                \
                 g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);              \
+        } else if (layer == 0 && g.pitch > kSegFloats && ef <= 1024 && (long long)g.count <= ((long long)vis << 16)) {          \
+            /* long rows are DRAM-bound and every re-evaluation is real traffic (C3: 440 GB read for 393 GB of algorithmic     \
+               bytes): same words, twice the entries */                                                                        \
+            constexpr int S = kSpecMidList | kSpecVis16;                                                                        \
+            const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
+            knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
+                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
         } else if (layer == 0) {                                                                                                \
             const int grid = configure_persistent(knn_search_kernel<M, false, 0>, per_warp, t, nq, warps);                     \
             knn_search_kernel<M, false, 0><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \

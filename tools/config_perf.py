@@ -23,6 +23,8 @@ def run(name, metric, n, dim, rank, M, efc, k, efs, nq=10000, rate=None, normali
     if rate: ix.set_distribution_rate(rate)
     t = time.time(); ix.add(data); tb = time.time() - t
     print(json.dumps({"cfg": name, "n": n, "dim": dim, "build_s": round(tb, 2), "inserts_per_s": round(n / tb), "build_kernel_ms": round(ix.stats()["last_build_ms"])}), flush=True)
+    for kv in sys.argv[2:]:
+        kk, vv = kv.split("="); ix.set_tuning(kk, int(vv))
     t = time.time(); gt, _ = ix.exact_knn(q[:1000], k); te = time.time() - t
     for ef in efs:
         ix.set_min_nn(ef); ix.enable_stats(True)
