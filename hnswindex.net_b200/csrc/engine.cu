@@ -98,7 +98,7 @@ Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), par
 Index::~Index() {
     cudaSetDevice(device_);
     cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
-    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
+    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_); cudaFree(d_gvis_search_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -109,6 +109,7 @@ void Index::set_tuning(const std::string& key, int value) {
     if (key == "vis_size_search") tuning_.vis_size_search = value;
     else if (key == "vis_size_build") tuning_.vis_size_build = value;
     else if (key == "vis_global_build") tuning_.vis_global_build = value;
+    else if (key == "vis_global_search") tuning_.vis_global_search = value;
     else if (key == "blocks_per_sm") tuning_.blocks_per_sm = value;
     else if (key == "flags") tuning_.flags = value;
     else if (key == "zero_copy") zero_copy_ = value != 0;
@@ -196,6 +197,18 @@ void Index::ensure_stats(int count) {
         HNSW_CUDA_CHECK(cudaMalloc(&d_stats_, (size_t)count * sizeof(QueryStats)));
         stats_cap_ = count;
     }
+}
+
+// Room for the per-warp exact visited sets of long-row searches: 16 warps per SM x min(vis_global_search, 64 ef) slots.
+void Index::ensure_search_gvis(int ef) {
+    if (pitch_ <= 128 || tuning_.vis_global_search <= 0 || ef > 1024) return;
+    int slots = 1024;
+    while (slots < tuning_.vis_global_search && slots < 64 * ef) slots <<= 1;
+    const size_t words = (size_t)device_sm_count() * 16 * slots;
+    if (words <= gvis_search_words_) return;
+    cudaFree(d_gvis_search_); d_gvis_search_ = nullptr; gvis_search_words_ = 0;
+    HNSW_CUDA_CHECK(cudaMalloc(&d_gvis_search_, words * sizeof(uint32_t)));
+    gvis_search_words_ = words;
 }
 
 void Index::set_stream(cudaStream_t s) {
@@ -533,8 +546,9 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
         q_src = d_q_;
     }
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    ensure_search_gvis(ef);
     launch_knn_search((int)metric_, view(), q_src, count, k, ef, layer, direct_out ? ids_dst : d_ids_, direct_out ? d_dst : d_dists_, d_counters_ + 3,
-                      collect_stats_ ? d_stats_ : nullptr, tuning_, stream_);
+                      collect_stats_ ? d_stats_ : nullptr, d_gvis_search_, gvis_search_words_, tuning_, stream_);
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     stats_.search_launches += 1;
     if (!direct_out) {
@@ -557,8 +571,9 @@ void Index::knn_query_device(const float* d_queries, int count, int dim, int k, 
     if (collect_stats_) ensure_stats(count);
     const int ef = std::max(params_.MinNN, k);
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-    launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr, tuning_,
-                      stream_);
+    ensure_search_gvis(ef);
+    launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr,
+                      d_gvis_search_, gvis_search_words_, tuning_, stream_);
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     stats_.search_launches += 1;
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));

@@ -111,6 +111,7 @@ private:
     void upload_graph(const HostGraph& g);
     GraphView view() const;
     void fetch_query_stats(int count);
+    void ensure_search_gvis(int ef);
     void active_add(int id);
     void active_remove(int id);
     void remove_chunk(const int* ids, int n);
@@ -153,6 +154,8 @@ private:
     u64* d_build_prof_ = nullptr;     // [16]
     uint32_t* d_gvis_ = nullptr;      // per-warp visited sets of the build search (allocated by the first add)
     size_t gvis_words_ = 0;
+    uint32_t* d_gvis_search_ = nullptr;  // per-warp visited sets of long-row searches
+    size_t gvis_search_words_ = 0;
 
     float* d_q_ = nullptr;
     int* d_ids_ = nullptr;

@@ -12,6 +12,8 @@ struct Tuning {
     int vis_size_build = 0;
     int vis_global_build = 0;     // slots per warp of an exact global-memory visited set for the build search (0 = off;
                                   // -23 % evaluations but one more L2 round trip per expansion: no net gain at 1M x 128)
+    int vis_global_search = 0;  // slots per warp of an exact global visited set for long-row (dim > 128) searches (0 = off:
+                                // at C3 it removes 8.7 % of the evaluations, but its L2 round trip per expansion costs as much)
     int blocks_per_sm = 0;    // 0 = occupancy query
     int flags = 2;            // bit 0: L2-prefetch rows of accepted candidates (no gain); bit 1: guess-row load
 };
@@ -26,8 +28,10 @@ int device_sm_count();
 // K2: batched KnnQuery (HNSWIndex.cs:107-137).  queries: device [nq][dim] dense fp32;
 // out_ids/out_dists: device [nq][k], rows ascending, padded with -1 / NaN.
 // `layer`: the layer searched (HNSWIndex.cs:107 `layer` argument; 0 = base layer), descent stops above it.
+// d_gvis / gvis_words: optional room for per-warp exact visited sets (used by long-row searches, see search_kernels.cu)
 void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
-                       unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream);
+                       unsigned* d_work_counter, QueryStats* d_stats, uint32_t* d_gvis, size_t gvis_words, const Tuning& t,
+                       cudaStream_t stream);
 
 // MultiLayerKnnQuery (HNSWIndex.cs:173-187): out_* are [nq][top_l + 1][k], rows of layers below min_layer all padding,
 // each row the layer's sorted result without its first entry.

@@ -23,11 +23,13 @@ namespace hnsw {
 template <int METRIC, bool ANY_LAYER, int SPEC>
 __global__ void __launch_bounds__(kThreads, 5)
 knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int layer, int vis_size, int cand_cap, int flags,
-                  int* __restrict__ out_ids, float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats) {
+                  int* __restrict__ out_ids, float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats, uint32_t* gvis,
+                  int gvis_slots) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis_size, cand_cap);
     WarpScratch s = carve_scratch(smem + warp * per_warp, g.pitch, ef, vis_size, cand_cap, lane);
+    if (SPEC & kSpecGvis) gvis_attach(s, gvis + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * gvis_slots, gvis_slots);
 
     for (;;) {
         unsigned qi = 0;
@@ -183,7 +185,8 @@ static int configure_persistent(Kern kern, size_t smem_per_warp, const Tuning& t
 }
 
 void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
-                       unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream) {
+                       unsigned* d_work_counter, QueryStats* d_stats, uint32_t* d_gvis, size_t gvis_words, const Tuning& t,
+                       cudaStream_t stream) {
     if (nq <= 0) return;
     const int vis = pick_vis_size(t.vis_size_search, ef);
     // 16-bit tags hold two entries per word: for the mid-size lists the same filter fits half the words (more warps per SM)
@@ -199,27 +202,41 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
             constexpr int S = kSpecShortRows | kSpecSmallList | kSpecVis16;                                                     \
             const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
-                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
+                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);                  \
         } else if (layer == 0 && g.pitch <= kSegFloats && ef <= 1024 && (long long)g.count <= ((long long)vis_mid << 16)) {     \
             constexpr int S = kSpecShortRows | kSpecMidList | kSpecVis16;                                                       \
             const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);                 \
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                                \
-                g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);              \
+                g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);              \
         } else if (layer == 0 && g.pitch > kSegFloats && ef <= 1024 && (long long)g.count <= ((long long)vis << 16)) {          \
             /* long rows are DRAM-bound and every re-evaluation is real traffic (C3: 440 GB read for 393 GB of algorithmic     \
-               bytes): same words, twice the entries */                                                                        \
+               bytes): 16-bit tags (same words, twice the entries) and, when the engine provides room, an exact per-warp set    \
+               in global memory behind them -- one 8-byte L2 access per candidate against 4 x dim bytes per evaluation */      \
             constexpr int S = kSpecMidList | kSpecVis16;                                                                        \
-            const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
-            knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
-                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
+            int grid = configure_persistent(knn_search_kernel<M, false, S | kSpecGvis>, per_warp, t, nq, warps);               \
+            int gslots = 0;                                                                                                     \
+            if (d_gvis != nullptr && t.vis_global_search > 0) {                                                                 \
+                gslots = 1024;                                                                                                  \
+                while (gslots < t.vis_global_search && gslots < 64 * ef) gslots <<= 1;                                          \
+                while (gslots >= 1024 && (size_t)gslots * grid * warps > gvis_words) gslots >>= 1;                              \
+                if (gslots < 1024) gslots = 0;                                                                                  \
+            }                                                                                                                   \
+            if (gslots > 0) {                                                                                                   \
+                knn_search_kernel<M, false, S | kSpecGvis><<<grid, 32 * warps, per_warp * warps, stream>>>(                    \
+                    g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, d_gvis, gslots); \
+            } else {                                                                                                            \
+                grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                           \
+                knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                \
+                    g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);  \
+            }                                                                                                                   \
         } else if (layer == 0) {                                                                                                \
             const int grid = configure_persistent(knn_search_kernel<M, false, 0>, per_warp, t, nq, warps);                     \
             knn_search_kernel<M, false, 0><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
-                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);                  \
+                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);                  \
         } else {                                                                                                                \
             const int grid = configure_persistent(knn_search_kernel<M, true, 0>, per_warp, t, nq, warps);                      \
             knn_search_kernel<M, true, 0><<<grid, 32 * warps, per_warp * warps, stream>>>(                                     \
-                g, d_queries, nq, k, ef, layer, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats);              \
+                g, d_queries, nq, k, ef, layer, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);              \
         }                                                                                                                       \
     }
     switch (metric) {
