@@ -246,6 +246,19 @@ int hnsw_knn_query_device(hnsw_handle handle, const float* dQueries, int count, 
     return 0;
     HNSW_CATCH(-1)
 }
+int hnsw_knn_query_device_async(hnsw_handle handle, const float* dQueries, int count, int dim, int k, int* dOutIds, float* dOutDists) {
+    HNSW_TRY
+    if (count > 0 && (dQueries == nullptr || dOutIds == nullptr || dOutDists == nullptr)) throw std::invalid_argument("null buffer");
+    get(handle)->knn_query_device_async(dQueries, count, dim, k, dOutIds, dOutDists);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_synchronize(hnsw_handle handle) {
+    HNSW_TRY
+    get(handle)->synchronize();
+    return 0;
+    HNSW_CATCH(-1)
+}
 int hnsw_set_stream(hnsw_handle handle, void* cudaStream) {
     HNSW_TRY
     get(handle)->set_stream(reinterpret_cast<cudaStream_t>(cudaStream));
@@ -322,7 +335,21 @@ int hnsw_wait_and_merge_device(hnsw_handle handle, const unsigned* dFlags, int w
                                int count, int k, int* dOutIds, float* dOutDists) {
     HNSW_TRY
     if (world < 1 || k < 1) throw std::invalid_argument("world and k must be positive");
-    get(handle)->wait_and_merge(dFlags, world, epoch, dInIds, dInDists, count, k, dOutIds, dOutDists);
+    get(handle)->wait_and_merge(dFlags, world, epoch, dInIds, dInDists, count, k, dOutIds, dOutDists, true);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_wait_and_merge_device_async(hnsw_handle handle, const unsigned* dFlags, int world, unsigned epoch, const int* dInIds,
+                                     const float* dInDists, int count, int k, int* dOutIds, float* dOutDists) {
+    HNSW_TRY
+    if (world < 1 || k < 1) throw std::invalid_argument("world and k must be positive");
+    get(handle)->wait_and_merge(dFlags, world, epoch, dInIds, dInDists, count, k, dOutIds, dOutDists, false);
+    return 0;
+    HNSW_CATCH(-1)
+}
+int hnsw_partition_sync(hnsw_handle handle) {
+    HNSW_TRY
+    get(handle)->partition_sync();
     return 0;
     HNSW_CATCH(-1)
 }

@@ -605,6 +605,26 @@ int Index::multilayer_knn_query(const float* queries, int count, int dim, int k,
     return layers;
 }
 
+// Stream-ordered variant: the search is only queued (no host synchronisation, no event timing); synchronize() waits.
+void Index::knn_query_device_async(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (count <= 0 || k < 1) return;
+    if (this->count() <= 0) throw std::runtime_error("knn_query_device_async on an empty index");
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    const int ef = std::max(params_.MinNN, k);
+    ensure_search_gvis(ef);
+    launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, nullptr, d_gvis_search_,
+                      gvis_search_words_, tuning_, stream_);
+    stats_.search_launches += 1;
+}
+
+void Index::synchronize() {
+    std::lock_guard<std::mutex> lock(mu_);
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
 void Index::knn_query_scatter(const float* d_queries, int count, int dim, int k, const ScatterArgs& sc) {
     std::lock_guard<std::mutex> lock(mu_);
     if (count <= 0 || k < 1) return;
@@ -617,16 +637,26 @@ void Index::knn_query_scatter(const float* d_queries, int count, int dim, int k,
 }
 
 void Index::wait_and_merge(const unsigned* d_flags, int world, unsigned epoch, const int* d_in_ids, const float* d_in_dists, int count, int k,
-                           int* d_out_ids, float* d_out_dists) {
+                           int* d_out_ids, float* d_out_dists, bool sync) {
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        HNSW_CUDA_CHECK(cudaSetDevice(device_));
+        int* d_err = reinterpret_cast<int*>(d_counters_ + 7);
+        launch_wait_flags(d_flags, world, epoch, d_err, stream_);
+        launch_merge_topk(d_in_ids, d_in_dists, world, count, k, d_out_ids, d_out_dists, stream_);
+        stats_.search_launches += 2;
+    }
+    if (sync) partition_sync();
+}
+
+// Wait for everything queued by knn_query_scatter / wait_and_merge and report a peer that never delivered.
+void Index::partition_sync() {
     std::lock_guard<std::mutex> lock(mu_);
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     int* d_err = reinterpret_cast<int*>(d_counters_ + 7);
-    launch_wait_flags(d_flags, world, epoch, d_err, stream_);
-    launch_merge_topk(d_in_ids, d_in_dists, world, count, k, d_out_ids, d_out_dists, stream_);
     int err = 0;
     HNSW_CUDA_CHECK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    stats_.search_launches += 2;
     if (err != 0) {
         HNSW_CUDA_CHECK(cudaMemset(d_err, 0, sizeof(int)));
         throw std::runtime_error("partitioned query: a peer GPU did not deliver its results in time");

@@ -68,11 +68,15 @@ public:
     int entry_point() const { return entry_; }
     // queries / outputs already resident in device memory of this index's GPU
     void knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists);
+    // the same, only queued on the index's stream (several batches back to back); synchronize() waits for them
+    void knn_query_device_async(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists);
+    void synchronize();
     // partitioned index: stream-ordered search + scatter of the local top-k to all peers (no synchronisation), and the
     // matching wait-for-peers + merge of this rank's gather buffer (synchronises; throws if a peer never arrives)
     void knn_query_scatter(const float* d_queries, int count, int dim, int k, const ScatterArgs& sc);
     void wait_and_merge(const unsigned* d_flags, int world, unsigned epoch, const int* d_in_ids, const float* d_in_dists, int count, int k,
-                        int* d_out_ids, float* d_out_dists);
+                        int* d_out_ids, float* d_out_dists, bool sync);
+    void partition_sync();
     void exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists);
     // BatchRangeQuery (HNSWIndex.cs:160-168): per query, (id, distance) ascending by distance
     void range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out);

@@ -66,6 +66,8 @@ def _load():
         "hnsw_set_device": (ct.c_int, [ct.c_int]),
         "hnsw_device_count": (ct.c_int, []),
         "hnsw_knn_query_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
+        "hnsw_knn_query_device_async": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
+        "hnsw_synchronize": (ct.c_int, [ct.c_void_p]),
         "hnsw_set_stream": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
         "hnsw_exact_knn": (ct.c_int, [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p]),
         "hnsw_merge_topk_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
@@ -79,6 +81,9 @@ def _load():
         "hnsw_ipc_close": (ct.c_int, [ct.c_void_p]),
         "hnsw_ipc_free": (ct.c_int, [ct.c_void_p]),
         "hnsw_knn_query_scatter": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p]),
+        "hnsw_partition_sync": (ct.c_int, [ct.c_void_p]),
+        "hnsw_wait_and_merge_device_async": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_uint, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int,
+                                                        ct.c_void_p, ct.c_void_p]),
         "hnsw_wait_and_merge_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_uint, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int,
                                                   ct.c_void_p, ct.c_void_p]),
         "hnsw_top_layer": (ct.c_int, [ct.c_void_p]),
@@ -356,6 +361,13 @@ class Index:
     def knn_query_device(self, q_ptr: int, n: int, k: int, ids_ptr: int, dists_ptr: int) -> None:
         """Queries / outputs already in this GPU's memory (raw device pointers, e.g. tensor.data_ptr())."""
         _check(lib.hnsw_knn_query_device(self._h, ct.c_void_p(q_ptr), int(n), self.dim, int(k), ct.c_void_p(ids_ptr), ct.c_void_p(dists_ptr)))
+
+    def knn_query_device_async(self, q_ptr: int, n: int, k: int, ids_ptr: int, dists_ptr: int) -> None:
+        """Queue a device-resident batch on the index's stream without waiting; synchronize() waits."""
+        _check(lib.hnsw_knn_query_device_async(self._h, ct.c_void_p(q_ptr), int(n), self.dim, int(k), ct.c_void_p(ids_ptr), ct.c_void_p(dists_ptr)))
+
+    def synchronize(self) -> None:
+        _check(lib.hnsw_synchronize(self._h))
 
     def set_stream(self, cuda_stream: int) -> None:
         _check(lib.hnsw_set_stream(self._h, ct.c_void_p(cuda_stream)))

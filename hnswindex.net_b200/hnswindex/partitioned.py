@@ -131,7 +131,21 @@ class PartitionedIndex:
         if w > 1:
             dist.barrier(group=self.group)          # every buffer is mapped before anybody writes into it
 
-    def _knn_query_fused(self, q_dev, nq: int, k: int):
+    def disable_fused(self) -> None:
+        """Unmap the peers' buffers and free this rank's (all ranks together: a barrier separates unmapping from freeing)."""
+        import torch.distributed as dist
+        from . import bindings as hb
+        f, self._fused = self._fused, None
+        if f is None:
+            return
+        for p, ptr in enumerate(f["base"]):
+            if p != self.rank:
+                hb.lib.hnsw_ipc_close(ptr)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        hb.lib.hnsw_ipc_free(f["own"])
+
+    def _knn_query_fused(self, q_dev, nq: int, k: int, sync: bool = True):
         import ctypes as ct
         from . import bindings as hb
         f = self._fused
@@ -150,16 +164,24 @@ class PartitionedIndex:
             sc.dists[p] = ct.cast(ct.c_void_p(f["base"][p] + d_off), ct.POINTER(ct.c_float))
             sc.flags[p] = ct.cast(ct.c_void_p(f["base"][p] + f["flags_off"]), ct.POINTER(ct.c_uint))
         hb._check(hb.lib.hnsw_knn_query_scatter(self.index._h, ct.c_void_p(q_dev.data_ptr()), nq, self.index.dim, k, ct.byref(sc)))
-        hb._check(hb.lib.hnsw_wait_and_merge_device(self.index._h, ct.c_void_p(f["own"] + f["flags_off"]), self.world, f["epoch"],
-                                                   ct.c_void_p(f["own"] + ids_off), ct.c_void_p(f["own"] + d_off), nq, k,
-                                                   ct.c_void_p(f["out_ids"].data_ptr()), ct.c_void_p(f["out_d"].data_ptr())))
+        fn = hb.lib.hnsw_wait_and_merge_device if sync else hb.lib.hnsw_wait_and_merge_device_async
+        hb._check(fn(self.index._h, ct.c_void_p(f["own"] + f["flags_off"]), self.world, f["epoch"],
+                     ct.c_void_p(f["own"] + ids_off), ct.c_void_p(f["own"] + d_off), nq, k,
+                     ct.c_void_p(f["out_ids"].data_ptr()), ct.c_void_p(f["out_d"].data_ptr())))
         return f["out_ids"][:nq], f["out_d"][:nq]
 
-    def knn_query_device(self, q_dev, k: int):
-        """Queries already on this GPU (torch tensor [nq, dim] fp32) -> merged (ids, dists) torch tensors on the GPU."""
+    def sync(self) -> None:
+        """Wait for the batches queued with knn_query_device(..., sync=False); raises if a peer never delivered."""
+        from . import bindings as hb
+        hb._check(hb.lib.hnsw_partition_sync(self.index._h))
+
+    def knn_query_device(self, q_dev, k: int, sync: bool = True):
+        """Queries already on this GPU (torch tensor [nq, dim] fp32) -> merged (ids, dists) torch tensors on the GPU.
+        sync=False (fused path only): the batch is only queued on the index's stream -- call sync() before reading the
+        result tensors, which the next batch overwrites."""
         nq = int(q_dev.shape[0])
         if self._fused is not None:
-            return self._knn_query_fused(q_dev, nq, k)
+            return self._knn_query_fused(q_dev, nq, k, sync)
         return self._knn_query_gather(q_dev, nq, k)
 
     def _knn_query_cuda(self, q: np.ndarray, k: int):

@@ -138,6 +138,10 @@ HNSW_API int hnsw_device_count(void);
 /* Same as hnsw_knn_query with queries/outputs already resident in the index's GPU memory
  * (dense [count][dim] fp32 -> [count][k]).  Synchronises before returning. */
 HNSW_API int hnsw_knn_query_device(hnsw_handle handle, const float* dQueries, int count, int dim, int k, int* dOutIds, float* dOutDists);
+/* Stream-ordered variant for serving loops: the batch is only queued on the index's stream (batches queued back to
+ * back keep the GPU busy across host jitter); hnsw_synchronize waits for everything queued so far. */
+HNSW_API int hnsw_knn_query_device_async(hnsw_handle handle, const float* dQueries, int count, int dim, int k, int* dOutIds, float* dOutDists);
+HNSW_API int hnsw_synchronize(hnsw_handle handle);
 /* Run the index's work on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream. */
 HNSW_API int hnsw_set_stream(hnsw_handle handle, void* cudaStream);
 
@@ -174,6 +178,11 @@ HNSW_API int hnsw_ipc_free(void* devPtr);
 HNSW_API int hnsw_knn_query_scatter(hnsw_handle handle, const float* dQueries, int count, int dim, int k, const hnsw_scatter* sc);
 HNSW_API int hnsw_wait_and_merge_device(hnsw_handle handle, const unsigned* dFlags, int world, unsigned epoch, const int* dInIds,
                                         const float* dInDists, int count, int k, int* dOutIds, float* dOutDists);
+/* The same without synchronising (several query batches can be queued back to back; results stay on the device), and
+ * the matching wait: hnsw_partition_sync returns -1 if a peer never delivered. */
+HNSW_API int hnsw_wait_and_merge_device_async(hnsw_handle handle, const unsigned* dFlags, int world, unsigned epoch, const int* dInIds,
+                                              const float* dInDists, int count, int k, int* dOutIds, float* dOutDists);
+HNSW_API int hnsw_partition_sync(hnsw_handle handle);
 
 /* Measurement hooks. */
 typedef struct hnsw_stats {

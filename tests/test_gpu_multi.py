@@ -115,6 +115,10 @@ def test_partitioned_fused_world1_matches_plain_query(hnswindex):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
     with pytest.raises(ValueError):
         pix.knn_query(data[:601], 7)
+    pix.disable_fused()
+    a = pix.knn_query(data[:50], 7)
+    b = ix.knn_query(data[:50], 7)
+    assert np.array_equal(a[0], b[0])
 
 
 def test_partitioned_fused_two_gpus_matches_all_gather_path(hnswindex):

@@ -49,6 +49,9 @@ def main():
     truth = np.argsort(-(queries[0][:200] @ data.T), axis=1)[:, :k]
     rec = np.mean([len(set(gathered[0][0][i]) & set(truth[i])) / k for i in range(200)])
     assert rec > 0.75, rec   # unstructured 64-d Gaussian data at ef = 64; search quality itself is covered by the parity tests
+    pix.disable_fused()
+    again = pix.knn_query(queries[1], k)      # back on the all-gather path
+    assert np.array_equal(again[0], gathered[1][0])
     t = torch.tensor([1.0], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
