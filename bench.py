@@ -669,7 +669,7 @@ def main():
     ap.add_argument("--mode", default="replicated", choices=["replicated", "partitioned", "build"],
                     help="partitioned = BASELINE config C4, build = C5 (secondary workloads, own metric names)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="replicated mode: c2 (the metric's config) or c3")
-    ap.add_argument("--build-sample", type=int, default=100_000, help="build mode: nodes the CPU oracle builds (bounded sample)")
+    ap.add_argument("--build-sample", type=int, default=400_000, help="build mode: nodes the CPU oracle builds (bounded sample, ~10-15 s on 16 cores)")
     ap.add_argument("--n-per-rank", type=int, default=1_250_000)
     args = ap.parse_args()
     if args.warmup < 3:
