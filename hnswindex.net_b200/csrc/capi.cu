@@ -253,6 +253,12 @@ int hnsw_knn_query_device_async(hnsw_handle handle, const float* dQueries, int c
     return 0;
     HNSW_CATCH(-1)
 }
+int hnsw_async_join(hnsw_handle handle) {
+    HNSW_TRY
+    get(handle)->async_join();
+    return 0;
+    HNSW_CATCH(-1)
+}
 int hnsw_synchronize(hnsw_handle handle) {
     HNSW_TRY
     get(handle)->synchronize();

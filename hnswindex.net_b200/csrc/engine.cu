@@ -86,8 +86,11 @@ Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), par
     stream_ = own_stream_;
     HNSW_CUDA_CHECK(cudaEventCreate(&ev0_));
     HNSW_CUDA_CHECK(cudaEventCreate(&ev1_));
-    HNSW_CUDA_CHECK(cudaMalloc(&d_counters_, 8 * sizeof(unsigned)));
-    HNSW_CUDA_CHECK(cudaMemset(d_counters_, 0, 8 * sizeof(unsigned)));
+    HNSW_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
+    HNSW_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    HNSW_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+    HNSW_CUDA_CHECK(cudaMalloc(&d_counters_, 16 * sizeof(unsigned)));
+    HNSW_CUDA_CHECK(cudaMemset(d_counters_, 0, 16 * sizeof(unsigned)));
     HNSW_CUDA_CHECK(cudaMalloc(&d_build_prof_, 16 * sizeof(u64)));
     HNSW_CUDA_CHECK(cudaMemset(d_build_prof_, 0, 16 * sizeof(u64)));
     stride0_ = stride_for(2 * params_.MaxEdges);
@@ -102,6 +105,9 @@ Index::~Index() {
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_join_) cudaEventDestroy(ev_join_);
+    if (aux_stream_) cudaStreamDestroy(aux_stream_);
     if (own_stream_) cudaStreamDestroy(own_stream_);
 }
 
@@ -115,6 +121,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "zero_copy") zero_copy_ = value != 0;
     else if (key == "build_batch_max") build_batch_max_ = std::max(1, value);
     else if (key == "build_batch_ratio") build_batch_ratio_ = std::max(1, value);
+    else if (key == "async_overlap") tuning_.async_overlap = value;
     else if (key == "remove_batch_max") remove_batch_max_ = std::max(1, value);
     else if (key == "remove_batch_ratio") remove_batch_ratio_ = std::max(1, value);
     else throw std::invalid_argument("unknown tuning key: " + key);
@@ -213,6 +220,7 @@ void Index::ensure_search_gvis(int ef) {
 
 void Index::set_stream(cudaStream_t s) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
     stream_ = s ? s : own_stream_;
 }
@@ -223,6 +231,7 @@ void Index::set_stream(cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
     std::vector<int> lv, ids_new, src_row;
@@ -473,6 +482,7 @@ void Index::remove_chunk(const int* ids, int n) {
 
 void Index::remove(const int* ids, int count) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (!params_.AllowRemovals) throw std::runtime_error("Removals are disabled in this index instance.");  // HNSWIndex.cs:85-86
     if (count <= 0) return;
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
@@ -525,6 +535,7 @@ static T* pinned_alias(const T* host) {
 
 void Index::knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists, int layer) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) {  // HNSWIndex.cs:109
         fill_empty(out_ids, out_dists, (size_t)count * k);
@@ -564,6 +575,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
 
 void Index::knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) throw std::runtime_error("knn_query_device on an empty index");
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
@@ -587,6 +599,7 @@ void Index::knn_query_device(const float* d_queries, int count, int dim, int k, 
 // outputs are [count][L][k] (pass null pointers to query L only).
 int Index::multilayer_knn_query(const float* queries, int count, int dim, int k, int max_layer, int min_layer, int* out_ids, float* out_dists) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (this->count() <= 0 || k < 1) return 0;  // HNSWIndex.cs:176
     if (max_layer < 0) throw std::out_of_range("maxLayer must not be negative");
     const int top_l = std::min(top_, max_layer);
@@ -606,6 +619,9 @@ int Index::multilayer_knn_query(const float* queries, int count, int dim, int k,
 }
 
 // Stream-ordered variant: the search is only queued (no host synchronisation, no event timing); synchronize() waits.
+// Odd-numbered batches go to the auxiliary stream (which first waits for everything queued on the primary one when it
+// is picked up again after a join), so two consecutive batches overlap: the blocks of the later one fill the SM slots
+// that the persistent blocks of the earlier one give up in its tail.
 void Index::knn_query_device_async(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists) {
     std::lock_guard<std::mutex> lock(mu_);
     if (count <= 0 || k < 1) return;
@@ -613,20 +629,53 @@ void Index::knn_query_device_async(const float* d_queries, int count, int dim, i
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
     const int ef = std::max(params_.MinNN, k);
-    ensure_search_gvis(ef);
-    launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, nullptr, d_gvis_search_,
-                      gvis_search_words_, tuning_, stream_);
+    const bool overlap = tuning_.vis_global_search <= 0 && tuning_.async_overlap != 0;
+    if (overlap && !aux_dirty_) {  // first batch of a sequence: the auxiliary stream starts behind what the primary holds NOW
+        HNSW_CUDA_CHECK(cudaEventRecord(ev_fork_, stream_));
+        HNSW_CUDA_CHECK(cudaStreamWaitEvent(aux_stream_, ev_fork_, 0));
+        aux_dirty_ = true;
+        async_seq_ = 0;
+    }
+    const bool use_aux = overlap && (async_seq_++ & 1u) != 0;
+    if (!use_aux) {
+        ensure_search_gvis(ef);
+        launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, nullptr, d_gvis_search_,
+                          gvis_search_words_, tuning_, stream_);
+    } else {
+        launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 8, nullptr, nullptr, 0, tuning_,
+                          aux_stream_);
+    }
     stats_.search_launches += 1;
+}
+
+void Index::join_aux_locked(bool host_wait) {
+    if (!aux_dirty_) return;
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    if (host_wait) {
+        HNSW_CUDA_CHECK(cudaStreamSynchronize(aux_stream_));
+    } else {
+        HNSW_CUDA_CHECK(cudaEventRecord(ev_join_, aux_stream_));
+        HNSW_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join_, 0));
+    }
+    aux_dirty_ = false;
+}
+
+void Index::async_join() {
+    std::lock_guard<std::mutex> lock(mu_);
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    join_aux_locked(false);
 }
 
 void Index::synchronize() {
     std::lock_guard<std::mutex> lock(mu_);
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    join_aux_locked(true);
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
 void Index::knn_query_scatter(const float* d_queries, int count, int dim, int k, const ScatterArgs& sc) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) throw std::runtime_error("knn_query_scatter on an empty shard");
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
@@ -665,6 +714,7 @@ void Index::partition_sync() {
 
 void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) {
         fill_empty(out_ids, out_dists, (size_t)count * k);
@@ -699,6 +749,7 @@ void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_
 // ---------------------------------------------------------------------------------------------
 void Index::range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     out.assign((size_t)std::max(count, 0), {});
     if (count <= 0 || this->count() <= 0) return;  // HNSWIndex.cs:146
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
@@ -815,6 +866,7 @@ int median_like_reference(std::vector<int>& v) {  // HNSWInfo.cs:45-51
 
 std::vector<Index::LayerInfo> Index::get_info() {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     std::vector<LayerInfo> out;
     if (count() <= 0) return out;
     HostGraph g;
@@ -854,6 +906,7 @@ std::vector<Index::LayerInfo> Index::get_info() {
 
 std::vector<int> Index::connected_component_counts() {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     std::vector<int> counts;
     if (count() <= 0) return counts;
     HostGraph g;
@@ -886,6 +939,7 @@ std::vector<int> Index::connected_component_counts() {
 
 void Index::serialize(const std::string& path, bool packed) {
     std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HostGraph g;
     export_graph(g);
     write_snapshot(g, path, packed);

@@ -14,6 +14,7 @@ struct Tuning {
                                   // -23 % evaluations but one more L2 round trip per expansion: no net gain at 1M x 128)
     int vis_global_search = 0;  // slots per warp of an exact global visited set for long-row (dim > 128) searches (0 = off:
                                 // at C3 it removes 8.7 % of the evaluations, but its L2 round trip per expansion costs as much)
+    int async_overlap = 1;    // hnsw_knn_query_device_async alternates two streams (consecutive batches overlap in their tails)
     int blocks_per_sm = 0;    // 0 = occupancy query
     int flags = 2;            // bit 0: L2-prefetch rows of accepted candidates (no gain); bit 1: guess-row load
 };

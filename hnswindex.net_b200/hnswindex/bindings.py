@@ -68,6 +68,7 @@ def _load():
         "hnsw_knn_query_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
         "hnsw_knn_query_device_async": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
         "hnsw_synchronize": (ct.c_int, [ct.c_void_p]),
+        "hnsw_async_join": (ct.c_int, [ct.c_void_p]),
         "hnsw_set_stream": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
         "hnsw_exact_knn": (ct.c_int, [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p]),
         "hnsw_merge_topk_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
@@ -368,6 +369,10 @@ class Index:
 
     def synchronize(self) -> None:
         _check(lib.hnsw_synchronize(self._h))
+
+    def async_join(self) -> None:
+        """Stream-ordered: the index's stream waits for the batches queued on the auxiliary stream (no host wait)."""
+        _check(lib.hnsw_async_join(self._h))
 
     def set_stream(self, cuda_stream: int) -> None:
         _check(lib.hnsw_set_stream(self._h, ct.c_void_p(cuda_stream)))

@@ -138,10 +138,14 @@ HNSW_API int hnsw_device_count(void);
 /* Same as hnsw_knn_query with queries/outputs already resident in the index's GPU memory
  * (dense [count][dim] fp32 -> [count][k]).  Synchronises before returning. */
 HNSW_API int hnsw_knn_query_device(hnsw_handle handle, const float* dQueries, int count, int dim, int k, int* dOutIds, float* dOutDists);
-/* Stream-ordered variant for serving loops: the batch is only queued on the index's stream (batches queued back to
- * back keep the GPU busy across host jitter); hnsw_synchronize waits for everything queued so far. */
+/* Variant for serving loops: the batch is only queued (batches queued back to back keep the GPU busy across host
+ * jitter).  Consecutive batches alternate between the index's stream and an internal auxiliary stream so that they
+ * overlap in their tails: give them distinct output buffers.  hnsw_synchronize waits (on the host) for everything queued
+ * so far; hnsw_async_join only makes the index's stream wait for the auxiliary one (for callers that time or chain work
+ * on that stream).  Every other call on the handle waits for queued batches first. */
 HNSW_API int hnsw_knn_query_device_async(hnsw_handle handle, const float* dQueries, int count, int dim, int k, int* dOutIds, float* dOutDists);
 HNSW_API int hnsw_synchronize(hnsw_handle handle);
+HNSW_API int hnsw_async_join(hnsw_handle handle);
 /* Run the index's work on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream. */
 HNSW_API int hnsw_set_stream(hnsw_handle handle, void* cudaStream);
 

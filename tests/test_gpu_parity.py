@@ -639,3 +639,34 @@ def test_remove_and_layer_queries_on_tiny_indexes(hnswindex, oracle):
     assert ix.get_info() == [] and len(ix.connected_component_counts()) == 0
     assert sorted(ix.add(v).tolist()) == sorted(ref.add(v).tolist()) == [0, 1, 2]
     assert ix.count == 3
+
+
+def test_async_queued_batches_match_the_synchronous_call(hnswindex):
+    # hnsw_knn_query_device_async: batches queued back to back (alternating two streams) return what the blocking call returns
+    import torch
+    rng = np.random.default_rng(12)
+    data = rng.random((20000, 64), dtype=np.float32)
+    ix = hnswindex.Index(64, "sq_euclid")
+    ix.set_collection_size(20000); ix.set_allow_removals(False)
+    ix.add(data)
+    ix.set_min_nn(32)
+    qs = [torch.from_numpy(rng.random((700 + 50 * i, 64), dtype=np.float32)).cuda() for i in range(7)]
+    want = [ix.knn_query(q.cpu().numpy(), 10) for q in qs]
+    outs = [(torch.empty((q.shape[0], 10), dtype=torch.int32, device="cuda"), torch.empty((q.shape[0], 10), dtype=torch.float32, device="cuda")) for q in qs]
+    for rep in range(3):
+        for q, (oi, od) in zip(qs, outs):
+            ix.knn_query_device_async(q.data_ptr(), q.shape[0], 10, oi.data_ptr(), od.data_ptr())
+        if rep == 1:
+            ix.async_join()          # stream-ordered join, then more batches
+        else:
+            ix.synchronize()
+    ix.synchronize()
+    for (oi, od), (wi, wd) in zip(outs, want):
+        assert np.array_equal(oi.cpu().numpy(), wi) and np.array_equal(od.cpu().numpy().view(np.uint32), wd.view(np.uint32))
+    # a blocking call right after queued batches waits for them and still answers correctly
+    ix.knn_query_device_async(qs[0].data_ptr(), qs[0].shape[0], 10, outs[0][0].data_ptr(), outs[0][1].data_ptr())
+    ix.knn_query_device_async(qs[1].data_ptr(), qs[1].shape[0], 10, outs[1][0].data_ptr(), outs[1][1].data_ptr())
+    again = ix.knn_query(qs[2].cpu().numpy(), 10)
+    assert np.array_equal(again[0], want[2][0])
+    new_ids = ix.add(data[:5])       # and so does a mutation
+    assert ix.count == 20005 and len(new_ids) == 5
