@@ -239,8 +239,10 @@ static int gvis_slots_per_warp(const uint32_t* d_gvis, size_t gvis_words, size_t
 
 // d_work_counter: three consecutive words -- [0] select work, [1] link work, [2] error flag
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, const int* d_new_ids, int count, int efc, unsigned* d_work_counter,
-                        u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream) {
+                        u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream,
+                        cudaStream_t link_stream, cudaEvent_t select_done) {
     if (count <= 0) return;
+    if (link_stream == nullptr) link_stream = stream;
     const int maxE0 = 2 * g.max_edges;
     const int list_cap_sel = std::max(efc, 1);
     const int list_cap_link = maxE0 + 1;
@@ -255,7 +257,8 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
     const bool vis16 = (long long)g.count <= ((long long)vis << 16);
     const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap);   // per warp
     const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap);  // per warp
-    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, 2 * sizeof(unsigned), stream));
+    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
+    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter + 1, 0, sizeof(unsigned), link_stream));
     int* err = reinterpret_cast<int*>(d_work_counter + 2);
 #define HNSW_LAUNCH_BUILD(M)                                                                                                    \
     {                                                                                                                           \
@@ -271,9 +274,14 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
             build_select_kernel<M, 0><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                 \
                 g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
         }                                                                                                                       \
+        if (link_stream != stream) { /* the links of this batch follow its select kernel, on their own stream */             \
+            HNSW_CUDA_CHECK(cudaEventRecord(select_done, stream));                                                             \
+            HNSW_CUDA_CHECK(cudaStreamWaitEvent(link_stream, select_done, 0));                                                 \
+        }                                                                                                                       \
         const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, count, w2);                                         \
-        build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, stream>>>(g, d_levels, d_new_ids, count, list_cap_link, cand_cap,  \
-                                                                      sel_cap, d_work_counter + 1, err, d_build_prof);         \
+        build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, link_stream>>>(g, d_levels, d_new_ids, count, list_cap_link,      \
+                                                                           cand_cap, sel_cap, d_work_counter + 1, err,        \
+                                                                           d_build_prof);                                      \
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_BUILD(SQ_EUCLID) break;

@@ -122,6 +122,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "build_batch_max") build_batch_max_ = std::max(1, value);
     else if (key == "build_batch_ratio") build_batch_ratio_ = std::max(1, value);
     else if (key == "async_overlap") tuning_.async_overlap = value;
+    else if (key == "build_overlap") tuning_.build_overlap = value;
     else if (key == "remove_batch_max") remove_batch_max_ = std::max(1, value);
     else if (key == "remove_batch_ratio") remove_batch_ratio_ = std::max(1, value);
     else throw std::invalid_argument("unknown tuning key: " + key);
@@ -324,6 +325,7 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     }
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     int done = 0;
+    bool links_on_aux = false;
     int linked = this->count() - nnew;  // nodes a new node can reach (everything active before this call, then batch by batch)
     while (done < nnew) {
         const int v = ids_new[done];
@@ -341,8 +343,15 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
             while (done + batch < nnew && batch < b && levels_[ids_new[done + batch]] <= top_) ++batch;
         }
         // nodes of the same batch cannot reach each other: nothing points at them before the link kernel runs
+        const bool overlap = tuning_.build_overlap != 0 && batch >= 2048 && !new_top;
+        if (!overlap && links_on_aux) {  // small / top-raising batches run strictly after everything before them
+            HNSW_CUDA_CHECK(cudaEventRecord(ev_join_, aux_stream_));
+            HNSW_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join_, 0));
+            links_on_aux = false;
+        }
         launch_build_batch((int)metric_, view(), d_levels_, d_new_ids_ + done, batch, params_.MaxCandidates, d_counters_, d_build_prof_, d_gvis_,
-                           gvis_words_, tuning_, stream_);
+                           gvis_words_, tuning_, stream_, overlap ? aux_stream_ : stream_, ev_fork_);
+        links_on_aux = links_on_aux || overlap;
         stats_.build_launches += 2;
         if (new_top) {  // GraphConnector.cs:36-41
             entry_ = v;
@@ -350,6 +359,10 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
         }
         done += batch;
         linked += batch;
+    }
+    if (links_on_aux) {
+        HNSW_CUDA_CHECK(cudaEventRecord(ev_join_, aux_stream_));
+        HNSW_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join_, 0));
     }
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     int err = 0;

@@ -14,6 +14,9 @@ struct Tuning {
                                   // -23 % evaluations but one more L2 round trip per expansion: no net gain at 1M x 128)
     int vis_global_search = 0;  // slots per warp of an exact global visited set for long-row (dim > 128) searches (0 = off:
                                 // at C3 it removes 8.7 % of the evaluations, but its L2 round trip per expansion costs as much)
+    int build_overlap = 0;    // large insertion batches: run the link kernel on a second stream so that the next batch's select
+                              // kernel fills the SM slots freed in the tails.  Off: -4.5 % build time, but the next batch
+                              // then sees the previous batch's reverse links only partly and recall@10 drops 0.2 pt
     int async_overlap = 1;    // hnsw_knn_query_device_async alternates two streams (consecutive batches overlap in their tails)
     int blocks_per_sm = 0;    // 0 = occupancy query
     int flags = 2;            // bit 0: L2-prefetch rows of accepted candidates (no gain); bit 1: guess-row load
@@ -47,7 +50,8 @@ void launch_item_norms(const float* d_vectors, int pitch, int dim, int first, in
 // K6: reverse links with per-node locks and overflow pruning.
 // d_build_prof: 16 u64 cycle / work counters accumulated by the kernels (build_kernels.cu BuildProf).
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, const int* d_new_ids, int count, int ef_construction,
-                        unsigned* d_work_counter, u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream);
+                        unsigned* d_work_counter, u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream,
+                        cudaStream_t link_stream = nullptr, cudaEvent_t select_done = nullptr);
 
 // RangeQuery (HNSWIndex.cs:144-168): traversal of all in-range nodes reachable from the layer-0 entry.  Work item w handles
 // query qmap[w] (or w when qmap is null); out_keys [nwork][cap] unsorted (distance|id) keys, out_count[w] = result size or -1
