@@ -148,6 +148,35 @@ int hnsw_connected_components(hnsw_handle handle, int* counts, int maxLayers) {
     HNSW_CATCH(-1)
 }
 
+// BatchRangeQuery with ONE allocation per output: offsets[count + 1] (caller-owned) delimit the queries' slices of
+// *outIds / *outDists (malloc'ed here, released with hnsw_free_flat).
+int hnsw_range_query_flat(hnsw_handle handle, const float* vectors, int count, int dim, float range, long long* offsets, int** outIds,
+                          float** outDists) {
+    if (!handle) return 0;
+    HNSW_TRY
+    if (count > 0 && (vectors == nullptr || offsets == nullptr || outIds == nullptr || outDists == nullptr)) throw std::invalid_argument("null buffer");
+    *outIds = nullptr; *outDists = nullptr;
+    std::vector<std::vector<std::pair<float, int>>> res;
+    get(handle)->range_query(vectors, count, dim, range, res);
+    long long total = 0;
+    for (int i = 0; i < count; ++i) { offsets[i] = total; total += (long long)res[i].size(); }
+    if (count >= 0) offsets[std::max(count, 0)] = total;
+    int* ids = static_cast<int*>(std::malloc(sizeof(int) * (size_t)std::max<long long>(total, 1)));
+    float* dists = static_cast<float*>(std::malloc(sizeof(float) * (size_t)std::max<long long>(total, 1)));
+    if (!ids || !dists) { std::free(ids); std::free(dists); throw std::bad_alloc(); }
+    for (int i = 0; i < count; ++i) {
+        long long o = offsets[i];
+        for (const auto& pr : res[i]) { ids[o] = pr.second; dists[o] = pr.first; ++o; }
+    }
+    *outIds = ids; *outDists = dists;
+    return 0;
+    HNSW_CATCH(-1)
+}
+void hnsw_free_flat(int* ids, float* dists) {
+    std::free(ids);
+    std::free(dists);
+}
+
 int hnsw_range_query(hnsw_handle handle, const float* vectors, int count, int dim, float range, void** outIds, void** outDists, int* counts) {
     if (!handle) return 0;
     try {

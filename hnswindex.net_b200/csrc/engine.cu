@@ -101,7 +101,8 @@ Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), par
 Index::~Index() {
     cudaSetDevice(device_);
     cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
-    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_); cudaFree(d_gvis_search_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
+    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_); cudaFree(d_gvis_search_);
+    cudaFree(rq_keys_); cudaFree(rq_hash_); cudaFree(rq_small_); cudaFree(rq_dense_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -770,56 +771,74 @@ void Index::range_query(const float* queries, int count, int dim, float range, s
     ensure_query_scratch(count, 1);
     HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
 
+    // Device scratch is kept between calls (grow-only).  Per round: search -> counts to the host -> offsets -> the device
+    // sorts every result and packs it -> only the packed results travel back.  Queries whose result or visited table
+    // overflowed are searched again with 4x the room.
+    auto grow = [&](void*& p, size_t& have, size_t need) {
+        if (need <= have) return;
+        cudaFree(p); p = nullptr; have = 0;
+        HNSW_CUDA_CHECK(cudaMalloc(&p, need));
+        have = need;
+    };
     std::vector<int> todo(count);
     for (int i = 0; i < count; ++i) todo[i] = i;
     int cap = 1024;
     const int cap_max = std::max(1024, length_);
+    std::vector<int> cnt, flags, retry;
+    std::vector<long long> off;
+    std::vector<u64> dense;
     while (!todo.empty()) {
         cap = std::min(cap, cap_max);
         int hash_size = 4096;
         while (hash_size < 4 * cap) hash_size <<= 1;  // load factor <= 0.5 at 2*cap visited nodes
         const size_t per_q = (size_t)cap * 8 + (size_t)hash_size * 4 + 8;
         const int chunk = (int)std::max<size_t>(1, std::min<size_t>(todo.size(), ((size_t)768 << 20) / per_q));
-        u64* d_keys = nullptr;
-        uint32_t* d_hash = nullptr;
-        int *d_cnt = nullptr, *d_map = nullptr;
-        HNSW_CUDA_CHECK(cudaMalloc(&d_keys, (size_t)chunk * cap * 8));
-        HNSW_CUDA_CHECK(cudaMalloc(&d_hash, (size_t)chunk * hash_size * 4));
-        HNSW_CUDA_CHECK(cudaMalloc(&d_cnt, (size_t)chunk * 4));
-        HNSW_CUDA_CHECK(cudaMalloc(&d_map, (size_t)chunk * 4));
-        std::vector<int> retry;
-        try {
-            std::vector<int> cnt(chunk);
-            std::vector<u64> keys;
-            for (size_t c0 = 0; c0 < todo.size(); c0 += chunk) {
-                const int nw = (int)std::min<size_t>(chunk, todo.size() - c0);
-                HNSW_CUDA_CHECK(cudaMemcpyAsync(d_map, todo.data() + c0, (size_t)nw * 4, cudaMemcpyHostToDevice, stream_));
-                launch_range_search((int)metric_, view(), d_q_, d_map, nw, range, cap, hash_size, d_keys, d_hash, d_cnt, d_counters_ + 3, tuning_, stream_);
-                stats_.search_launches += 1;
-                HNSW_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nw * 4, cudaMemcpyDeviceToHost, stream_));
-                HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
-                int maxn = 0;
-                for (int w = 0; w < nw; ++w) maxn = std::max(maxn, cnt[w]);
-                keys.resize((size_t)nw * cap);
-                if (maxn > 0) {
-                    HNSW_CUDA_CHECK(cudaMemcpyAsync(keys.data(), d_keys, (size_t)nw * cap * 8, cudaMemcpyDeviceToHost, stream_));
-                    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
-                }
-                for (int w = 0; w < nw; ++w) {
-                    const int qi = todo[c0 + w];
-                    if (cnt[w] < 0) { retry.push_back(qi); continue; }
-                    u64* kq = keys.data() + (size_t)w * cap;
-                    std::sort(kq, kq + cnt[w]);  // ascending by (distance, id): OrderBy(c => c.Dist), HNSWIndex.cs:154
-                    auto& dst = out[qi];
-                    dst.resize(cnt[w]);
-                    for (int j = 0; j < cnt[w]; ++j) dst[j] = {key_dist(kq[j]), key_id(kq[j])};
-                }
+        grow(rq_keys_, rq_keys_bytes_, (size_t)chunk * cap * 8);
+        grow(rq_hash_, rq_hash_bytes_, (size_t)chunk * hash_size * 4);
+        const size_t off_at = ((size_t)chunk * 12 + 7) & ~(size_t)7;  // counts, map, flags (int each), then 8-byte offsets
+        grow(rq_small_, rq_small_bytes_, off_at + (size_t)chunk * 8);
+        int* d_cnt = static_cast<int*>(rq_small_);
+        int* d_map = d_cnt + chunk;
+        int* d_flag = d_map + chunk;
+        long long* d_off = reinterpret_cast<long long*>(static_cast<char*>(rq_small_) + off_at);
+        retry.clear();
+        for (size_t c0 = 0; c0 < todo.size(); c0 += chunk) {
+            const int nw = (int)std::min<size_t>(chunk, todo.size() - c0);
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_map, todo.data() + c0, (size_t)nw * 4, cudaMemcpyHostToDevice, stream_));
+            launch_range_search((int)metric_, view(), d_q_, d_map, nw, range, cap, hash_size, static_cast<u64*>(rq_keys_),
+                                static_cast<uint32_t*>(rq_hash_), d_cnt, d_counters_ + 3, tuning_, stream_);
+            stats_.search_launches += 1;
+            cnt.resize(nw);
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nw * 4, cudaMemcpyDeviceToHost, stream_));
+            HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            off.resize(nw);
+            long long total = 0;
+            for (int w = 0; w < nw; ++w) {
+                off[w] = total;
+                if (cnt[w] > 0) total += cnt[w];
             }
-        } catch (...) {
-            cudaFree(d_keys); cudaFree(d_hash); cudaFree(d_cnt); cudaFree(d_map);
-            throw;
+            if (total > 0) {
+                grow(rq_dense_, rq_dense_bytes_, (size_t)total * 8);
+                HNSW_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), (size_t)nw * 8, cudaMemcpyHostToDevice, stream_));
+                launch_range_finalize(static_cast<u64*>(rq_keys_), cap, d_cnt, d_off, nw, static_cast<u64*>(rq_dense_), d_flag, stream_);
+                stats_.search_launches += 1;
+                dense.resize((size_t)total);
+                flags.resize(nw);
+                HNSW_CUDA_CHECK(cudaMemcpyAsync(dense.data(), rq_dense_, (size_t)total * 8, cudaMemcpyDeviceToHost, stream_));
+                HNSW_CUDA_CHECK(cudaMemcpyAsync(flags.data(), d_flag, (size_t)nw * 4, cudaMemcpyDeviceToHost, stream_));
+                HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            }
+            for (int w = 0; w < nw; ++w) {
+                const int qi = todo[c0 + w];
+                if (cnt[w] < 0) { retry.push_back(qi); continue; }
+                if (cnt[w] == 0) continue;
+                u64* kq = dense.data() + off[w];
+                if (flags[w]) std::sort(kq, kq + cnt[w]);  // ascending by (distance, id): OrderBy(c => c.Dist), HNSWIndex.cs:154
+                auto& dst = out[qi];
+                dst.resize(cnt[w]);
+                for (int j = 0; j < cnt[w]; ++j) dst[j] = {key_dist(kq[j]), key_id(kq[j])};
+            }
         }
-        cudaFree(d_keys); cudaFree(d_hash); cudaFree(d_cnt); cudaFree(d_map);
         if (!retry.empty() && cap >= cap_max) throw std::runtime_error("range_query: result does not fit the index size (internal error)");
         todo.swap(retry);
         cap *= 4;

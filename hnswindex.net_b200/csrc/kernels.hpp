@@ -60,6 +60,11 @@ void launch_range_search(int metric, const GraphView& g, const float* d_queries,
                          int hash_size, u64* d_out_keys, uint32_t* d_hash, int* d_out_count, unsigned* d_work_counter, const Tuning& t,
                          cudaStream_t stream);
 
+// per query: sort the result keys ascending on the device and pack them at d_offsets[w] of d_dense (results larger
+// than 2048 keys are packed unsorted and flagged in d_unsorted_flag for the host)
+void launch_range_finalize(const u64* d_keys, int cap, const int* d_counts, const long long* d_offsets, int nwork, u64* d_dense,
+                           int* d_unsorted_flag, cudaStream_t stream);
+
 // K3: exact brute-force top-k (recall ground truth), same metric arithmetic.
 void launch_exact_knn(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists,
                       void* d_scratch, size_t scratch_bytes, cudaStream_t stream);

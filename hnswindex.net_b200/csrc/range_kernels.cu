@@ -107,6 +107,59 @@ range_search_kernel(GraphView g, const float* __restrict__ queries, const int* _
     }
 }
 
+// One warp per query: sorts the query's result keys ascending (bitonic sort in shared memory, up to kSortMax keys;
+// larger results are copied as they are and flagged for the host) and writes them to their place in the dense output.
+constexpr int kSortMax = 2048;
+__global__ void __launch_bounds__(kThreads)
+range_finalize_kernel(const u64* __restrict__ keys, int cap, const int* __restrict__ counts, const long long* __restrict__ offsets, int nwork,
+                      u64* __restrict__ dense, int* __restrict__ unsorted_flag) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u64* buf = reinterpret_cast<u64*>(smem) + (size_t)warp * kSortMax;
+    for (int w = blockIdx.x * kWarpsPerBlock + warp; w < nwork; w += gridDim.x * kWarpsPerBlock) {
+        const int n = counts[w];
+        if (n <= 0) continue;
+        const u64* src = keys + (size_t)w * cap;
+        u64* dst = dense + offsets[w];
+        if (n > kSortMax) {
+            for (int i = lane; i < n; i += 32) dst[i] = src[i];
+            if (lane == 0) unsorted_flag[w] = 1;
+            continue;
+        }
+        int p2 = 32;
+        while (p2 < n) p2 <<= 1;
+        for (int i = lane; i < p2; i += 32) buf[i] = i < n ? src[i] : ~0ull;
+        __syncwarp();
+        for (int size = 2; size <= p2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = lane; i < (p2 >> 1); i += 32) {
+                    const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
+                    const bool up = ((lo & size) == 0);
+                    const u64 a = buf[lo], b = buf[hi];
+                    if ((a > b) == up) { buf[lo] = b; buf[hi] = a; }
+                }
+                __syncwarp();
+            }
+        for (int i = lane; i < n; i += 32) dst[i] = buf[i];
+        __syncwarp();
+    }
+}
+
+void launch_range_finalize(const u64* d_keys, int cap, const int* d_counts, const long long* d_offsets, int nwork, u64* d_dense,
+                           int* d_unsorted_flag, cudaStream_t stream) {
+    if (nwork <= 0) return;
+    const size_t smem = (size_t)kWarpsPerBlock * kSortMax * sizeof(u64);
+    static bool configured = false;
+    if (!configured) {
+        HNSW_CUDA_CHECK(cudaFuncSetAttribute(range_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    HNSW_CUDA_CHECK(cudaMemsetAsync(d_unsorted_flag, 0, (size_t)nwork * sizeof(int), stream));
+    const int grid = std::max(1, std::min((nwork + kWarpsPerBlock - 1) / kWarpsPerBlock, 148 * 3));
+    range_finalize_kernel<<<grid, kThreads, smem, stream>>>(d_keys, cap, d_counts, d_offsets, nwork, d_dense, d_unsorted_flag);
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_range_search(int metric, const GraphView& g, const float* d_queries, const int* d_qmap, int nwork, float range, int cap,
                          int hash_size, u64* d_out_keys, uint32_t* d_hash, int* d_out_count, unsigned* d_work_counter, const Tuning& t,
                          cudaStream_t stream) {

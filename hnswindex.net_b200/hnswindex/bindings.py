@@ -77,6 +77,8 @@ def _load():
         "hnsw_knn_query_layer": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
         "hnsw_multilayer_knn_query": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]),
         "hnsw_ids": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
+        "hnsw_range_query_flat": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_float, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
+        "hnsw_free_flat": (None, [ct.c_void_p, ct.c_void_p]),
         "hnsw_ipc_alloc": (ct.c_int, [ct.c_size_t, ct.c_void_p, ct.c_void_p]),
         "hnsw_ipc_open": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
         "hnsw_ipc_close": (ct.c_int, [ct.c_void_p]),
@@ -241,23 +243,28 @@ class Index:
         return ids, dists
 
     def range_query(self, queries, radius: float) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+        """BatchRangeQuery (HNSWIndex.cs:160-168): per query the ids and distances within `radius`, ascending.  Uses the
+        flat variant of the export (one buffer per output) -- the per-query marshalling of the reference's binding
+        (bindings.py:523-597) would cost more than the search."""
         q = _rows_f32(queries, self.dim)
         n = int(q.shape[0])
-        ids_pp, dists_pp, counts = (ct.c_void_p * n)(), (ct.c_void_p * n)(), (ct.c_int * n)()
-        _check(lib.hnsw_range_query(self._h, _fp(q), n, self.dim, float(radius), ids_pp, dists_pp, counts))
-        ids, dists = [], []
+        if self._h is None or n == 0:
+            return [np.empty(0, dtype=np.int32) for _ in range(n)], [np.empty(0, dtype=np.float32) for _ in range(n)]
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        ids_p, dists_p = ct.POINTER(ct.c_int)(), ct.POINTER(ct.c_float)()
+        _check(lib.hnsw_range_query_flat(self._h, _fp(q), n, self.dim, float(radius), offsets.ctypes.data_as(ct.POINTER(ct.c_longlong)),
+                                         ct.byref(ids_p), ct.byref(dists_p)))
         try:
-            for i in range(n):
-                m = counts[i]
-                if m == 0:
-                    ids.append(np.empty(0, dtype=np.int32))
-                    dists.append(np.empty(0, dtype=np.float32))
-                    continue
-                ids.append(np.ctypeslib.as_array(ct.cast(ids_pp[i], ct.POINTER(ct.c_int)), shape=(m,)).copy())
-                dists.append(np.ctypeslib.as_array(ct.cast(dists_pp[i], ct.POINTER(ct.c_float)), shape=(m,)).copy())
+            total = int(offsets[n])
+            if total > 0:
+                ids_all = np.ctypeslib.as_array(ids_p, shape=(total,)).copy()
+                d_all = np.ctypeslib.as_array(dists_p, shape=(total,)).copy()
+            else:
+                ids_all, d_all = np.empty(0, dtype=np.int32), np.empty(0, dtype=np.float32)
         finally:
-            lib.hnsw_free_results(ids_pp, dists_pp, n)
-        return ids, dists
+            lib.hnsw_free_flat(ids_p, dists_p)
+        cut = offsets[1:-1]
+        return np.split(ids_all, cut), np.split(d_all, cut)
 
     # ---- what the C# class has and the reference's native shim lacks ------------------------------
     @property

@@ -76,6 +76,11 @@ HNSW_API int hnsw_range_query(hnsw_handle handle, const float* vectors, int coun
 
 /* HNSWIndexExports.cs:199-217. */
 HNSW_API void hnsw_free_results(void** idsArray, void** distsArray, int count);
+/* BatchRangeQuery with one allocation per output instead of two per query: offsets[count + 1] (caller-owned) delimit
+ * the queries' slices of *outIds / *outDists, each slice ascending by distance.  Release with hnsw_free_flat. */
+HNSW_API int hnsw_range_query_flat(hnsw_handle handle, const float* vectors, int count, int dim, float range, long long* offsets,
+                                   int** outIds, float** outDists);
+HNSW_API void hnsw_free_flat(int* ids, float* dists);
 
 /* HNSWIndexExports.cs:219-273: mutate the pending parameters used by the NEXT hnsw_create
  * (HNSWParameters.cs:13-55).  Return 0, or -1 on error. */

@@ -670,3 +670,32 @@ def test_async_queued_batches_match_the_synchronous_call(hnswindex):
     assert np.array_equal(again[0], want[2][0])
     new_ids = ix.add(data[:5])       # and so does a mutation
     assert ix.count == 20005 and len(new_ids) == 5
+
+
+def test_range_query_exports_agree(hnswindex):
+    # the reference's export (HNSWIndexExports.cs:151-217: two allocations per query, hnsw_free_results) and the flat
+    # variant the Python host uses return the same results, including empty and large (> 2048, host-sorted) ones
+    import ctypes as ct
+    rng = np.random.default_rng(21)
+    data = rng.random((6000, 8), dtype=np.float32)
+    ix = hnswindex.Index(8, "sq_euclid")
+    ix.add(data)
+    q = np.ascontiguousarray(rng.random((64, 8), dtype=np.float32))
+    for radius in (1e-4, 0.05, 0.4, 5.0):
+        f_ids, f_d = ix.range_query(q, radius)
+        n = len(q)
+        ids_pp, dists_pp, counts = (ct.c_void_p * n)(), (ct.c_void_p * n)(), (ct.c_int * n)()
+        rc = hnswindex.lib.hnsw_range_query(ix._h, q.ctypes.data_as(ct.POINTER(ct.c_float)), n, 8, ct.c_float(radius), ids_pp, dists_pp, counts)
+        assert rc == 0, hnswindex.last_error()
+        try:
+            for i in range(n):
+                m = counts[i]
+                assert m == len(f_ids[i])
+                if m:
+                    a = np.ctypeslib.as_array(ct.cast(ids_pp[i], ct.POINTER(ct.c_int)), shape=(m,))
+                    d = np.ctypeslib.as_array(ct.cast(dists_pp[i], ct.POINTER(ct.c_float)), shape=(m,))
+                    assert np.array_equal(a, f_ids[i]) and np.array_equal(d, f_d[i])
+                    assert (np.diff(d) >= 0).all() and (d <= radius).all()
+        finally:
+            hnswindex.lib.hnsw_free_results(ids_pp, dists_pp, n)
+    assert max(len(x) for x in ix.range_query(q, 5.0)[0]) == 6000     # everything is in range: > 2048 keys per query
