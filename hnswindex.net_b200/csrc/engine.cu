@@ -102,7 +102,8 @@ Index::~Index() {
     cudaSetDevice(device_);
     cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
     cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_); cudaFree(d_gvis_search_);
-    cudaFree(rq_keys_); cudaFree(rq_hash_); cudaFree(rq_small_); cudaFree(rq_dense_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
+    cudaFree(rq_keys_); cudaFree(rq_hash_); cudaFree(rq_small_); cudaFree(rq_dense_);
+    cudaFree(rm_small_); cudaFree(rm_aff_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -443,9 +444,15 @@ void Index::replace_entry_point(const std::vector<unsigned char>& in_chunk, int 
 }
 
 void Index::remove_chunk(const int* ids, int n) {
-    std::vector<unsigned char> in_chunk(length_, 0);
-    for (int i = 0; i < n; ++i) in_chunk[ids[i]] = 1;
-    if (in_chunk[entry_]) replace_entry_point(in_chunk, n);
+    // membership of the chunk: a byte map for large chunks, a linear scan for the one-id-per-call case
+    std::vector<unsigned char> in_chunk;
+    bool entry_in_chunk = false;
+    for (int i = 0; i < n && !entry_in_chunk; ++i) entry_in_chunk = ids[i] == entry_;
+    if (entry_in_chunk) {
+        in_chunk.assign(length_, 0);
+        for (int i = 0; i < n; ++i) in_chunk[ids[i]] = 1;
+        replace_entry_point(in_chunk, n);
+    }
 
     // work items: (node, layer) for every layer of every removed node, a node's items consecutive from layer 0
     std::vector<int> item_node, item_layer, item_first(n);
@@ -456,37 +463,37 @@ void Index::remove_chunk(const int* ids, int n) {
     const int nitems = (int)item_node.size();
     const int rmc = std::max(1, params_.RemoveMaxCandidates);
     const size_t max_rows = (size_t)length_ + (size_t)upper_rows_;
-    int *d_ids = nullptr, *d_item_node = nullptr, *d_item_layer = nullptr, *d_item_first = nullptr, *d_cand = nullptr;
-    int2* d_aff = nullptr;
-    auto free_all = [&]() { cudaFree(d_ids); cudaFree(d_item_node); cudaFree(d_item_layer); cudaFree(d_item_first); cudaFree(d_cand); cudaFree(d_aff); };
-    try {
-        HNSW_CUDA_CHECK(cudaMalloc(&d_ids, (size_t)n * 4));
-        HNSW_CUDA_CHECK(cudaMalloc(&d_item_node, (size_t)nitems * 4));
-        HNSW_CUDA_CHECK(cudaMalloc(&d_item_layer, (size_t)nitems * 4));
-        HNSW_CUDA_CHECK(cudaMalloc(&d_item_first, (size_t)n * 4));
-        HNSW_CUDA_CHECK(cudaMalloc(&d_cand, (size_t)nitems * rmc * 4));
-        HNSW_CUDA_CHECK(cudaMalloc(&d_aff, max_rows * sizeof(int2)));
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_ids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_node, item_node.data(), (size_t)nitems * 4, cudaMemcpyHostToDevice, stream_));
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_layer, item_layer.data(), (size_t)nitems * 4, cudaMemcpyHostToDevice, stream_));
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_first, item_first.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
-        launch_set_rm_index(d_rm_index_, d_ids, n, true, 0, stream_);
-        const GraphView g = view();
-        launch_remove_search((int)metric_, g, d_item_node, d_item_layer, nitems, rmc, d_cand, d_counters_ + 4, stream_);
-        launch_find_affected(g, d_levels_, length_, d_aff, d_counters_ + 5, stream_);
-        unsigned naff = 0;
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(&naff, d_counters_ + 5, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
-        HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
-        launch_relink((int)metric_, g, d_aff, (int)naff, d_item_first, d_cand, rmc, d_counters_ + 4, stream_);
-        launch_clear_rows(g, d_item_node, d_item_layer, nitems, stream_);
-        launch_set_rm_index(d_rm_index_, d_ids, n, false, -2, stream_);
-        HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
-        stats_.remove_launches += 6;
-    } catch (...) {
-        free_all();
-        throw;
-    }
-    free_all();
+    // device scratch, kept between calls (grow-only): ids | item_node | item_layer | item_first | cand, and the affected rows
+    auto grow = [&](void*& p, size_t& have, size_t need) {
+        if (need <= have) return;
+        cudaFree(p); p = nullptr; have = 0;
+        HNSW_CUDA_CHECK(cudaMalloc(&p, need + need / 2));
+        have = need + need / 2;
+    };
+    grow(rm_small_, rm_small_bytes_, ((size_t)n * 2 + (size_t)nitems * 2 + (size_t)nitems * rmc) * 4);
+    grow(rm_aff_, rm_aff_bytes_, max_rows * sizeof(int2));
+    int* d_ids = static_cast<int*>(rm_small_);
+    int* d_item_first = d_ids + n;
+    int* d_item_node = d_item_first + n;
+    int* d_item_layer = d_item_node + nitems;
+    int* d_cand = d_item_layer + nitems;
+    int2* d_aff = static_cast<int2*>(rm_aff_);
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_ids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_first, item_first.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_node, item_node.data(), (size_t)nitems * 4, cudaMemcpyHostToDevice, stream_));
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(d_item_layer, item_layer.data(), (size_t)nitems * 4, cudaMemcpyHostToDevice, stream_));
+    launch_set_rm_index(d_rm_index_, d_ids, n, true, 0, stream_);
+    const GraphView g = view();
+    launch_remove_search((int)metric_, g, d_item_node, d_item_layer, nitems, rmc, d_cand, d_counters_ + 4, stream_);
+    launch_find_affected(g, d_levels_, length_, d_aff, d_counters_ + 5, stream_);
+    unsigned naff = 0;
+    HNSW_CUDA_CHECK(cudaMemcpyAsync(&naff, d_counters_ + 5, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    launch_relink((int)metric_, g, d_aff, (int)naff, d_item_first, d_cand, rmc, d_counters_ + 4, stream_);
+    launch_clear_rows(g, d_item_node, d_item_layer, nitems, stream_);
+    launch_set_rm_index(d_rm_index_, d_ids, n, false, -2, stream_);
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    stats_.remove_launches += 6;
     for (int i = 0; i < n; ++i) {  // GraphData.RemoveItem, GraphData.cs:124-128
         removed_[ids[i]] = 1;
         removed_stack_.push_back(ids[i]);
@@ -501,13 +508,13 @@ void Index::remove(const int* ids, int count) {
     if (count <= 0) return;
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     {
-        std::vector<unsigned char> seen(length_, 0);
+        std::vector<int> sorted(ids, ids + count);
+        std::sort(sorted.begin(), sorted.end());
         for (int i = 0; i < count; ++i) {
-            const int id = ids[i];
+            const int id = sorted[i];
             if (id < 0 || id >= length_) throw std::out_of_range("remove: item index " + std::to_string(id) + " is out of range");
             if (removed_[id]) throw std::invalid_argument("remove: item " + std::to_string(id) + " has already been removed");
-            if (seen[id]) throw std::invalid_argument("remove: item " + std::to_string(id) + " is listed twice");
-            seen[id] = 1;
+            if (i > 0 && sorted[i - 1] == id) throw std::invalid_argument("remove: item " + std::to_string(id) + " is listed twice");
         }
     }
     int done = 0;

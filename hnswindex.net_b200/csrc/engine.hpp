@@ -161,6 +161,8 @@ private:
     u64* d_build_prof_ = nullptr;     // [16]
     uint32_t* d_gvis_ = nullptr;      // per-warp visited sets of the build search (allocated by the first add)
     size_t gvis_words_ = 0;
+    void *rm_small_ = nullptr, *rm_aff_ = nullptr;   // remove() scratch (grow-only)
+    size_t rm_small_bytes_ = 0, rm_aff_bytes_ = 0;
     // range_query scratch (grow-only): per-query key slices, visited tables, small arrays, packed results
     void *rq_keys_ = nullptr, *rq_hash_ = nullptr, *rq_small_ = nullptr, *rq_dense_ = nullptr;
     size_t rq_keys_bytes_ = 0, rq_hash_bytes_ = 0, rq_small_bytes_ = 0, rq_dense_bytes_ = 0;
