@@ -573,16 +573,40 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
     int* ids_dst = zero_copy_ ? pinned_alias(out_ids) : nullptr;
     float* d_dst = zero_copy_ ? pinned_alias(out_dists) : nullptr;
     const bool direct_out = ids_dst != nullptr && d_dst != nullptr;
-    if (!q_src) {
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
-        q_src = d_q_;
-    }
-    HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    int* ids_out = direct_out ? ids_dst : d_ids_;
+    float* d_out = direct_out ? d_dst : d_dists_;
     ensure_search_gvis(ef);
-    launch_knn_search((int)metric_, view(), q_src, count, k, ef, layer, direct_out ? ids_dst : d_ids_, direct_out ? d_dst : d_dists_, d_counters_ + 3,
-                      collect_stats_ ? d_stats_ : nullptr, d_gvis_search_, gvis_search_words_, tuning_, stream_);
+    // Pageable queries (what numpy hands over through the reference's own bindings.py) are staged by the driver, and the
+    // host thread is held while that happens: a large batch is therefore uploaded in four pieces, each piece's search
+    // launched as soon as it is on the device and alternating between the two streams, so the upload of piece i+1 runs
+    // under the search of piece i.
+    const int pieces = (!q_src && !collect_stats_ && layer == 0 && count >= 4096 && tuning_.async_overlap != 0 &&
+                        tuning_.vis_global_search <= 0) ? 4 : 1;
+    HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    if (pieces == 1) {
+        if (!q_src) {
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
+            q_src = d_q_;
+        }
+        launch_knn_search((int)metric_, view(), q_src, count, k, ef, layer, ids_out, d_out, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr,
+                          d_gvis_search_, gvis_search_words_, tuning_, stream_);
+        stats_.search_launches += 1;
+    } else {
+        HNSW_CUDA_CHECK(cudaEventRecord(ev_fork_, stream_));
+        HNSW_CUDA_CHECK(cudaStreamWaitEvent(aux_stream_, ev_fork_, 0));
+        const GraphView g = view();
+        for (int p = 0; p < pieces; ++p) {
+            const int q0 = (int)((long long)count * p / pieces), q1 = (int)((long long)count * (p + 1) / pieces);
+            cudaStream_t st = (p & 1) ? aux_stream_ : stream_;
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_ + (size_t)q0 * dim, queries + (size_t)q0 * dim, (size_t)(q1 - q0) * dim * 4, cudaMemcpyHostToDevice, st));
+            launch_knn_search((int)metric_, g, d_q_ + (size_t)q0 * dim, q1 - q0, k, ef, 0, ids_out + (size_t)q0 * k, d_out + (size_t)q0 * k,
+                              d_counters_ + ((p & 1) ? 8 : 3), nullptr, nullptr, 0, tuning_, st);
+            stats_.search_launches += 1;
+        }
+        HNSW_CUDA_CHECK(cudaEventRecord(ev_join_, aux_stream_));
+        HNSW_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join_, 0));
+    }
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
-    stats_.search_launches += 1;
     if (!direct_out) {
         HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
         HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists, d_dists_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
