@@ -18,6 +18,7 @@
 
 #include "build_scratch.cuh"
 #include "kernels.hpp"
+#include "launch.hpp"
 
 namespace hnsw {
 
@@ -212,21 +213,7 @@ static int pow2_ge(int v) {
 
 template <typename Kern>
 static int persistent_grid(Kern kern, size_t smem_per_warp, const Tuning& t, int work_items, int& warps) {
-    int dev = 0, max_optin = 0, sms = 0, per_sm = 0;
-    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
-    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    warps = kWarpsPerBlock;
-    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) --warps;  // as many independent warps as fit (4, 3, 2 or 1)
-    const size_t smem = smem_per_warp * warps;
-    if (smem > (size_t)max_optin)
-        throw std::runtime_error("MaxCandidates / MaxEdges too large for shared memory: need " + std::to_string(smem) + " B per warp");
-    HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem));
-    if (per_sm < 1) per_sm = 1;
-    if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);
-    const int need = (work_items + warps - 1) / warps;
-    return std::max(1, std::min(need, sms * per_sm));
+    return persistent_launch(kern, smem_per_warp, t.blocks_per_sm, work_items, warps);
 }
 
 // slots of the global visited set each warp of the select kernel gets (0 = not used)

@@ -19,6 +19,7 @@
 
 #include "build_scratch.cuh"
 #include "kernels.hpp"
+#include "launch.hpp"
 
 namespace hnsw {
 
@@ -185,19 +186,7 @@ static int pow2_ge(int v) {
 
 template <typename Kern>
 static int persistent_grid(Kern kern, size_t smem_per_warp, int work_items, int& warps) {
-    int dev = 0, max_optin = 0, sms = 0, per_sm = 0;
-    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
-    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    warps = kWarpsPerBlock;
-    while (warps > 1 && smem_per_warp * warps > (size_t)max_optin) --warps;  // as many independent warps as fit (4, 3, 2 or 1)
-    const size_t smem = smem_per_warp * warps;
-    if (smem > (size_t)max_optin) throw std::runtime_error("RemoveMaxCandidates / MaxEdges too large for shared memory");
-    HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int need = (work_items + warps - 1) / warps;
-    return std::max(1, std::min(need, sms * per_sm));
+    return persistent_launch(kern, smem_per_warp, 0, work_items, warps);
 }
 
 void launch_set_rm_index(int* d_rm_index, const int* d_ids, int n, bool use_index, int value, cudaStream_t stream) {

@@ -9,12 +9,11 @@
 #include <math_constants.h>
 
 #include <algorithm>
-#include <map>
 #include <mutex>
-#include <tuple>
 
 #include "beam.cuh"
 #include "kernels.hpp"
+#include "launch.hpp"
 
 namespace hnsw {
 
@@ -165,50 +164,9 @@ int pick_vis_size(int requested, int ef) {
 
 // Persistent launch shape: `warps` independent warps per block (4, fewer when one warp's scratch is large),
 // at most one resident wave of blocks.  Returns the grid size and sets `warps`.
-// The driver queries behind a launch shape (opt-in shared memory, occupancy) cost several microseconds each; they
-// depend only on (device, kernel, scratch per warp), so they are answered once and remembered.
-struct LaunchShape {
-    int warps, per_sm, sms;
-};
 template <typename Kern>
 static int configure_persistent(Kern kern, size_t smem_per_warp, const Tuning& t, int work_items, int& warps) {
-    static std::mutex mu;
-    static std::map<std::tuple<int, const void*, size_t>, LaunchShape> cache;
-    static std::map<std::pair<int, const void*>, size_t> optin;  // largest dynamic shared memory a kernel was opted in for
-    int dev = 0;
-    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
-    const auto key = std::make_tuple(dev, reinterpret_cast<const void*>(kern), smem_per_warp);
-    LaunchShape shape;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        auto it = cache.find(key);
-        if (it == cache.end()) {
-            int max_optin = 0;
-            HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-            shape.warps = kWarpsPerBlock;
-            while (shape.warps > 1 && smem_per_warp * shape.warps > (size_t)max_optin) --shape.warps;  // 4, 3, 2 or 1 warps per block
-            const size_t smem = smem_per_warp * shape.warps;
-            if (smem > (size_t)max_optin)
-                throw std::runtime_error("search width (max(MinNN, k)) too large for shared memory: need " + std::to_string(smem) +
-                                         " B per warp, have " + std::to_string(max_optin));
-            size_t& have = optin[std::make_pair(dev, reinterpret_cast<const void*>(kern))];
-            if (smem > have) {  // the attribute is per kernel, not per launch: only ever raise it
-                HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                have = smem;
-            }
-            shape.per_sm = 0;
-            HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shape.per_sm, kern, 32 * shape.warps, smem));
-            if (shape.per_sm < 1) shape.per_sm = 1;
-            shape.sms = device_sm_count();
-            it = cache.emplace(key, shape).first;
-        }
-        shape = it->second;
-    }
-    warps = shape.warps;
-    int per_sm = shape.per_sm;
-    if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);
-    const int need = (work_items + warps - 1) / warps;
-    return std::max(1, std::min(need, shape.sms * per_sm));
+    return persistent_launch(kern, smem_per_warp, t.blocks_per_sm, work_items, warps);
 }
 
 void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
