@@ -20,7 +20,7 @@ OBJ = HERE / "build"
 OUT_DIR = HERE / "hnswindex" / "artifacts" / "native" / "linux-x64"
 OUT = OUT_DIR / "HNSWIndex.Native.so"
 
-SOURCES = ["search_kernels.cu", "build_kernels.cu", "exact_kernels.cu", "range_kernels.cu", "remove_kernels.cu", "partition_kernels.cu", "engine.cu", "capi.cu", "snapshot.cpp"]
+SOURCES = ["search_kernels.cu", "build_kernels.cu", "exact_kernels.cu", "exact_tf32_kernels.cu", "range_kernels.cu", "remove_kernels.cu", "partition_kernels.cu", "engine.cu", "capi.cu", "snapshot.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo",

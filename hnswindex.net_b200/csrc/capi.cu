@@ -306,6 +306,13 @@ int hnsw_exact_knn(hnsw_handle handle, const float* queries, int count, int dim,
     return 0;
     HNSW_CATCH(-1)
 }
+int hnsw_exact_knn_tf32(hnsw_handle handle, const float* queries, int count, int dim, int k, int* outIds, float* outDists, int* outFallbacks) {
+    HNSW_TRY
+    const int fb = get(handle)->exact_knn_tf32(queries, count, dim, k, outIds, outDists);
+    if (outFallbacks) *outFallbacks = fb;
+    return 0;
+    HNSW_CATCH(-1)
+}
 int hnsw_merge_topk_device(const int* dInIds, const float* dInDists, int parts, int count, int k, int* dOutIds, float* dOutDists, void* cudaStream) {
     HNSW_TRY
     if (parts < 1 || k < 1) throw std::invalid_argument("parts and k must be positive");

@@ -767,7 +767,12 @@ void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_
     }
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
-    // bound the scratch: process the batch in slabs
+    exact_scan_locked(queries, count, k, out_ids, out_dists);
+}
+
+// K3 (exact_kernels.cu) over a host batch, in slabs that bound the scratch
+void Index::exact_scan_locked(const float* queries, int count, int k, int* out_ids, float* out_dists) {
+    const int dim = dim_;
     const int slab = std::max(8, std::min(count, (int)((size_t)(1u << 30) / ((size_t)32 * k * 8))));
     void* scratch = nullptr;
     const size_t sbytes = exact_knn_scratch_bytes(slab, k, length_);
@@ -787,6 +792,66 @@ void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_
         throw;
     }
     cudaFree(scratch);
+}
+
+// K3b: tensor-core filter + bit-exact re-ranking; uncertified queries go through K3.  Same answers as exact_knn.
+int Index::exact_knn_tf32(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
+    std::lock_guard<std::mutex> lock(mu_);
+    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
+    if (count <= 0 || k < 1) return 0;
+    if (this->count() <= 0) {
+        fill_empty(out_ids, out_dists, (size_t)count * k);
+        return 0;
+    }
+    HNSW_CUDA_CHECK(cudaSetDevice(device_));
+    ensure_dim(dim);
+    if (exact_tf32_block_queries(dim_, k) == 0) {  // very long rows / very large k: the FFMA scan answers everything
+        exact_scan_locked(queries, count, k, out_ids, out_dists);
+        return count;
+    }
+    const int kp = exact_tf32_candidates(k);
+    const int slab = std::max(64, std::min(count, (int)((size_t)(1u << 30) / ((size_t)33 * kp * 8))));
+    const size_t sbytes = exact_tf32_scratch_bytes(slab, k, length_);
+    void* scratch = nullptr;
+    int* d_fail = nullptr;
+    std::vector<int> fail, redo;
+    try {
+        HNSW_CUDA_CHECK(cudaMalloc(&scratch, sbytes));
+        HNSW_CUDA_CHECK(cudaMalloc(&d_fail, (size_t)slab * sizeof(int)));
+        for (int q0 = 0; q0 < count; q0 += slab) {
+            const int n = std::min(slab, count - q0);
+            ensure_query_scratch(n, k);
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries + (size_t)q0 * dim, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream_));
+            launch_exact_knn_tf32((int)metric_, view(), d_q_, n, k, d_ids_, d_dists_, d_fail, scratch, sbytes, q0 == 0, stream_);
+            stats_.search_launches += q0 == 0 ? 4 : 3;
+            fail.resize(n);
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids + (size_t)q0 * k, d_ids_, (size_t)n * k * 4, cudaMemcpyDeviceToHost, stream_));
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists + (size_t)q0 * k, d_dists_, (size_t)n * k * 4, cudaMemcpyDeviceToHost, stream_));
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(fail.data(), d_fail, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+            HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            for (int i = 0; i < n; ++i)
+                if (fail[i]) redo.push_back(q0 + i);
+        }
+    } catch (...) {
+        cudaFree(scratch);
+        cudaFree(d_fail);
+        throw;
+    }
+    cudaFree(scratch);
+    cudaFree(d_fail);
+    if (!redo.empty()) {
+        const size_t m = redo.size();
+        std::vector<float> rq(m * dim);
+        std::vector<int> rids(m * k);
+        std::vector<float> rd(m * k);
+        for (size_t i = 0; i < m; ++i) std::memcpy(rq.data() + i * dim, queries + (size_t)redo[i] * dim, (size_t)dim * 4);
+        exact_scan_locked(rq.data(), (int)m, k, rids.data(), rd.data());
+        for (size_t i = 0; i < m; ++i) {
+            std::memcpy(out_ids + (size_t)redo[i] * k, rids.data() + i * k, (size_t)k * 4);
+            std::memcpy(out_dists + (size_t)redo[i] * k, rd.data() + i * k, (size_t)k * 4);
+        }
+    }
+    return (int)redo.size();
 }
 
 // ---------------------------------------------------------------------------------------------

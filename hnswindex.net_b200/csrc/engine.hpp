@@ -81,6 +81,10 @@ public:
                         int* d_out_ids, float* d_out_dists, bool sync);
     void partition_sync();
     void exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists);
+    // the same answers through the 3xTF32 tensor-core filter + bit-exact re-ranking (exact_tf32_kernels.cu); returns the
+    // number of queries whose certificate failed and that were answered by the FFMA scan instead (all of them when
+    // dim / k do not fit the variant)
+    int exact_knn_tf32(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists);
     // BatchRangeQuery (HNSWIndex.cs:160-168): per query, (id, distance) ascending by distance
     void range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out);
     void serialize(const std::string& path, bool packed);
@@ -111,6 +115,7 @@ public:
 
 private:
     void ensure_dim(int dim);
+    void exact_scan_locked(const float* queries, int count, int k, int* out_ids, float* out_dists);
     void ensure_capacity(int needed);
     void ensure_upper_rows(int needed);
     void ensure_query_scratch(int count, int k);

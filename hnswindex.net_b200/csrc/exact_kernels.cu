@@ -232,6 +232,14 @@ void launch_exact_knn(int metric, const GraphView& g, const float* d_queries, in
     HNSW_CUDA_CHECK(cudaGetLastError());
 }
 
+void launch_merge_keys(const u64* d_part_keys, int parts, int nq, int k, int* d_out_ids, float* d_out_dists, cudaStream_t stream) {
+    if (nq <= 0) return;
+    const size_t msmem = (size_t)kWarpsPerBlock * k * 8;
+    HNSW_CUDA_CHECK(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    merge_keys_kernel<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, msmem, stream>>>(d_part_keys, parts, nq, k, d_out_ids, d_out_dists);
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_merge_topk(const int* d_in_ids, const float* d_in_dists, int parts, int nq, int k, int* d_out_ids, float* d_out_dists,
                        cudaStream_t stream) {
     if (nq <= 0) return;

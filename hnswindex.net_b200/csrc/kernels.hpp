@@ -70,6 +70,17 @@ void launch_exact_knn(int metric, const GraphView& g, const float* d_queries, in
                       void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t exact_knn_scratch_bytes(int nq, int k, int count);
 
+// K3b: the same answers through a 3xTF32 tensor-core GEMM filter + bit-exact re-ranking (exact_tf32_kernels.cu).
+// d_fail[q] = 1 where the certificate did not hold (the caller re-runs those queries with launch_exact_knn).
+// refresh_aux: recompute the per-item norms kept at the start of the scratch (needed after the index changed).
+int exact_tf32_candidates(int k);
+int exact_tf32_block_queries(int dim, int k);  // 64 / 32 / 16, or 0 when dim / k do not fit the variant
+size_t exact_tf32_scratch_bytes(int nq, int k, int count);
+void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists, int* d_fail,
+                           void* d_scratch, size_t scratch_bytes, bool refresh_aux, cudaStream_t stream);
+// per query: merge `parts` sorted key lists [nq][parts][k] (~0 padded) into ids / distances [nq][k] (-1 / NaN padded)
+void launch_merge_keys(const u64* d_part_keys, int parts, int nq, int k, int* d_out_ids, float* d_out_dists, cudaStream_t stream);
+
 // Remove (GraphConnector.cs:53-167) for one chunk of removed nodes, see remove_kernels.cu.
 //   rm_index[id] = position of id in the chunk (use_index) or `value`
 void launch_set_rm_index(int* d_rm_index, const int* d_ids, int n, bool use_index, int value, cudaStream_t stream);

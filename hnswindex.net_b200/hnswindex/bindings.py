@@ -71,6 +71,7 @@ def _load():
         "hnsw_async_join": (ct.c_int, [ct.c_void_p]),
         "hnsw_set_stream": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
         "hnsw_exact_knn": (ct.c_int, [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p]),
+        "hnsw_exact_knn_tf32": (ct.c_int, [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, i32p]),
         "hnsw_merge_topk_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
         "hnsw_enable_stats": (ct.c_int, [ct.c_void_p, ct.c_int]),
         "hnsw_get_stats": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
@@ -174,6 +175,7 @@ class Index:
         self.metric = metric
         self._initialized = False
         self._h = None
+        self.last_exact_fallbacks = 0
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -357,13 +359,22 @@ class Index:
         return out[:n]
 
     # ---- engine extras -------------------------------------------------------------------------------
-    def exact_knn(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
-        """Brute-force exact top-k on the GPU (recall ground truth)."""
+    def exact_knn(self, queries, k: int, tensor_cores: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+        """Brute-force exact top-k on the GPU (recall ground truth).
+
+        tensor_cores=True ranks all pairs with a 3xTF32 GEMM first and evaluates only k + slack candidates per
+        query with the exact metric; the answers are the same, `last_exact_fallbacks` tells how many queries could
+        not be certified and went through the plain scan."""
         q = _rows_f32(queries, self.dim)
         n = int(q.shape[0])
         ids = np.empty((n, k), dtype=np.int32)
         dists = np.empty((n, k), dtype=np.float32)
-        _check(lib.hnsw_exact_knn(self._h, _fp(q), n, self.dim, int(k), _ip(ids), _fp(dists)))
+        if tensor_cores:
+            fb = np.zeros(1, dtype=np.int32)
+            _check(lib.hnsw_exact_knn_tf32(self._h, _fp(q), n, self.dim, int(k), _ip(ids), _fp(dists), _ip(fb)))
+            self.last_exact_fallbacks = int(fb[0])
+        else:
+            _check(lib.hnsw_exact_knn(self._h, _fp(q), n, self.dim, int(k), _ip(ids), _fp(dists)))
         return ids, dists
 
     def knn_query_device(self, q_ptr: int, n: int, k: int, ids_ptr: int, dists_ptr: int) -> None:

@@ -157,6 +157,13 @@ HNSW_API int hnsw_set_stream(hnsw_handle handle, void* cudaStream);
 /* Exact brute-force top-k over the indexed vectors with the index's metric (recall ground truth). */
 HNSW_API int hnsw_exact_knn(hnsw_handle handle, const float* queries, int count, int dim, int k, int* outIds, float* outDists);
 
+/* The same answers (ids and distance bits) through the tensor cores: a 3xTF32 split-precision GEMM ranks all pairs
+ * approximately and keeps k + slack candidates per query, which are then evaluated with the metric's exact fp32
+ * arithmetic; a query whose k-th exact distance is not provably below everything outside its candidates is answered by
+ * the FFMA scan of hnsw_exact_knn instead.  *outFallbacks (may be null) = number of such queries. */
+HNSW_API int hnsw_exact_knn_tf32(hnsw_handle handle, const float* queries, int count, int dim, int k, int* outIds, float* outDists,
+                                 int* outFallbacks);
+
 /* Merge `parts` per-partition top-k results (device memory, [parts][count][k], rows ascending,
  * -1 padded) into [count][k] on the current device. */
 HNSW_API int hnsw_merge_topk_device(const int* dInIds, const float* dInDists, int parts, int count, int k, int* dOutIds, float* dOutDists,
