@@ -313,6 +313,11 @@ int hnsw_exact_knn_tf32(hnsw_handle handle, const float* queries, int count, int
     return 0;
     HNSW_CATCH(-1)
 }
+int hnsw_exact_tcgen05_supported(int dim, int k) {
+    HNSW_TRY
+    return exact_tcgen05_supported(dim, k) ? 1 : 0;
+    HNSW_CATCH(-1)
+}
 int hnsw_merge_topk_device(const int* dInIds, const float* dInDists, int parts, int count, int k, int* dOutIds, float* dOutDists, void* cudaStream) {
     HNSW_TRY
     if (parts < 1 || k < 1) throw std::invalid_argument("parts and k must be positive");

@@ -125,6 +125,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "build_batch_ratio") build_batch_ratio_ = std::max(1, value);
     else if (key == "async_overlap") tuning_.async_overlap = value;
     else if (key == "build_overlap") tuning_.build_overlap = value;
+    else if (key == "exact_tcgen05") tuning_.exact_tcgen05 = value;
     else if (key == "remove_batch_max") remove_batch_max_ = std::max(1, value);
     else if (key == "remove_batch_ratio") remove_batch_ratio_ = std::max(1, value);
     else throw std::invalid_argument("unknown tuning key: " + key);
@@ -822,7 +823,8 @@ int Index::exact_knn_tf32(const float* queries, int count, int dim, int k, int* 
             const int n = std::min(slab, count - q0);
             ensure_query_scratch(n, k);
             HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries + (size_t)q0 * dim, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream_));
-            launch_exact_knn_tf32((int)metric_, view(), d_q_, n, k, d_ids_, d_dists_, d_fail, scratch, sbytes, q0 == 0, stream_);
+            launch_exact_knn_tf32((int)metric_, view(), d_q_, n, k, d_ids_, d_dists_, d_fail, scratch, sbytes, q0 == 0, tuning_.exact_tcgen05 != 0,
+                                  stream_);
             stats_.search_launches += q0 == 0 ? 4 : 3;
             fail.resize(n);
             HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids + (size_t)q0 * k, d_ids_, (size_t)n * k * 4, cudaMemcpyDeviceToHost, stream_));

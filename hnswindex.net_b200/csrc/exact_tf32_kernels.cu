@@ -353,6 +353,232 @@ exact_tf32_rerank_kernel(GraphView g, const float* __restrict__ queries, int nq,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Pass A on the 5th-generation tensor cores (tcgen05 + TMEM), opt-in (tuning key "exact_tcgen05") for rows of at most
+// 128 floats.  One block = 128 queries = the 128 TMEM lanes of one accumulator D[128 x 64] (64 TMEM columns).  Both
+// operands are split into tf32 hi / lo parts when they are written to shared memory, in the K-major no-swizzle
+// canonical layout of a UMMA shared-memory descriptor: 8-row x 16-byte core matrices, 128 B each, consecutive along K
+// (leading byte offset 128), 8-row groups Kt * 32 bytes apart (stride byte offset).  Per tile of 64 stored vectors
+// one elected thread issues 3 x Kt / 8 `tcgen05.mma.cta_group::1.kind::tf32` (lo*hi, hi*lo, hi*hi per K-step of 8)
+// and commits them to an mbarrier; every thread then owns one query row: `tcgen05.ld.32x32b` brings its 64 dot products
+// to registers, and the few that beat the row's kp-th best are inserted into the row's sorted list by that thread
+// alone.  Same part_keys output as exact_tf32_scan_kernel, so merge, re-ranking and certificate are shared.
+// (Synchronous and single-buffered: the stage for the next tile is filled after the epilogue.  A TMA / multi-stage
+// pipeline only matters if brute force ever becomes a hot path.)
+namespace tc5 {
+
+constexpr int kM = 128;  // queries per block (UMMA M, TMEM lanes)
+constexpr int kN = 64;   // stored vectors per tile (UMMA N, TMEM columns)
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 [4,6) = 1, A / B = tf32 [7,10) / [10,13) = 2, both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), no swizzle: start address, leading / stride byte offsets
+// (all >> 4), version 1 at [46,48)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+           ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: never hang the device on a lost completion
+    }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// byte offset of the 16-byte piece (row r, floats 4 * k4 .. 4 * k4 + 3) in the canonical K-major layout
+__device__ __forceinline__ uint32_t piece_off(int r, int k4, int kt) { return (uint32_t)(r >> 3) * (uint32_t)(kt * 32) + (uint32_t)k4 * 128u + (uint32_t)(r & 7) * 16u; }
+__device__ __forceinline__ void store_split(unsigned char* hi_base, unsigned char* lo_base, uint32_t off, float4 v) {
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+    split_tf32(v.x, h0, l0);
+    split_tf32(v.y, h1, l1);
+    split_tf32(v.z, h2, l2);
+    split_tf32(v.w, h3, l3);
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h0, h1, h2, h3);
+    *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l0, l1, l2, l3);
+}
+
+}  // namespace tc5
+
+template <int METRIC>
+__global__ void __launch_bounds__(tc5::kM, 1)
+exact_tc5_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, int kp, int chunk_items, const float* __restrict__ xaux,
+                      u64* __restrict__ part_keys) {
+    using namespace tc5;
+    extern __shared__ __align__(16) unsigned char smem[];  // descriptors without swizzle need 16 B alignment only
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.x, chunks = gridDim.x;
+    const int q0 = blockIdx.y * kM;
+    const int kt = (g.dim + 15) & ~15;  // staged K extent, zero padded
+    const int pitchL = kp | 1;           // odd list pitch (in keys): rows of different threads spread over the banks
+
+    unsigned char* a_hi = smem;
+    unsigned char* a_lo = a_hi + (size_t)kM * kt * 4;
+    unsigned char* b_hi = a_lo + (size_t)kM * kt * 4;
+    unsigned char* b_lo = b_hi + (size_t)kN * kt * 4;
+    u64* lists = reinterpret_cast<u64*>(b_lo + (size_t)kN * kt * 4);  // [kM][pitchL]
+    float* xa_s = reinterpret_cast<float*>(lists + (size_t)kM * pitchL);  // [2][kN] per-item norms of the tile, by tile parity
+    u64* bar = reinterpret_cast<u64*>(xa_s + 2 * kN);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(bar);
+
+    // one warp tile = 8 rows x 4 pieces: coalesced 64 B runs in global memory, one conflict-free 512 B run in shared memory
+    const int rr = lane & 7, kk = lane >> 3;
+    const int kgroups = kt >> 4;
+    for (int wt = warp; wt < (kM / 8) * kgroups; wt += kM / 32) {
+        const int r = (wt / kgroups) * 8 + rr, k4 = (wt % kgroups) * 4 + kk;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + r < nq) {
+            const float* src = queries + (size_t)(q0 + r) * g.dim;
+            const int d = k4 * 4;
+            if (d < g.dim) v.x = __ldg(src + d);
+            if (d + 1 < g.dim) v.y = __ldg(src + d + 1);
+            if (d + 2 < g.dim) v.z = __ldg(src + d + 2);
+            if (d + 3 < g.dim) v.w = __ldg(src + d + 3);
+        }
+        store_split(a_hi, a_lo, piece_off(r, k4, kt), v);
+    }
+    float qa = 0.f;  // |q|^2 or 1/|q| of this thread's query row
+    if (q0 + tid < nq) {
+        const float* src = queries + (size_t)(q0 + tid) * g.dim;
+        float s = 0.f;
+        for (int d = 0; d < g.dim; ++d) { const float a = __ldg(src + d); s = fmaf(a, a, s); }
+        qa = metric_is_sq(METRIC) ? s : (METRIC == COSINE ? (s > 1e-36f ? rsqrtf(s) : 0.f) : 0.f);
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(kN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    u64* list = lists + (size_t)tid * pitchL;
+    int n = 0;
+    uint32_t thr = 0xFFFFFFFFu;
+    const int begin = chunk * chunk_items, end = min(g.count, begin + chunk_items);
+    const int ntiles = begin < end ? (end - begin + kN - 1) / kN : 0;
+    const uint32_t a_hi_addr = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_addr = (uint32_t)__cvta_generic_to_shared(a_lo);
+    const uint32_t b_hi_addr = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_addr = (uint32_t)__cvta_generic_to_shared(b_lo);
+    const uint32_t sbo = (uint32_t)kt * 32u;
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int base = begin + tile * kN;
+        for (int wt = warp; wt < (kN / 8) * kgroups; wt += kM / 32) {
+            const int r = (wt / kgroups) * 8 + rr, k4 = (wt % kgroups) * 4 + kk;
+            const int id = min(base + r, end - 1);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k4 * 4 < g.pitch) v = ldg_f4(reinterpret_cast<const float4*>(g.vectors + (size_t)id * g.pitch) + k4);
+            store_split(b_hi, b_lo, piece_off(r, k4, kt), v);
+        }
+        float* xa_t = xa_s + (tile & 1) * kN;  // (a thread still in the previous tile's epilogue reads the other half)
+        if (tid < kN) xa_t[tid] = base + tid < end ? __ldg(xaux + base + tid) : CUDART_NAN_F;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tensor core reads shared memory through the async proxy
+        tc_fence_before();  // (the previous tile's tcgen05.ld of every warp are complete)
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < (kt >> 3); ++ks) {
+                const uint32_t adv = (uint32_t)ks * 256u;  // 8 floats along K = two core matrices
+                const uint64_t dah = smem_desc(a_hi_addr + adv, 128u, sbo), dal = smem_desc(a_lo_addr + adv, 128u, sbo);
+                const uint64_t dbh = smem_desc(b_hi_addr + adv, 128u, sbo), dbl = smem_desc(b_lo_addr + adv, 128u, sbo);
+                umma_tf32(tmem_d, dal, dbh, ks > 0 ? 1u : 0u);  // small terms first
+                umma_tf32(tmem_d, dah, dbl, 1u);
+                umma_tf32(tmem_d, dah, dbh, 1u);
+            }
+            umma_commit(bar_addr);
+        }
+        mbar_wait(bar_addr, (uint32_t)(tile & 1));
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the spin
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < kN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            if (q0 + tid >= nq) continue;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int id = base + c0 + j;
+                const float xa = xa_t[c0 + j];
+                if (id >= end || xa != xa) continue;  // past the chunk, or a removed item
+                const float c = __uint_as_float(v[j]);
+                float s;
+                if (metric_is_sq(METRIC)) s = (qa + xa) - 2.0f * c;
+                else if (METRIC == COSINE) s = 1.0f - c * (qa * xa);
+                else s = 1.0f - c;
+                if (f2ord(s) > thr) continue;
+                const u64 key = make_key(s, id);
+                if (n == kp && key >= list[kp - 1]) continue;
+                int i = n < kp ? n : kp - 1;
+                while (i > 0 && list[i - 1] > key) { list[i] = list[i - 1]; --i; }
+                list[i] = key;
+                if (n < kp) ++n;
+                if (n == kp) thr = key_ord(list[kp - 1]);
+            }
+        }
+    }
+    if (q0 + tid < nq) {
+        u64* out = part_keys + ((size_t)(q0 + tid) * chunks + chunk) * kp;
+        for (int j = 0; j < kp; ++j) out[j] = j < n ? list[j] : ~0ull;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) __syncwarp();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kN));
+}
+
+static size_t tc5_scan_smem(int dim, int kp) {
+    const int kt = (dim + 15) & ~15;
+    return (size_t)(tc5::kM + tc5::kN) * kt * 8 + (size_t)tc5::kM * (kp | 1) * 8 + 2 * tc5::kN * 4 + 16;
+}
+
+// the tcgen05 pass A handles rows of at most 128 floats whose lists fit next to the operand tiles
+bool exact_tcgen05_supported(int dim, int k) {
+    if (dim < 1 || dim > 128 || k < 1) return false;
+    int dev = 0, max_optin = 0;
+    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return tc5_scan_smem(dim, exact_tf32_candidates(k)) <= (size_t)max_optin;
+}
+
 // ---------------------------------------------------------------------------------------------
 static int tf32_chunks(int count) { return std::max(1, std::min(32, (count + 4095) / 4096)); }
 
@@ -390,8 +616,9 @@ size_t exact_tf32_scratch_bytes(int nq, int k, int count) {
 }
 
 void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists, int* d_fail,
-                           void* d_scratch, size_t scratch_bytes, bool refresh_aux, cudaStream_t stream) {
+                           void* d_scratch, size_t scratch_bytes, bool refresh_aux, bool use_tcgen05, cudaStream_t stream) {
     if (nq <= 0) return;
+    use_tcgen05 = use_tcgen05 && exact_tcgen05_supported(g.dim, k);
     const int tq = exact_tf32_block_queries(g.dim, k);
     if (tq == 0) throw std::runtime_error("exact_knn_tf32: dim / k do not fit the tensor-core variant");
     if (scratch_bytes < exact_tf32_scratch_bytes(nq, k, g.count)) throw std::runtime_error("exact_knn_tf32: scratch too small");
@@ -430,7 +657,11 @@ void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_querie
             exact_tf32_aux_kernel<M><<<sms * 8, kThreads, 0, stream>>>(g, d_xaux, d_xmax2);                                     \
             HNSW_CUDA_CHECK(cudaGetLastError());                                                                                \
         }                                                                                                                       \
-        if (tq == 64) HNSW_TF32_SCAN(M, 4) else if (tq == 32) HNSW_TF32_SCAN(M, 2) else HNSW_TF32_SCAN(M, 1)                    \
+        if (use_tcgen05) {                                                                                                      \
+            const size_t tsmem = tc5_scan_smem(g.dim, kp);                                                                      \
+            HNSW_CUDA_CHECK(cudaFuncSetAttribute(exact_tc5_scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)); \
+            exact_tc5_scan_kernel<M><<<dim3(chunks, (nq + tc5::kM - 1) / tc5::kM), tc5::kM, tsmem, stream>>>(g, d_queries, nq, kp, chunk_items, d_xaux, d_part); \
+        } else if (tq == 64) HNSW_TF32_SCAN(M, 4) else if (tq == 32) HNSW_TF32_SCAN(M, 2) else HNSW_TF32_SCAN(M, 1)             \
         HNSW_CUDA_CHECK(cudaGetLastError());                                                                                    \
         launch_merge_keys(d_part, chunks, nq, kp, d_cids, d_capx, stream);                                                      \
         HNSW_CUDA_CHECK(cudaFuncSetAttribute(exact_tf32_rerank_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem)); \

@@ -72,6 +72,7 @@ def _load():
         "hnsw_set_stream": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
         "hnsw_exact_knn": (ct.c_int, [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p]),
         "hnsw_exact_knn_tf32": (ct.c_int, [ct.c_void_p, f32p, ct.c_int, ct.c_int, ct.c_int, i32p, f32p, i32p]),
+        "hnsw_exact_tcgen05_supported": (ct.c_int, [ct.c_int, ct.c_int]),
         "hnsw_merge_topk_device": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
         "hnsw_enable_stats": (ct.c_int, [ct.c_void_p, ct.c_int]),
         "hnsw_get_stats": (ct.c_int, [ct.c_void_p, ct.c_void_p]),

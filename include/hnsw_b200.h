@@ -163,6 +163,10 @@ HNSW_API int hnsw_exact_knn(hnsw_handle handle, const float* queries, int count,
  * the FFMA scan of hnsw_exact_knn instead.  *outFallbacks (may be null) = number of such queries. */
 HNSW_API int hnsw_exact_knn_tf32(hnsw_handle handle, const float* queries, int count, int dim, int k, int* outIds, float* outDists,
                                  int* outFallbacks);
+/* With hnsw_set_tuning(handle, "exact_tcgen05", 1) the GEMM of hnsw_exact_knn_tf32 runs as tcgen05.mma kind::tf32 with the
+ * accumulator in tensor memory instead of mma.sync, for the shapes this returns 1 for (rows of at most 128 floats and a
+ * k whose candidate lists fit in shared memory); other shapes keep using the mma.sync kernel.  -1 on error. */
+HNSW_API int hnsw_exact_tcgen05_supported(int dim, int k);
 
 /* Merge `parts` per-partition top-k results (device memory, [parts][count][k], rows ascending,
  * -1 padded) into [count][k] on the current device. */

@@ -2,7 +2,8 @@
 GPU tests of the tensor-core exact top-k (hnsw_exact_knn_tf32, csrc/exact_tf32_kernels.cu): a 3xTF32 GEMM ranks all
 pairs approximately, k + slack candidates per query are evaluated with the bit-exact metric, uncertified queries go
 through the FFMA scan -- so the answers must equal hnsw_exact_knn's to the bit (which test_gpu_parity.py pins on the
-oracle's brute force).
+oracle's brute force).  The GEMM exists twice: tcgen05.mma + TMEM (rows of at most 128 floats, tuning key
+"exact_tcgen05" = 1, the default) and mma.sync (every other shape, or "exact_tcgen05" = 0); both are covered.
 """
 import time
 
@@ -33,11 +34,24 @@ def _index(hnswindex, metric, data, **kw):
 
 
 def _same(ix, q, k):
+    """scan == tensor-core variant for both GEMM kernels; returns the larger number of fall-backs"""
     a_ids, a_d = ix.exact_knn(q, k)
-    b_ids, b_d = ix.exact_knn(q, k, tensor_cores=True)
-    assert np.array_equal(a_ids, b_ids), f"ids differ in {(a_ids != b_ids).any(axis=1).sum()} of {len(q)} rows"
-    assert np.array_equal(a_d.view(np.uint32), b_d.view(np.uint32)), "distances are not bit-identical"
-    return ix.last_exact_fallbacks
+    fb = 0
+    for tcgen05 in (1, 0):
+        ix.set_tuning("exact_tcgen05", tcgen05)
+        b_ids, b_d = ix.exact_knn(q, k, tensor_cores=True)
+        assert np.array_equal(a_ids, b_ids), f"ids differ in {(a_ids != b_ids).any(axis=1).sum()} of {len(q)} rows (tcgen05={tcgen05})"
+        assert np.array_equal(a_d.view(np.uint32), b_d.view(np.uint32)), f"distances are not bit-identical (tcgen05={tcgen05})"
+        fb = max(fb, ix.last_exact_fallbacks)
+    ix.set_tuning("exact_tcgen05", 1)
+    return fb
+
+
+def test_tcgen05_kernel_covers_the_headline_shape(hnswindex):
+    from hnswindex.bindings import lib
+    assert lib.hnsw_exact_tcgen05_supported(128, 10) == 1   # C2: 1M x 128, k = 10
+    assert lib.hnsw_exact_tcgen05_supported(96, 10) == 1    # C4
+    assert lib.hnsw_exact_tcgen05_supported(960, 100) == 0  # C3 rows are too long for one block's shared memory: mma.sync
 
 
 @pytest.mark.parametrize("metric,dim", [("sq_euclid", 128), ("cosine", 100), ("ucosine", 96), ("euclid", 64), ("sq_euclid", 3),
@@ -81,12 +95,11 @@ def test_tensor_core_exact_on_clustered_data_200k(hnswindex):
     x = (z @ A + 0.25 * rng.standard_normal((202000, 128)).astype(np.float32)).astype(np.float32)
     data, q = x[:200000], x[200000:]
     ix = _index(hnswindex, "sq_euclid", data, max_edges=8, max_candidates=32)
+    fb = _same(ix, q, 10)
     t0 = time.time()
-    a = ix.exact_knn(q, 10)
+    ix.exact_knn(q, 10)
     t1 = time.time()
-    b = ix.exact_knn(q, 10, tensor_cores=True)
+    ix.exact_knn(q, 10, tensor_cores=True)
     t2 = time.time()
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
-    print(f"\nexact top-10, 2000 queries x 200k x 128: scan {t1 - t0:.3f} s, tensor cores {t2 - t1:.3f} s, "
-          f"fall-backs {ix.last_exact_fallbacks}")
-    assert ix.last_exact_fallbacks <= 200
+    print(f"\nexact top-10, 2000 queries x 200k x 128: scan {t1 - t0:.3f} s, tensor cores {t2 - t1:.3f} s, fall-backs {fb}")
+    assert fb <= 200

@@ -1,5 +1,5 @@
 """Exact top-k at the C2 size: FFMA scan (hnsw_exact_knn) against the tensor-core variant (hnsw_exact_knn_tf32).
-Usage: python tools/exact_perf.py [n_items] [n_queries]"""
+Usage: python tools/exact_perf.py [n_items] [n_queries] [repetitions]"""
 import json
 import sys
 import time
@@ -30,18 +30,22 @@ ix.add(x[:n])
 print("build (M=4, efC=8): %.2f s" % (time.time() - t), flush=True)
 q = x[n:]
 out = {"n": n, "nq": nq, "dim": 128}
-for k in (10, 100):
-    for name, tc in (("scan", False), ("tf32", True)):
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+for k in (10,) if reps == 1 else (10, 100):
+    ref = None
+    for name, tc, t5 in (("scan", False, 0), ("mma_sync", True, 0), ("tcgen05", True, 1)):
+        ix.set_tuning("exact_tcgen05", t5)
         ix.exact_knn(q[:64], k, tensor_cores=tc)
         best = 1e9
-        for _ in range(2):
+        for _ in range(reps):
             t = time.time()
             r = ix.exact_knn(q, k, tensor_cores=tc)
             best = min(best, time.time() - t)
         out[f"{name}_k{k}_s"] = round(best, 4)
         out[f"{name}_k{k}_tflops_fp32_equiv"] = round(2.0 * n * nq * 128 / best / 1e12, 2)
-        if tc:
-            out[f"tf32_k{k}_fallbacks"] = ix.last_exact_fallbacks
-            out[f"tf32_k{k}_identical"] = bool(np.array_equal(r[0], prev[0]) and np.array_equal(r[1].view(np.uint32), prev[1].view(np.uint32)))
-        prev = r
+        if ref is None:
+            ref = r
+        else:
+            out[f"{name}_k{k}_fallbacks"] = ix.last_exact_fallbacks
+            out[f"{name}_k{k}_identical"] = bool(np.array_equal(r[0], ref[0]) and np.array_equal(r[1].view(np.uint32), ref[1].view(np.uint32)))
 print(json.dumps(out))
