@@ -364,8 +364,9 @@ exact_tf32_rerank_kernel(GraphView g, const float* __restrict__ queries, int nq,
 // and commits them to an mbarrier; every thread then owns one query row: `tcgen05.ld.32x32b` brings its 64 dot products
 // to registers, and the few that beat the row's kp-th best are inserted into the row's sorted list by that thread
 // alone.  Same part_keys output as exact_tf32_scan_kernel, so merge, re-ranking and certificate are shared.
-// (Synchronous and single-buffered: the stage for the next tile is filled after the epilogue.  A TMA / multi-stage
-// pipeline only matters if brute force ever becomes a hot path.)
+// Two accumulators alternate, so the epilogue of tile t - 1 runs under the MMAs of tile t, and the rows of tile t + 1 are
+// on their way from global memory into registers meanwhile; the operand stage itself is single-buffered (at 128 floats
+// per row the two split operand tiles and the lists fill the 227 KB), which is what a TMA-fed multi-stage ring would lift.
 namespace tc5 {
 
 constexpr int kM = 128;  // queries per block (UMMA M, TMEM lanes)
@@ -449,8 +450,8 @@ exact_tc5_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, in
     unsigned char* b_hi = a_lo + (size_t)kM * kt * 4;
     unsigned char* b_lo = b_hi + (size_t)kN * kt * 4;
     u64* lists = reinterpret_cast<u64*>(b_lo + (size_t)kN * kt * 4);  // [kM][pitchL]
-    float* xa_s = reinterpret_cast<float*>(lists + (size_t)kM * pitchL);  // [2][kN] per-item norms of the tile, by tile parity
-    u64* bar = reinterpret_cast<u64*>(xa_s + 2 * kN);
+    float* xa_s = reinterpret_cast<float*>(lists + (size_t)kM * pitchL);  // [3][kN] per-item norms of the tiles in flight
+    u64* bar = reinterpret_cast<u64*>(xa_s + 3 * kN);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(bar);
 
@@ -479,7 +480,7 @@ exact_tc5_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, in
     }
     if (warp == 0) {
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(kN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(2 * kN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
@@ -491,83 +492,174 @@ exact_tc5_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, in
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
 
+    // This thread's query row: an UNSORTED list of the kp best keys so far plus the position of its largest entry (an
+    // insertion overwrites that entry and rescans for the new maximum with independent loads -- a sorted insertion is a
+    // chain of dependent shared-memory round trips, which the ncu source page showed to dominate); sorted once at the end.
     u64* list = lists + (size_t)tid * pitchL;
-    int n = 0;
-    uint32_t thr = 0xFFFFFFFFu;
+    int n = 0, maxpos = 0;
+    u64 maxkey = 0;
+    float thr_f = CUDART_INF_F;  // distance of the kp-th best, +inf while the list is not full
     const int begin = chunk * chunk_items, end = min(g.count, begin + chunk_items);
     const int ntiles = begin < end ? (end - begin + kN - 1) / kN : 0;
-    const uint32_t a_hi_addr = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_addr = (uint32_t)__cvta_generic_to_shared(a_lo);
-    const uint32_t b_hi_addr = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_addr = (uint32_t)__cvta_generic_to_shared(b_lo);
     const uint32_t sbo = (uint32_t)kt * 32u;
+    const uint64_t dah0 = smem_desc((uint32_t)__cvta_generic_to_shared(a_hi), 128u, sbo), dal0 = smem_desc((uint32_t)__cvta_generic_to_shared(a_lo), 128u, sbo);
+    const uint64_t dbh0 = smem_desc((uint32_t)__cvta_generic_to_shared(b_hi), 128u, sbo), dbl0 = smem_desc((uint32_t)__cvta_generic_to_shared(b_lo), 128u, sbo);
+    const int b_tiles = (kN / 8) * kgroups;  // warp tiles of one stage: at most 64, i.e. 16 per warp
 
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const int base = begin + tile * kN;
-        for (int wt = warp; wt < (kN / 8) * kgroups; wt += kM / 32) {
-            const int r = (wt / kgroups) * 8 + rr, k4 = (wt % kgroups) * 4 + kk;
-            const int id = min(base + r, end - 1);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k4 * 4 < g.pitch) v = ldg_f4(reinterpret_cast<const float4*>(g.vectors + (size_t)id * g.pitch) + k4);
-            store_split(b_hi, b_lo, piece_off(r, k4, kt), v);
-        }
-        float* xa_t = xa_s + (tile & 1) * kN;  // (a thread still in the previous tile's epilogue reads the other half)
-        if (tid < kN) xa_t[tid] = base + tid < end ? __ldg(xaux + base + tid) : CUDART_NAN_F;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tensor core reads shared memory through the async proxy
-        tc_fence_before();  // (the previous tile's tcgen05.ld of every warp are complete)
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            for (int ks = 0; ks < (kt >> 3); ++ks) {
-                const uint32_t adv = (uint32_t)ks * 256u;  // 8 floats along K = two core matrices
-                const uint64_t dah = smem_desc(a_hi_addr + adv, 128u, sbo), dal = smem_desc(a_lo_addr + adv, 128u, sbo);
-                const uint64_t dbh = smem_desc(b_hi_addr + adv, 128u, sbo), dbl = smem_desc(b_lo_addr + adv, 128u, sbo);
-                umma_tf32(tmem_d, dal, dbh, ks > 0 ? 1u : 0u);  // small terms first
-                umma_tf32(tmem_d, dah, dbl, 1u);
-                umma_tf32(tmem_d, dah, dbh, 1u);
-            }
-            umma_commit(bar_addr);
-        }
-        mbar_wait(bar_addr, (uint32_t)(tile & 1));
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the spin
-        tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < kN; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-            if (q0 + tid >= nq) continue;
+    // per-thread pieces of a stage, fixed for the whole kernel: byte offset in shared memory (-1: none) and float offset
+    // from the tile's first row in the slab (-1: beyond the row pitch, stays zero)
+    int poff[16], goff[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int id = base + c0 + j;
-                const float xa = xa_t[c0 + j];
-                if (id >= end || xa != xa) continue;  // past the chunk, or a removed item
-                const float c = __uint_as_float(v[j]);
-                float s;
-                if (metric_is_sq(METRIC)) s = (qa + xa) - 2.0f * c;
-                else if (METRIC == COSINE) s = 1.0f - c * (qa * xa);
-                else s = 1.0f - c;
-                if (f2ord(s) > thr) continue;
-                const u64 key = make_key(s, id);
-                if (n == kp && key >= list[kp - 1]) continue;
-                int i = n < kp ? n : kp - 1;
-                while (i > 0 && list[i - 1] > key) { list[i] = list[i - 1]; --i; }
-                list[i] = key;
-                if (n < kp) ++n;
-                if (n == kp) thr = key_ord(list[kp - 1]);
-            }
+    for (int i = 0; i < 16; ++i) {
+        const int wt = warp + i * (kM / 32);
+        poff[i] = goff[i] = -1;
+        if (wt < b_tiles) {
+            const int r = (wt / kgroups) * 8 + rr, k4 = (wt % kgroups) * 4 + kk;
+            poff[i] = (int)piece_off(r, k4, kt);
+            if (k4 * 4 < g.pitch) goff[i] = r * g.pitch + k4 * 4;
         }
     }
+
+    // Software pipeline over the tiles, iteration t:
+    //   stage(t): the rows prefetched into registers one iteration earlier are split and written to shared memory
+    //   MMA(t) is issued into accumulator t & 1 (asynchronous), the rows of tile t + 1 are requested from global memory,
+    //   epilogue(t - 1) drains accumulator (t - 1) & 1 while MMA(t) runs, then everybody waits for MMA(t).
+    float4 pre[16];
+    float xa_pre = CUDART_NAN_F;
+#define HNSW_TC5_PREFETCH(TILE)                                                                                              \
+    {                                                                                                                        \
+        const int pbase = begin + (TILE) * kN;                                                                               \
+        const float* tb = g.vectors + (size_t)pbase * g.pitch;                                                               \
+        if (pbase + kN <= end) {                                                                                             \
+            _Pragma("unroll") for (int i = 0; i < 16; ++i) {                                                                 \
+                pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                                    \
+                if (goff[i] >= 0) pre[i] = ldg_f4(reinterpret_cast<const float4*>(tb + goff[i]));                            \
+            }                                                                                                                \
+        } else { /* last, partial tile: rows past the end re-read the last vector and are masked by their NaN norm */       \
+            _Pragma("unroll") for (int i = 0; i < 16; ++i) {                                                                 \
+                const int wt = warp + i * (kM / 32);                                                                         \
+                pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                                    \
+                if (goff[i] >= 0) {                                                                                          \
+                    const int r = (wt / kgroups) * 8 + rr, k4 = (wt % kgroups) * 4 + kk;                                     \
+                    const int id = min(pbase + r, end - 1);                                                                  \
+                    pre[i] = ldg_f4(reinterpret_cast<const float4*>(g.vectors + (size_t)id * g.pitch) + k4);                 \
+                }                                                                                                            \
+            }                                                                                                                \
+        }                                                                                                                    \
+        if (tid < kN) xa_pre = pbase + tid < end ? __ldg(xaux + pbase + tid) : CUDART_NAN_F;                                 \
+    }
+    if (ntiles > 0) HNSW_TC5_PREFETCH(0)
+
+    for (int tile = 0; tile <= ntiles; ++tile) {
+        if (tile < ntiles) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (poff[i] >= 0) store_split(b_hi, b_lo, (uint32_t)poff[i], pre[i]);
+            if (tid < kN) xa_s[(tile % 3) * kN + tid] = xa_pre;  // three slots: read one iteration later, rewritten three later
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tensor core reads shared memory through the async proxy
+        }
+        tc_fence_before();  // (this thread's tcgen05.ld of the previous iteration are complete)
+        __syncthreads();
+        if (tile < ntiles) {
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t d = tmem_d + (uint32_t)(tile & 1) * kN;
+                for (int ks = 0; ks < (kt >> 3); ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 16);  // 8 floats along K = two core matrices = 256 B, in 16 B units
+                    umma_tf32(d, dal0 + adv, dbh0 + adv, ks > 0 ? 1u : 0u);  // small terms first
+                    umma_tf32(d, dah0 + adv, dbl0 + adv, 1u);
+                    umma_tf32(d, dah0 + adv, dbh0 + adv, 1u);
+                }
+                umma_commit(bar_addr);
+            }
+            if (tile + 1 < ntiles) HNSW_TC5_PREFETCH(tile + 1)
+        }
+        __syncwarp();  // tcgen05.ld is warp-collective
+        if (tile > 0) {
+            const int base = begin + (tile - 1) * kN;
+            const float* xa_t = xa_s + ((tile - 1) % 3) * kN;  // NaN for removed items and past the chunk: never below a threshold
+            const uint32_t d = tmem_d + (uint32_t)((tile - 1) & 1) * kN + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(d + (uint32_t)c0, v);
+                if (q0 + tid >= nq) continue;
+                float xa[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(xa_t + c0 + j);
+                    xa[j] = x4.x; xa[j + 1] = x4.y; xa[j + 2] = x4.z; xa[j + 3] = x4.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float c = __uint_as_float(v[j]);
+                    float s;
+                    if (metric_is_sq(METRIC)) s = fmaf(-2.0f, c, qa + xa[j]);
+                    else if (METRIC == COSINE) s = fmaf(-c, qa * xa[j], 1.0f);
+                    else s = (xa[j] + 1.0f) - c;  // xa is 0 for a live item
+                    if (!(s <= thr_f)) continue;
+                    const u64 key = make_key(s, base + c0 + j);
+                    if (n < kp) {
+                        list[n] = key;
+                        if (n == 0 || key > maxkey) { maxkey = key; maxpos = n; }
+                        if (++n == kp) thr_f = key_dist(maxkey);
+                    } else if (key < maxkey) {
+                        list[maxpos] = key;
+                        u64 m = 0;
+                        int mp = 0;
+                        for (int t = 0; t < kp; ++t) {
+                            const u64 e = list[t];
+                            if (e >= m) { m = e; mp = t; }
+                        }
+                        maxkey = m;
+                        maxpos = mp;
+                        thr_f = key_dist(m);
+                    }
+                }
+            }
+        }
+        if (tile < ntiles) {
+            mbar_wait(bar_addr, (uint32_t)(tile & 1));
+            __syncwarp();
+            tc_fence_after();
+        }
+    }
+#undef HNSW_TC5_PREFETCH
     if (q0 + tid < nq) {
+        for (int a = 1; a < n; ++a) {  // sort this row's keys ascending (once)
+            const u64 key = list[a];
+            int i = a;
+            while (i > 0 && list[i - 1] > key) { list[i] = list[i - 1]; --i; }
+            list[i] = key;
+        }
         u64* out = part_keys + ((size_t)(q0 + tid) * chunks + chunk) * kp;
         for (int j = 0; j < kp; ++j) out[j] = j < n ? list[j] : ~0ull;
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) __syncwarp();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kN));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(2 * kN));
 }
 
 static size_t tc5_scan_smem(int dim, int kp) {
     const int kt = (dim + 15) & ~15;
-    return (size_t)(tc5::kM + tc5::kN) * kt * 8 + (size_t)tc5::kM * (kp | 1) * 8 + 2 * tc5::kN * 4 + 16;
+    return (size_t)(tc5::kM + tc5::kN) * kt * 8 + (size_t)tc5::kM * (kp | 1) * 8 + 3 * tc5::kN * 4 + 16;
+}
+
+static int tf32_chunks(int count) { return std::max(1, std::min(32, (count + 4095) / 4096)); }
+
+// Data chunks for the tcgen05 kernel: every chunk starts its lists from scratch (k' log(N / chunks / k') insertions per
+// query and chunk), so as few as fill the device evenly: the candidate with the best wave efficiency, smaller first.
+static int tc5_chunks(int count, int nq, int sms) {
+    const int cmax = tf32_chunks(count), qt = (nq + tc5::kM - 1) / tc5::kM;
+    int best = 1;
+    double best_score = -1.0;
+    for (int c = 1; c <= cmax; ++c) {
+        const long long ctas = (long long)c * qt, rounds = (ctas + sms - 1) / sms;
+        const double score = (double)ctas / (double)(rounds * sms) - 0.004 * c;
+        if (score > best_score) { best_score = score; best = c; }
+    }
+    return best;
 }
 
 // the tcgen05 pass A handles rows of at most 128 floats whose lists fit next to the operand tiles
@@ -580,7 +672,6 @@ bool exact_tcgen05_supported(int dim, int k) {
 }
 
 // ---------------------------------------------------------------------------------------------
-static int tf32_chunks(int count) { return std::max(1, std::min(32, (count + 4095) / 4096)); }
 
 int exact_tf32_candidates(int k) { return k + 16 + k / 4; }
 
@@ -623,7 +714,13 @@ void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_querie
     if (tq == 0) throw std::runtime_error("exact_knn_tf32: dim / k do not fit the tensor-core variant");
     if (scratch_bytes < exact_tf32_scratch_bytes(nq, k, g.count)) throw std::runtime_error("exact_knn_tf32: scratch too small");
     const int kp = exact_tf32_candidates(k);
-    const int chunks = tf32_chunks(g.count);
+    int sms = 148;
+    {
+        int dev = 0;
+        HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+        HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int chunks = use_tcgen05 ? tc5_chunks(g.count, nq, sms) : tf32_chunks(g.count);  // (the scratch is sized for the larger)
     const int chunk_items = (g.count + chunks - 1) / chunks;
     // scratch layout (256 B aligned pieces): xmax2 | xaux | part keys | candidate ids | candidate distances
     unsigned char* p = static_cast<unsigned char*>(d_scratch);
@@ -635,12 +732,6 @@ void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_querie
     float* d_capx = reinterpret_cast<float*>(take((size_t)nq * kp * 4));
     if ((size_t)(p - static_cast<unsigned char*>(d_scratch)) > scratch_bytes) throw std::runtime_error("exact_knn_tf32: scratch layout overflow");
 
-    int sms = 148;
-    {
-        int dev = 0;
-        HNSW_CUDA_CHECK(cudaGetDevice(&dev));
-        HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
     const size_t smem = tf32_scan_smem(g.dim, kp, tq);
     dim3 grid(chunks, (nq + tq - 1) / tq);
     const size_t rsmem = (size_t)kWarpsPerBlock * (((g.pitch + 3) & ~3) * 4 + (size_t)k * 8);
