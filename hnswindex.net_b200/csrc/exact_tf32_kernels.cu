@@ -492,11 +492,12 @@ exact_tc5_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, in
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
 
-    // This thread's query row: an UNSORTED list of the kp best keys so far plus the position of its largest entry (an
-    // insertion overwrites that entry and rescans for the new maximum with independent loads -- a sorted insertion is a
-    // chain of dependent shared-memory round trips, which the ncu source page showed to dominate); sorted once at the end.
+    // This thread's query row: the kp best keys so far as a binary MAX-HEAP in shared memory (an insertion replaces the
+    // root and sifts down at most log2(kp) levels; a sorted insertion is a chain of up to kp dependent shared-memory round
+    // trips and a rescan for the maximum costs kp loads per insertion -- the ncu source pages showed either to dominate
+    // the kernel); sorted once at the end.
     u64* list = lists + (size_t)tid * pitchL;
-    int n = 0, maxpos = 0;
+    int n = 0;
     u64 maxkey = 0;
     float thr_f = CUDART_INF_F;  // distance of the kp-th best, +inf while the list is not full
     const int begin = chunk * chunk_items, end = min(g.count, begin + chunk_items);
@@ -601,19 +602,38 @@ exact_tc5_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, in
                     const u64 key = make_key(s, base + c0 + j);
                     if (n < kp) {
                         list[n] = key;
-                        if (n == 0 || key > maxkey) { maxkey = key; maxpos = n; }
-                        if (++n == kp) thr_f = key_dist(maxkey);
-                    } else if (key < maxkey) {
-                        list[maxpos] = key;
-                        u64 m = 0;
-                        int mp = 0;
-                        for (int t = 0; t < kp; ++t) {
-                            const u64 e = list[t];
-                            if (e >= m) { m = e; mp = t; }
+                        if (++n == kp) {  // full: turn the array into a max-heap (largest key at list[0])
+                            for (int h0 = kp / 2 - 1; h0 >= 0; --h0) {
+                                const u64 val = list[h0];
+                                int i = h0;
+                                for (;;) {
+                                    int ch = 2 * i + 1;
+                                    if (ch >= kp) break;
+                                    u64 cv = list[ch];
+                                    if (ch + 1 < kp) { const u64 rv = list[ch + 1]; if (rv > cv) { cv = rv; ++ch; } }
+                                    if (cv <= val) break;
+                                    list[i] = cv;
+                                    i = ch;
+                                }
+                                list[i] = val;
+                            }
+                            maxkey = list[0];
+                            thr_f = key_dist(maxkey);
                         }
-                        maxkey = m;
-                        maxpos = mp;
-                        thr_f = key_dist(m);
+                    } else if (key < maxkey) {  // replace the root and sift the new key down: at most log2(kp) levels
+                        int i = 0;
+                        for (;;) {
+                            int ch = 2 * i + 1;
+                            if (ch >= kp) break;
+                            u64 cv = list[ch];
+                            if (ch + 1 < kp) { const u64 rv = list[ch + 1]; if (rv > cv) { cv = rv; ++ch; } }
+                            if (cv <= key) break;
+                            list[i] = cv;
+                            i = ch;
+                        }
+                        list[i] = key;
+                        maxkey = list[0];
+                        thr_f = key_dist(maxkey);
                     }
                 }
             }
