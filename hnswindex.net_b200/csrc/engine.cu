@@ -823,7 +823,7 @@ int Index::exact_knn_tf32(const float* queries, int count, int dim, int k, int* 
             const int n = std::min(slab, count - q0);
             ensure_query_scratch(n, k);
             HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries + (size_t)q0 * dim, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream_));
-            launch_exact_knn_tf32((int)metric_, view(), d_q_, n, k, d_ids_, d_dists_, d_fail, scratch, sbytes, q0 == 0, tuning_.exact_tcgen05 != 0,
+            launch_exact_knn_tf32((int)metric_, view(), d_q_, n, k, d_ids_, d_dists_, d_fail, scratch, sbytes, q0 == 0, tuning_.exact_tcgen05,
                                   stream_);
             stats_.search_launches += q0 == 0 ? 4 : 3;
             fail.resize(n);

@@ -661,9 +661,242 @@ exact_tc5_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, in
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(2 * kN));
 }
 
+// ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL (tuning key "exact_tcgen05" = 2; written at the end of round 1 without GPU time left to run it): the
+// same pass A, warp-specialised.  256 threads: warps 0-3 only drain the accumulators (thread t = query row t, as above),
+// warps 4-7 only stage the operand tile (prefetch to registers, split, store) and one of their threads issues the MMAs.
+//   mma_done[b]  (count 1, tcgen05.commit)   accumulator b holds tile t (t & 1 == b) and the operand stage is free again
+//   tmem_free[b] (count 128, consumer threads) accumulator b has been read and may be overwritten by tile t + 2
+// The producers of tile t + 1 wait for mma_done(t), the consumers of tile t wait for mma_done(t): the epilogue of tile t
+// runs while tile t + 1 is staged and multiplied.
+template <int METRIC>
+__global__ void __launch_bounds__(2 * tc5::kM, 1)
+exact_tc5ws_scan_kernel(GraphView g, const float* __restrict__ queries, int nq, int kp, int chunk_items, const float* __restrict__ xaux,
+                        u64* __restrict__ part_keys) {
+    using namespace tc5;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.x, chunks = gridDim.x;
+    const int q0 = blockIdx.y * kM;
+    const int kt = (g.dim + 15) & ~15;
+    const int pitchL = kp | 1;
+
+    unsigned char* a_hi = smem;
+    unsigned char* a_lo = a_hi + (size_t)kM * kt * 4;
+    unsigned char* b_hi = a_lo + (size_t)kM * kt * 4;
+    unsigned char* b_lo = b_hi + (size_t)kN * kt * 4;
+    u64* lists = reinterpret_cast<u64*>(b_lo + (size_t)kN * kt * 4);
+    float* xa_s = reinterpret_cast<float*>(lists + (size_t)kM * pitchL);  // [3][kN]
+    u64* bars = reinterpret_cast<u64*>(xa_s + 3 * kN);                     // mma_done[2], tmem_free[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    const uint32_t mma_done0 = bar0, tmem_free0 = bar0 + 16;
+
+    const int rr = lane & 7, kk = lane >> 3;
+    const int kgroups = kt >> 4;
+    // queries -> split A tile (all 8 warps)
+    for (int wt = warp; wt < (kM / 8) * kgroups; wt += 2 * kM / 32) {
+        const int r = (wt / kgroups) * 8 + rr, k4 = (wt % kgroups) * 4 + kk;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + r < nq) {
+            const float* src = queries + (size_t)(q0 + r) * g.dim;
+            const int d = k4 * 4;
+            if (d < g.dim) v.x = __ldg(src + d);
+            if (d + 1 < g.dim) v.y = __ldg(src + d + 1);
+            if (d + 2 < g.dim) v.z = __ldg(src + d + 2);
+            if (d + 3 < g.dim) v.w = __ldg(src + d + 3);
+        }
+        store_split(a_hi, a_lo, piece_off(r, k4, kt), v);
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(2 * kN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mma_done0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mma_done0 + 8));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tmem_free0), "r"(kM));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tmem_free0 + 8), "r"(kM));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the A tile, for the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    const int begin = chunk * chunk_items, end = min(g.count, begin + chunk_items);
+    const int ntiles = begin < end ? (end - begin + kN - 1) / kN : 0;
+
+    if (warp >= kM / 32) {
+        // ===== producers: warps 4-7 =====
+        const int pw = warp - kM / 32, ptid = tid - kM;
+        const uint32_t sbo = (uint32_t)kt * 32u;
+        const uint64_t dah0 = smem_desc((uint32_t)__cvta_generic_to_shared(a_hi), 128u, sbo), dal0 = smem_desc((uint32_t)__cvta_generic_to_shared(a_lo), 128u, sbo);
+        const uint64_t dbh0 = smem_desc((uint32_t)__cvta_generic_to_shared(b_hi), 128u, sbo), dbl0 = smem_desc((uint32_t)__cvta_generic_to_shared(b_lo), 128u, sbo);
+        const int b_tiles = (kN / 8) * kgroups;
+        int poff[16], goff[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int wt = pw + i * (kM / 32);
+            poff[i] = goff[i] = -1;
+            if (wt < b_tiles) {
+                const int r = (wt / kgroups) * 8 + rr, k4 = (wt % kgroups) * 4 + kk;
+                poff[i] = (int)piece_off(r, k4, kt);
+                if (k4 * 4 < g.pitch) goff[i] = r * g.pitch + k4 * 4;
+            }
+        }
+        float4 pre[16];
+        float xa_pre = CUDART_NAN_F;
+#define HNSW_TC5WS_PREFETCH(TILE)                                                                                            \
+    {                                                                                                                        \
+        const int pbase = begin + (TILE) * kN;                                                                               \
+        const float* tb = g.vectors + (size_t)pbase * g.pitch;                                                               \
+        if (pbase + kN <= end) {                                                                                             \
+            _Pragma("unroll") for (int i = 0; i < 16; ++i) {                                                                 \
+                pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                                    \
+                if (goff[i] >= 0) pre[i] = ldg_f4(reinterpret_cast<const float4*>(tb + goff[i]));                            \
+            }                                                                                                                \
+        } else {                                                                                                             \
+            _Pragma("unroll") for (int i = 0; i < 16; ++i) {                                                                 \
+                const int wt = pw + i * (kM / 32);                                                                           \
+                pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                                    \
+                if (goff[i] >= 0) {                                                                                          \
+                    const int r = (wt / kgroups) * 8 + rr, k4 = (wt % kgroups) * 4 + kk;                                     \
+                    const int id = min(pbase + r, end - 1);                                                                  \
+                    pre[i] = ldg_f4(reinterpret_cast<const float4*>(g.vectors + (size_t)id * g.pitch) + k4);                 \
+                }                                                                                                            \
+            }                                                                                                                \
+        }                                                                                                                    \
+        if (ptid < kN) xa_pre = pbase + ptid < end ? __ldg(xaux + pbase + ptid) : CUDART_NAN_F;                              \
+    }
+        if (ntiles > 0) HNSW_TC5WS_PREFETCH(0)
+        for (int tile = 0; tile < ntiles; ++tile) {
+            if (tile > 0) mbar_wait(mma_done0 + 8u * (uint32_t)((tile - 1) & 1), (uint32_t)(((tile - 1) >> 1) & 1));  // stage free
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (poff[i] >= 0) store_split(b_hi, b_lo, (uint32_t)poff[i], pre[i]);
+            if (ptid < kN) xa_s[(tile % 3) * kN + ptid] = xa_pre;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four producer warps
+            if (ptid == 0) {
+                if (tile >= 2) mbar_wait(tmem_free0 + 8u * (uint32_t)(tile & 1), (uint32_t)(((tile - 2) >> 1) & 1));  // accumulator drained
+                tc_fence_after();
+                const uint32_t d = tmem_d + (uint32_t)(tile & 1) * kN;
+                for (int ks = 0; ks < (kt >> 3); ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 16);
+                    umma_tf32(d, dal0 + adv, dbh0 + adv, ks > 0 ? 1u : 0u);
+                    umma_tf32(d, dah0 + adv, dbl0 + adv, 1u);
+                    umma_tf32(d, dah0 + adv, dbh0 + adv, 1u);
+                }
+                umma_commit(mma_done0 + 8u * (uint32_t)(tile & 1));
+            }
+            if (tile + 1 < ntiles) HNSW_TC5WS_PREFETCH(tile + 1)
+        }
+#undef HNSW_TC5WS_PREFETCH
+    } else {
+        // ===== consumers: warps 0-3, thread t owns query row t =====
+        float qa = 0.f;
+        if (q0 + tid < nq) {
+            const float* src = queries + (size_t)(q0 + tid) * g.dim;
+            float s = 0.f;
+            for (int d = 0; d < g.dim; ++d) { const float a = __ldg(src + d); s = fmaf(a, a, s); }
+            qa = metric_is_sq(METRIC) ? s : (METRIC == COSINE ? (s > 1e-36f ? rsqrtf(s) : 0.f) : 0.f);
+        }
+        u64* list = lists + (size_t)tid * pitchL;
+        int n = 0;
+        u64 maxkey = 0;
+        float thr_f = CUDART_INF_F;
+        for (int tile = 0; tile < ntiles; ++tile) {
+            mbar_wait(mma_done0 + 8u * (uint32_t)(tile & 1), (uint32_t)((tile >> 1) & 1));
+            __syncwarp();
+            tc_fence_after();
+            const int base = begin + tile * kN;
+            const float* xa_t = xa_s + (tile % 3) * kN;
+            const uint32_t d = tmem_d + (uint32_t)(tile & 1) * kN + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(d + (uint32_t)c0, v);
+                if (q0 + tid >= nq) continue;
+                float xa[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(xa_t + c0 + j);
+                    xa[j] = x4.x; xa[j + 1] = x4.y; xa[j + 2] = x4.z; xa[j + 3] = x4.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float c = __uint_as_float(v[j]);
+                    float s;
+                    if (metric_is_sq(METRIC)) s = fmaf(-2.0f, c, qa + xa[j]);
+                    else if (METRIC == COSINE) s = fmaf(-c, qa * xa[j], 1.0f);
+                    else s = (xa[j] + 1.0f) - c;
+                    if (!(s <= thr_f)) continue;
+                    const u64 key = make_key(s, base + c0 + j);
+                    if (n < kp) {
+                        list[n] = key;
+                        if (++n == kp) {
+                            for (int h0 = kp / 2 - 1; h0 >= 0; --h0) {
+                                const u64 val = list[h0];
+                                int i = h0;
+                                for (;;) {
+                                    int ch = 2 * i + 1;
+                                    if (ch >= kp) break;
+                                    u64 cv = list[ch];
+                                    if (ch + 1 < kp) { const u64 rv = list[ch + 1]; if (rv > cv) { cv = rv; ++ch; } }
+                                    if (cv <= val) break;
+                                    list[i] = cv;
+                                    i = ch;
+                                }
+                                list[i] = val;
+                            }
+                            maxkey = list[0];
+                            thr_f = key_dist(maxkey);
+                        }
+                    } else if (key < maxkey) {
+                        int i = 0;
+                        for (;;) {
+                            int ch = 2 * i + 1;
+                            if (ch >= kp) break;
+                            u64 cv = list[ch];
+                            if (ch + 1 < kp) { const u64 rv = list[ch + 1]; if (rv > cv) { cv = rv; ++ch; } }
+                            if (cv <= key) break;
+                            list[i] = cv;
+                            i = ch;
+                        }
+                        list[i] = key;
+                        maxkey = list[0];
+                        thr_f = key_dist(maxkey);
+                    }
+                }
+            }
+            __syncwarp();
+            tc_fence_before();  // this thread's tcgen05.ld of the accumulator are complete ...
+            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(tmem_free0 + 8u * (uint32_t)(tile & 1)) : "memory");  // ... it may be overwritten
+        }
+        if (q0 + tid < nq) {
+            for (int a = 1; a < n; ++a) {
+                const u64 key = list[a];
+                int i = a;
+                while (i > 0 && list[i - 1] > key) { list[i] = list[i - 1]; --i; }
+                list[i] = key;
+            }
+            u64* out = part_keys + ((size_t)(q0 + tid) * chunks + chunk) * kp;
+            for (int j = 0; j < kp; ++j) out[j] = j < n ? list[j] : ~0ull;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) __syncwarp();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(2 * kN));
+}
+
 static size_t tc5_scan_smem(int dim, int kp) {
     const int kt = (dim + 15) & ~15;
-    return (size_t)(tc5::kM + tc5::kN) * kt * 8 + (size_t)tc5::kM * (kp | 1) * 8 + 3 * tc5::kN * 4 + 16;
+    return (size_t)(tc5::kM + tc5::kN) * kt * 8 + (size_t)tc5::kM * (kp | 1) * 8 + 3 * tc5::kN * 4 + 48;  // + barriers, TMEM slot
 }
 
 static int tf32_chunks(int count) { return std::max(1, std::min(32, (count + 4095) / 4096)); }
@@ -727,9 +960,9 @@ size_t exact_tf32_scratch_bytes(int nq, int k, int count) {
 }
 
 void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists, int* d_fail,
-                           void* d_scratch, size_t scratch_bytes, bool refresh_aux, bool use_tcgen05, cudaStream_t stream) {
+                           void* d_scratch, size_t scratch_bytes, bool refresh_aux, int tcgen05_mode, cudaStream_t stream) {
     if (nq <= 0) return;
-    use_tcgen05 = use_tcgen05 && exact_tcgen05_supported(g.dim, k);
+    const bool use_tcgen05 = tcgen05_mode != 0 && exact_tcgen05_supported(g.dim, k);
     const int tq = exact_tf32_block_queries(g.dim, k);
     if (tq == 0) throw std::runtime_error("exact_knn_tf32: dim / k do not fit the tensor-core variant");
     if (scratch_bytes < exact_tf32_scratch_bytes(nq, k, g.count)) throw std::runtime_error("exact_knn_tf32: scratch too small");
@@ -771,6 +1004,10 @@ void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_querie
         if (use_tcgen05) {                                                                                                      \
             const size_t tsmem = tc5_scan_smem(g.dim, kp);                                                                      \
             HNSW_CUDA_CHECK(cudaFuncSetAttribute(exact_tc5_scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)); \
+            if (tcgen05_mode == 2) { /* experimental warp-specialised variant */                                                \
+                HNSW_CUDA_CHECK(cudaFuncSetAttribute(exact_tc5ws_scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)); \
+                exact_tc5ws_scan_kernel<M><<<dim3(chunks, (nq + tc5::kM - 1) / tc5::kM), 2 * tc5::kM, tsmem, stream>>>(g, d_queries, nq, kp, chunk_items, d_xaux, d_part); \
+            } else                                                                                                              \
             exact_tc5_scan_kernel<M><<<dim3(chunks, (nq + tc5::kM - 1) / tc5::kM), tc5::kM, tsmem, stream>>>(g, d_queries, nq, kp, chunk_items, d_xaux, d_part); \
         } else if (tq == 64) HNSW_TF32_SCAN(M, 4) else if (tq == 32) HNSW_TF32_SCAN(M, 2) else HNSW_TF32_SCAN(M, 1)             \
         HNSW_CUDA_CHECK(cudaGetLastError());                                                                                    \

@@ -19,7 +19,8 @@ struct Tuning {
                               // then sees the previous batch's reverse links only partly and recall@10 drops 0.2 pt
     int async_overlap = 1;    // hnsw_knn_query_device_async alternates two streams (consecutive batches overlap in their tails)
     int blocks_per_sm = 0;    // 0 = occupancy query
-    int exact_tcgen05 = 1;    // exact_knn_tf32: pass A on tcgen05 / TMEM where the shape allows (rows <= 128 floats), else mma.sync
+    int exact_tcgen05 = 1;    // exact_knn_tf32: pass A on tcgen05 / TMEM where the shape allows (rows <= 128 floats), else mma.sync;
+                              // 2 = experimental warp-specialised tcgen05 kernel, 0 = always mma.sync
     int flags = 2;            // bit 0: L2-prefetch rows of accepted candidates (no gain); bit 1: guess-row load
 };
 
@@ -77,10 +78,11 @@ size_t exact_knn_scratch_bytes(int nq, int k, int count);
 int exact_tf32_candidates(int k);
 int exact_tf32_block_queries(int dim, int k);  // 64 / 32 / 16, or 0 when dim / k do not fit the variant
 size_t exact_tf32_scratch_bytes(int nq, int k, int count);
-// use_tcgen05: pass A as tcgen05.mma kind::tf32 with the accumulator in TMEM (rows <= 128 floats; else the mma.sync kernel)
+// tcgen05_mode: 0 = mma.sync; 1 = pass A as tcgen05.mma kind::tf32 with the accumulator in TMEM (rows <= 128 floats, else
+// the mma.sync kernel); 2 = the experimental warp-specialised tcgen05 kernel (not yet run on a GPU)
 bool exact_tcgen05_supported(int dim, int k);
 void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists, int* d_fail,
-                           void* d_scratch, size_t scratch_bytes, bool refresh_aux, bool use_tcgen05, cudaStream_t stream);
+                           void* d_scratch, size_t scratch_bytes, bool refresh_aux, int tcgen05_mode, cudaStream_t stream);
 // per query: merge `parts` sorted key lists [nq][parts][k] (~0 padded) into ids / distances [nq][k] (-1 / NaN padded)
 void launch_merge_keys(const u64* d_part_keys, int parts, int nq, int k, int* d_out_ids, float* d_out_dists, cudaStream_t stream);
 

@@ -1,5 +1,7 @@
 """One-shot check of the tcgen05 / TMEM pass A of hnsw_exact_knn_tf32 (tuning key "exact_tcgen05") against the FFMA scan:
-ids and distance bits must be identical.  Run under `timeout` on a B200.  Prints one JSON line."""
+ids and distance bits must be identical.  Run under `timeout` on a B200.  Prints two JSON lines.
+Usage: python tools/exact_tcgen05_check.py [mode]   (mode 1 = the default tcgen05 kernel, 2 = the experimental
+warp-specialised one, see csrc/exact_tf32_kernels.cu)"""
 import json
 import sys
 import time
@@ -16,7 +18,8 @@ ge.build()
 import hnswindex  # noqa: E402
 from hnswindex.bindings import lib  # noqa: E402
 
-out = {"cases": [], "ok": True}
+MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+out = {"mode": MODE, "cases": [], "ok": True}
 rng = np.random.default_rng(21)
 for metric, dim, n in (("sq_euclid", 128, 5000), ("cosine", 100, 5000), ("ucosine", 96, 5000), ("euclid", 64, 5000), ("sq_euclid", 3, 2000),
                        ("sq_euclid", 128, 37)):
@@ -32,7 +35,7 @@ for metric, dim, n in (("sq_euclid", 128, 5000), ("cosine", 100, 5000), ("ucosin
     ix.add(data)
     if n >= 2000:
         ix.remove(np.arange(0, n, 7, dtype=np.int32))
-    ix.set_tuning("exact_tcgen05", 1)
+    ix.set_tuning("exact_tcgen05", MODE)
     for k in (1, 10):
         sup = lib.hnsw_exact_tcgen05_supported(dim, k)
         a_ids, a_d = ix.exact_knn(q, k)
@@ -56,7 +59,7 @@ ix.add(x[:n])
 q = x[n:]
 res = {}
 ref = None
-for name, tc, t5 in (("scan", False, 0), ("mma_sync", True, 0), ("tcgen05", True, 1)):
+for name, tc, t5 in (("scan", False, 0), ("mma_sync", True, 0), ("tcgen05", True, MODE)):
     ix.set_tuning("exact_tcgen05", t5)
     ix.exact_knn(q[:128], 10, tensor_cores=tc)
     best = 1e9
