@@ -81,6 +81,10 @@ int hnsw_add(hnsw_handle handle, const float* vectors, int count, int dim, int* 
     if (!handle) return 0;
     HNSW_TRY
     if (vectors == nullptr || count <= 0 || dim <= 0) return 0;
+    if (outIds == nullptr) {  // (the reference would fault here; the ids are simply not reported)
+        std::vector<int> ids((size_t)count);
+        return get(handle)->add(vectors, count, dim, ids.data());
+    }
     return get(handle)->add(vectors, count, dim, outIds);
     HNSW_CATCH(-1)
 }
@@ -302,12 +306,14 @@ int hnsw_set_stream(hnsw_handle handle, void* cudaStream) {
 }
 int hnsw_exact_knn(hnsw_handle handle, const float* queries, int count, int dim, int k, int* outIds, float* outDists) {
     HNSW_TRY
+    if (count > 0 && (queries == nullptr || outIds == nullptr || outDists == nullptr)) throw std::invalid_argument("null buffer");
     get(handle)->exact_knn(queries, count, dim, k, outIds, outDists);
     return 0;
     HNSW_CATCH(-1)
 }
 int hnsw_exact_knn_tf32(hnsw_handle handle, const float* queries, int count, int dim, int k, int* outIds, float* outDists, int* outFallbacks) {
     HNSW_TRY
+    if (count > 0 && (queries == nullptr || outIds == nullptr || outDists == nullptr)) throw std::invalid_argument("null buffer");
     const int fb = get(handle)->exact_knn_tf32(queries, count, dim, k, outIds, outDists);
     if (outFallbacks) *outFallbacks = fb;
     return 0;
