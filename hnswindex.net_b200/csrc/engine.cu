@@ -170,9 +170,12 @@ void Index::ensure_dim(int dim) {
 
 // GraphData.cs:98-111: Capacity doubles whenever Length exceeds it
 void Index::ensure_capacity(int needed) {
-    while (needed > capacity_) capacity_ *= 2;
-    if (capacity_ <= dev_capacity_) return;
-    const size_t o = (size_t)dev_capacity_, n = (size_t)capacity_;
+    if (needed > (1 << 30)) throw std::runtime_error("the index cannot hold more than 2^30 items");
+    int cap = std::max(1, capacity_);
+    while (needed > cap) cap *= 2;
+    if (cap <= dev_capacity_) { capacity_ = cap; return; }
+    // capacity_ / dev_capacity_ only change once every array has grown: a failed allocation leaves the index as it was
+    const size_t o = (size_t)dev_capacity_, n = (size_t)cap;
     grow_device(d_vectors_, o * pitch_, n * pitch_, 0, stream_);
     if (metric_ == COSINE) grow_device(d_norms_, o, n, 0, stream_);
     grow_device(d_adj0_, o * stride0_, n * stride0_, 0xFF, stream_);
@@ -180,7 +183,8 @@ void Index::ensure_capacity(int needed) {
     grow_device(d_locks_, o, n, 0, stream_);
     grow_device(d_rm_index_, o, n, 0xFF, stream_);
     grow_device(d_levels_, o, n, 0, stream_);
-    dev_capacity_ = capacity_;
+    capacity_ = cap;
+    dev_capacity_ = cap;
 }
 
 void Index::ensure_upper_rows(int needed) {

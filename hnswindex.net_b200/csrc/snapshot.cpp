@@ -455,7 +455,31 @@ void read_snapshot(const std::string& path, HostGraph& g) {
     const int nactive = n - (int)removed_nodes.size();
     if (count_field != 0 && count_field != nactive) throw std::runtime_error("snapshot: Count does not match the number of active nodes");
     if (g.capacity < n) g.capacity = std::max(n, p.CollectionSize);
-    if (nactive > 0 && (g.entry < 0 || g.entry >= n)) throw std::runtime_error("snapshot: EntryPointId out of range");
+    if (g.capacity > (1 << 30)) throw std::runtime_error("snapshot: Capacity is not a plausible collection size");
+    // EntryPointId: -1 (empty index) or a live slot -- checked whether or not any node is active: the engine indexes its
+    // per-node arrays with it
+    if (g.entry < -1 || g.entry >= n) throw std::runtime_error("snapshot: EntryPointId out of range");
+    if (nactive > 0 && g.entry < 0) throw std::runtime_error("snapshot: EntryPointId out of range");
+    if (g.entry >= 0 && !g.removed.empty() && g.removed[g.entry]) throw std::runtime_error("snapshot: the entry point is a removed node");
+    // ActiveNodes: live slots, each once
+    if (!g.active.empty()) {
+        std::vector<unsigned char> seen((size_t)n, 0);
+        for (int id : g.active) {
+            if (id < 0 || id >= n || seen[id] || (!g.removed.empty() && g.removed[id])) throw std::runtime_error("snapshot: inconsistent ActiveNodes");
+            seen[id] = 1;
+        }
+    }
+    // RemovedIndexes is the free-slot stack Add pops from (GraphData.cs:84-91): every entry must be a removed slot of this
+    // file, each exactly once, and every removed slot must be on it -- otherwise a later Add would write outside the arrays
+    // or hand one slot to two items
+    if (g.removed_stack.size() != removed_nodes.size()) throw std::runtime_error("snapshot: RemovedIndexes and IsRemoved flags disagree");
+    {
+        std::vector<unsigned char> seen((size_t)n, 0);
+        for (int id : g.removed_stack) {
+            if (id < 0 || id >= n || !g.removed[id] || seen[id]) throw std::runtime_error("snapshot: inconsistent RemovedIndexes");
+            seen[id] = 1;
+        }
+    }
     for (int v : g.adj0) if (v >= n) throw std::runtime_error("snapshot: edge to a node that does not exist");
     for (int v : g.adjU) if (v >= n) throw std::runtime_error("snapshot: edge to a node that does not exist");
 }
