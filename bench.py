@@ -276,6 +276,15 @@ def run_b200(args):
     _, _, kms = timed(step_resident, args.steps, args.warmup, collect_kernel_ms=True)   # the same launches, timed one by one
     e2e_dev_ms, e2e_wall_ms, _ = timed(step_e2e, args.steps, args.warmup)
 
+    # ---- N > 1: the partitioned mode (BASELINE config C4) on the same ranks, as a sub-record of this line
+    part = None
+    if world > 1 and not args.no_partitioned:
+        try:
+            part = partitioned_pass(args, steps=min(args.steps, 20), warmup=3)
+        except Exception as e:   # the headline line must still be printed; the failure is reported in its place
+            part = {"error": f"{type(e).__name__}: {e}"[:500]}
+            log(f"[bench] rank {rank}: partitioned pass failed: {e}")
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -352,6 +361,8 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "wall_ms_per_step": round(wall_ms / args.steps, 4),
     }
+    if part is not None:
+        line["partitioned"] = part
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -435,28 +446,23 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------- partitioned mode (C4)
-def run_partitioned(args):
-    """BASELINE config C4: 1.25M x 96 ucosine per GPU (10M over 8), every rank searches ALL queries on its own
-    sub-graph, per-rank top-k lists are exchanged with one NCCL all-gather and merged (K7).  Not the headline
-    metric: a second workload, printed with its own metric name."""
+def partitioned_pass(args, steps, warmup, per_rank=None, nq=None):
+    """BASELINE config C4 (10M x 96 ucosine over 8 GPUs = 1.25M per GPU): every rank owns one sub-graph and searches ALL
+    queries on it; the per-rank top-k lists are exchanged and merged.  Two exchanges are timed on the same sub-graphs:
+      fused      the search kernel's epilogue stores every query's top-k into every peer's gather buffer (CUDA IPC pointers,
+                 NVLink stores) + flags; ONE wait+merge kernel follows in stream order -- no collective
+      allgather  search -> NCCL all_gather of ids and distances -> merge kernel
+    All times are CUDA-event times on the stream the kernels run on, max over ranks.  The process group must be initialised
+    (world > 1) and the device set.  Returns the record on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
+    import hnswindex
+    from hnswindex import partitioned as P
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import __graft_entry__ as ge
-    if rank == 0:
-        ge.build()
-    if world > 1:
-        dist.barrier()
-    import hnswindex
-    from hnswindex import bindings as hb
-    from hnswindex import partitioned as P
-    hb.set_device(local)
-    dim, rank_lr, k, per_rank, nq = 96, 16, 10, args.n_per_rank, args.nq
+    dim, rank_lr, k = 96, 16, 10
+    per_rank = per_rank or args.n_per_rank
+    nq = nq or args.nq
     total = per_rank * world
     rng = np.random.default_rng(99)
     A = rng.standard_normal((rank_lr, dim)).astype(np.float32)
@@ -475,7 +481,10 @@ def run_partitioned(args):
     ix = hnswindex.Index(dim, "ucosine")
     ix.set_collection_size(e0 - s0); ix.set_max_edges(16); ix.set_max_candidates(200); ix.set_allow_removals(False)
     tb = time.time(); ix.add(shard); build_s = time.time() - tb
+    build_kernel_ms = ix.stats()["last_build_ms"]
     del shard
+    stream = torch.cuda.current_stream()
+    ix.set_stream(stream.cuda_stream)
     pix = P.PartitionedIndex(rank, world, total, index=ix)
     # ground truth: exact top-k per shard, merged the same way
     ns = min(1000, nq)
@@ -488,80 +497,113 @@ def run_partitioned(args):
         ix.set_min_nn(cand)
         r = recall_at_k(pix.knn_query(queries[:ns], k)[0], truth)
         if rank == 0:
-            log(f"  ef={cand}: recall@10={r:.4f}")
+            log(f"  [partitioned] ef={cand}: recall@10={r:.4f}")
         if r >= 0.95:
             ef = cand
             break
     ix.set_min_nn(ef or EF_GRID[-1])
     q_dev = torch.from_numpy(queries).cuda()
 
-    def timed(fn):
-        for i in range(args.warmup):
+    def timed(fn, end=None):
+        for i in range(warmup):
             fn()
+        if end:
+            end()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t = time.perf_counter()
-        for i in range(args.steps):
-            fn()
         torch.cuda.synchronize()
-        el = time.perf_counter() - t
-        tt = torch.tensor([el], dtype=torch.float64, device="cuda")
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t = time.perf_counter()
+        e0_.record(stream)
+        for i in range(steps):
+            fn()
+        e1_.record(stream)
+        if end:
+            end()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t
+        tt = torch.tensor([e0_.elapsed_time(e1_), wall * 1e3], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+        return float(tt[0].item()) / steps, float(tt[1].item()) / steps      # ms per batch: device, wall
     # (0) the local search alone (no exchange, no merge): what the exchange is measured against
     ids_loc = torch.empty((nq, k), dtype=torch.int32, device="cuda")
     d_loc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-    el_search = timed(lambda: ix.knn_query_device(q_dev.data_ptr(), nq, k, ids_loc.data_ptr(), d_loc.data_ptr()))
+    #     queued back to back on ONE stream exactly like the fused batches below (no host wait between batches, no two-stream
+    #     tail overlap), so that the difference is the exchange + merge and nothing else
+    ix.set_tuning("async_overlap", 0)
+    ms_search, _ = timed(lambda: ix.knn_query_device_async(q_dev.data_ptr(), nq, k, ids_loc.data_ptr(), d_loc.data_ptr()), end=ix.synchronize)
+    ix.set_tuning("async_overlap", 1)
     # (a) NCCL path: search, all-gather of the per-rank top-k, merge kernel -- queries resident on the device
-    el_gather = timed(lambda: pix.knn_query_device(q_dev, k))
-    ref_ids = pix.knn_query_device(q_dev, k)[0].cpu().numpy()
-    # (b) fused path: the search kernel's epilogue stores into every peer's buffer (CUDA IPC / NVLink), no collective
+    ms_gather, _ = timed(lambda: pix.knn_query_device(q_dev, k))
+    ref_ids, ref_d = [x.cpu().numpy() for x in pix.knn_query_device(q_dev, k)]
+    # (b) fused path, batches queued back to back on the stream (results stay on the device; one host wait at the end)
     pix.enable_fused(nq, k)
-    el_fused_sync = timed(lambda: pix.knn_query_device(q_dev, k))
-    # the same with the batches queued back to back on the stream (results stay on the device; one host wait at the end)
-    def queued():
-        pix.knn_query_device(q_dev, k, sync=False)
-    for i in range(args.warmup):
-        queued()
-    pix.sync()
-    if world > 1:
-        dist.barrier()
-    t = time.perf_counter()
-    for i in range(args.steps):
-        queued()
-    pix.sync()
-    tt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    el = float(tt.item())
-    same = bool(np.array_equal(pix.knn_query_device(q_dev, k)[0].cpu().numpy(), ref_ids))
+    ms_fused, _ = timed(lambda: pix.knn_query_device(q_dev, k, sync=False), end=pix.sync)
+    ms_fused_sync, _ = timed(lambda: pix.knn_query_device(q_dev, k))          # a host wait per batch
+    f_ids, f_d = [x.cpu().numpy() for x in pix.knn_query_device(q_dev, k)]
+    same = bool(np.array_equal(f_ids, ref_ids) and np.array_equal(f_d.view(np.uint32), ref_d.view(np.uint32)))
     q_pin = torch.from_numpy(queries).pin_memory()
 
     def step_e2e():                                       # pinned host queries in, host results out
         ids, d = pix.knn_query_device(q_pin.to("cuda", non_blocking=True), k)
         return ids.cpu(), d.cpu()
-    el_e2e = timed(step_e2e)
-    r = recall_at_k(pix.knn_query(queries[:ns], k)[0], truth)
+    _, ms_e2e_wall = timed(step_e2e)
+    r = recall_at_k(f_ids[:ns], truth)
+    same_all = torch.tensor([1 if same else 0], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(same_all, op=dist.ReduceOp.MIN)
     pix.disable_fused()
+    ix.set_stream(0)
+    del pix, ix
+    if rank != 0:
+        return None
+    return {
+        "workload": f"C4: {total} x {dim} fp32 ucosine (rank-16 + 0.25 noise, L2-normalised) in {world} sub-graphs of {per_rank}, "
+                    f"{nq} queries seen by every rank, k={k}, ef={ef}; every rank ends with the merged global top-k",
+        "qps_fused": round(nq / (ms_fused / 1e3), 1), "qps_allgather": round(nq / (ms_gather / 1e3), 1),
+        "qps_fused_host_wait_per_batch": round(nq / (ms_fused_sync / 1e3), 1),
+        "local_search_ms": round(ms_search, 4), "fused_ms": round(ms_fused, 4), "allgather_ms": round(ms_gather, 4),
+        "exchange_plus_merge_ms": round(ms_fused - ms_search, 4), "allgather_exchange_plus_merge_ms": round(ms_gather - ms_search, 4),
+        "fused_equals_allgather": bool(int(same_all.item()) == 1), "recall_at_10": round(r, 4), "ef": ef,
+        "e2e_qps": round(nq / (ms_e2e_wall / 1e3), 1), "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 8,
+        "build_s_per_shard": round(build_s, 2), "build_kernel_inserts_per_s_per_gpu": round((e0 - s0) / (build_kernel_ms / 1e3)),
+        "steps": steps, "warmup": warmup, "timing": "CUDA events on the stream of the kernels, max over ranks",
+        "exchange": "search-kernel epilogue stores into every peer's gather buffer (CUDA IPC pointers over NVLink) + flag, "
+                    "one wait+merge kernel; no collective",
+        "gpu_launches_per_step": 2,
+        "l2_policy": f"inputs larger than L2: {per_rank * (dim * 4 + 128) / 1e6:.0f} MB sub-graph per GPU vs 126 MB L2"}
+
+
+def run_partitioned(args):
+    """`--mode partitioned`: the C4 pass alone, printed as its own line (secondary workload, own metric name)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
     if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from hnswindex import bindings as hb
+    hb.set_device(local)
+    rec = partitioned_pass(args, args.steps, args.warmup)
+    if rank == 0:
+        nq = args.nq
         print(json.dumps({
             "metric": "QPS at recall@10>=0.95, partitioned index (C4: 1.25M x 96 ucosine per GPU, search fused with the peer-store exchange of top-k)",
-            "value": round(nq * args.steps / el, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(el / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"C4: {total} x {dim} fp32 ucosine (rank-16 + 0.25 noise, L2-normalised) in {world} sub-graphs of {per_rank}, "
-                                   f"{nq} queries seen by every rank, k={k}, ef={ef}; every rank ends with the merged global top-k",
-                       "recall_at_10": round(r, 4), "ef": ef, "build_s_per_shard": round(build_s, 2),
-                       "exchange": "search-kernel epilogue stores into every peer's gather buffer (CUDA IPC pointers over NVLink) + flag, "
-                                   "wait kernel, merge kernel; no collective",
-                       "local_search_only_ms": round(el_search / args.steps * 1e3, 4),
-                       "fused_with_host_sync_per_batch_qps": round(nq * args.steps / el_fused_sync, 1),
-                       "nccl_allgather_path_qps": round(nq * args.steps / el_gather, 1), "fused_equals_allgather_results": same,
-                       "l2_policy": f"inputs larger than L2: {per_rank * (dim * 4 + 128) / 1e6:.0f} MB sub-graph per GPU vs 126 MB L2"},
-            "e2e": {"value": round(nq * args.steps / el_e2e, 1), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 8},
-            "gpu_launches": int(args.steps * 3)}), flush=True)
+            "value": rec["qps_fused"], "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": rec["fused_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": rec,
+            "e2e": {"value": rec["e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": rec["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": rec["d2h_bytes_per_step"]},
+            "gpu_launches": int(args.steps * 2)}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -678,6 +720,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="replicated mode: c2 (the metric's config) or c3")
     ap.add_argument("--build-sample", type=int, default=400_000, help="build mode: nodes the CPU oracle builds (bounded sample, ~10-15 s on 16 cores)")
     ap.add_argument("--n-per-rank", type=int, default=1_250_000)
+    ap.add_argument("--no-partitioned", action="store_true", help="N > 1: skip the partitioned-index (C4) sub-record")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup

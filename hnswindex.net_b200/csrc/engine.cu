@@ -126,6 +126,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "async_overlap") tuning_.async_overlap = value;
     else if (key == "build_overlap") tuning_.build_overlap = value;
     else if (key == "exact_tcgen05") tuning_.exact_tcgen05 = value;
+    else if (key == "peer_timeout_ms") tuning_.peer_timeout_ms = std::max(1, value);
     else if (key == "remove_batch_max") remove_batch_max_ = std::max(1, value);
     else if (key == "remove_batch_ratio") remove_batch_ratio_ = std::max(1, value);
     else throw std::invalid_argument("unknown tuning key: " + key);
@@ -741,9 +742,8 @@ void Index::wait_and_merge(const unsigned* d_flags, int world, unsigned epoch, c
         std::lock_guard<std::mutex> lock(mu_);
         HNSW_CUDA_CHECK(cudaSetDevice(device_));
         int* d_err = reinterpret_cast<int*>(d_counters_ + 7);
-        launch_wait_flags(d_flags, world, epoch, d_err, stream_);
-        launch_merge_topk(d_in_ids, d_in_dists, world, count, k, d_out_ids, d_out_dists, stream_);
-        stats_.search_launches += 2;
+        launch_wait_merge(d_flags, world, epoch, tuning_.peer_timeout_ms, d_err, d_in_ids, d_in_dists, count, k, d_out_ids, d_out_dists, stream_);
+        stats_.search_launches += 1;
     }
     if (sync) partition_sync();
 }
@@ -758,7 +758,9 @@ void Index::partition_sync() {
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
     if (err != 0) {
         HNSW_CUDA_CHECK(cudaMemset(d_err, 0, sizeof(int)));
-        throw std::runtime_error("partitioned query: a peer GPU did not deliver its results in time");
+        throw std::runtime_error("partitioned query: a peer GPU did not deliver its results within " + std::to_string(tuning_.peer_timeout_ms) +
+                                 " ms (tuning key peer_timeout_ms); the outputs of the affected batches are -1 / NaN and the exchange "
+                                 "must be set up again (enable_fused + barrier) before the next fused query");
     }
 }
 

@@ -21,6 +21,8 @@ struct Tuning {
     int blocks_per_sm = 0;    // 0 = occupancy query
     int exact_tcgen05 = 1;    // exact_knn_tf32: pass A on tcgen05 / TMEM where the shape allows (rows <= 128 floats), else mma.sync;
                               // 2 = experimental warp-specialised tcgen05 kernel, 0 = always mma.sync
+    int peer_timeout_ms = 10000;  // partitioned index: how long the wait+merge kernel waits for a peer GPU's results before it
+                                  // gives up (error + poisoned outputs).  Wall time; raise it for very large / high-ef batches
     int flags = 2;            // bit 0: L2-prefetch rows of accepted candidates (no gain); bit 1: guess-row load
 };
 
@@ -111,8 +113,11 @@ struct ScatterArgs {
 };
 void launch_knn_scatter(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, const ScatterArgs& sc,
                         unsigned* d_work_counter, unsigned* d_done_counter, const Tuning& t, cudaStream_t stream);
-// one warp spins (bounded) until d_flags[0..world) have all reached `epoch`; *d_error = 1 on timeout
-void launch_wait_flags(const unsigned* d_flags, int world, unsigned epoch, int* d_error, cudaStream_t stream);
+// wait (bounded by timeout_ms of wall time) until d_flags[0..world) have all reached `epoch`, then merge the gather buffer
+// in_* [world][nq][k] into out_* [nq][k] -- one kernel.  On timeout (or when *d_error is already set) *d_error = 1 and
+// every output row is -1 / NaN.
+void launch_wait_merge(const unsigned* d_flags, int world, unsigned epoch, int timeout_ms, int* d_error, const int* d_in_ids,
+                       const float* d_in_dists, int nq, int k, int* d_out_ids, float* d_out_dists, cudaStream_t stream);
 
 // K7: merge `parts` sorted top-k lists per query: in_* are [parts][nq][k], out_* [nq][k]
 void launch_merge_topk(const int* d_in_ids, const float* d_in_dists, int parts, int nq, int k, int* d_out_ids, float* d_out_dists,

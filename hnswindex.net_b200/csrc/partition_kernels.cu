@@ -6,7 +6,7 @@
 // of query i+1 and no collective is launched.  Completion is signalled with one flag per (peer, source rank):
 //   every warp:   result stores to all peers -> __threadfence_system() -> atomicAdd(done)
 //   last warp:    flags[peer][rank] = epoch  (system-scope release) for every peer
-//   wait kernel:  spins (bounded) until flags[rank][*] >= epoch (acquire), then the merge kernel runs in stream order.
+//   wait+merge:   one kernel, every warp polls flags[rank][*] >= epoch (acquire, wall-clock deadline), then merges its query.
 // Buffers are double-buffered by epoch parity; a rank cannot run two epochs ahead of a peer because each epoch's wait
 // needs that peer's flag of the same epoch, which the peer raises only after finishing the previous epoch's merge
 // (stream order).
@@ -82,22 +82,80 @@ knn_scatter_kernel(GraphView g, const float* __restrict__ queries, int nq, int k
     }
 }
 
-// One warp: lane p waits for rank p's flag of this epoch.  Bounded: a peer that never arrives sets *error instead of
-// hanging the GPU.
-__global__ void wait_flags_kernel(const unsigned* flags, int world, unsigned epoch, int* error) {
-    const int lane = threadIdx.x;
-    if (lane < world) {
-        const volatile unsigned* f = flags + lane;
-        unsigned spins = 0;
-        while ((int)(*f - epoch) < 0) {  // a fast peer may already have raised the next epoch
-            __nanosleep(200);
-            if (++spins > (1u << 24)) {  // ~ 3+ s
-                atomicExch(error, 1);
-                break;
-            }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Wait + merge in ONE kernel, one warp per query: lane p polls rank p's flag of this epoch (acquire, system scope) until it
+// arrives or `timeout_ns` of wall time have passed (%globaltimer: independent of clocks and of how long a poll takes), then
+// the warp merges the `world` sorted top-k lists of its query straight out of the gather buffer (peer stores land in this
+// GPU's L2; they are read past L1) -- no separate wait, pack and merge launches, no scratch allocation per batch.
+// A peer that never arrives does not hang the GPU and does not leak stale data: *error is set and every output row of the
+// batch is poisoned (-1 / NaN).  Once *error is set, later batches poison immediately instead of waiting again: after a
+// timeout the epoch protocol is out of step (the late peer may still write into a buffer parity the waiter has moved past)
+// and the exchange has to be set up again (PartitionedIndex.enable_fused + barrier).
+__global__ void __launch_bounds__(kThreads)
+wait_merge_kernel(const unsigned* flags, int world, unsigned epoch, unsigned long long timeout_ns, int* error, const int* in_ids,
+                  const float* in_dists, int nq, int k, int* __restrict__ out_ids, float* __restrict__ out_dists) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kWarpsPerBlock + warp;
+    if (q >= nq) return;
+    bool ok = *reinterpret_cast<volatile int*>(error) == 0;
+    if (ok && lane < world) {
+        const unsigned* f = flags + lane;
+        const unsigned long long t0 = global_ns();
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - epoch) >= 0) break;  // a fast peer may already have raised the next epoch
+            if (global_ns() - t0 > timeout_ns) { ok = false; break; }
+            __nanosleep(100);
         }
     }
-    __threadfence_system();
+    ok = __all_sync(FULL, ok);
+    if (!ok) {
+        if (lane == 0) atomicExch(error, 1);
+        for (int j = lane; j < k; j += 32) {
+            out_ids[(size_t)q * k + j] = -1;
+            out_dists[(size_t)q * k + j] = CUDART_NAN_F;
+        }
+        return;
+    }
+    u64* list = reinterpret_cast<u64*>(smem) + (size_t)warp * k;
+    BeamState st;
+    st.n = 0; st.ef = k; st.cursor = 0; st.far_ord = 0xFFFFFFFFu;
+    const int total = world * k;
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        u64 mykey = ~0ull;
+        if (i < total) {
+            const int p = i / k, j = i - p * k;
+            const size_t at = ((size_t)p * nq + q) * k + j;
+            const int id = __ldcg(in_ids + at);
+            if (id >= 0) mykey = make_key(__ldcg(in_dists + at), id);
+        }
+        bool pending = mykey != ~0ull;
+        for (;;) {
+            const bool want = pending && (st.n < k || mykey < list[k - 1]);
+            const unsigned mk = __ballot_sync(FULL, want);
+            if (!mk) break;
+            const int src = __ffs(mk) - 1;
+            const u64 kn = __shfl_sync(FULL, mykey, src);
+            if (lane == src) pending = false;
+            list_insert(list, st, kn, lane);
+        }
+    }
+    __syncwarp();
+    for (int j = lane; j < k; j += 32) {
+        int id = -1;
+        float d = CUDART_NAN_F;
+        if (j < st.n) { id = key_id(list[j]); d = key_dist(list[j]); }
+        out_ids[(size_t)q * k + j] = id;
+        out_dists[(size_t)q * k + j] = d;
+    }
 }
 
 template <typename Kern>
@@ -139,8 +197,19 @@ void launch_knn_scatter(int metric, const GraphView& g, const float* d_queries, 
     HNSW_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_wait_flags(const unsigned* d_flags, int world, unsigned epoch, int* d_error, cudaStream_t stream) {
-    wait_flags_kernel<<<1, 32, 0, stream>>>(d_flags, world, epoch, d_error);
+void launch_wait_merge(const unsigned* d_flags, int world, unsigned epoch, int timeout_ms, int* d_error, const int* d_in_ids,
+                       const float* d_in_dists, int nq, int k, int* d_out_ids, float* d_out_dists, cudaStream_t stream) {
+    if (nq <= 0) return;
+    if (world < 1 || world > 32) throw std::invalid_argument("wait_merge: world size out of range");
+    static size_t optin = 0;
+    const size_t msmem = (size_t)kWarpsPerBlock * k * 8;
+    if (msmem > optin) {
+        HNSW_CUDA_CHECK(cudaFuncSetAttribute(wait_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+        optin = msmem;
+    }
+    const unsigned long long timeout_ns = (unsigned long long)std::max(1, timeout_ms) * 1000000ull;
+    wait_merge_kernel<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, msmem, stream>>>(d_flags, world, epoch, timeout_ns, d_error, d_in_ids,
+                                                                                              d_in_dists, nq, k, d_out_ids, d_out_dists);
     HNSW_CUDA_CHECK(cudaGetLastError());
 }
 

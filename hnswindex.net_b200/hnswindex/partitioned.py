@@ -149,6 +149,9 @@ class PartitionedIndex:
         import ctypes as ct
         from . import bindings as hb
         f = self._fused
+        if f.get("broken"):
+            raise RuntimeError("fused partitioned query: a peer timed out earlier and the epoch protocol is out of step; "
+                               "call disable_fused() and enable_fused() on ALL ranks before the next fused query")
         if nq > f["nq_max"] or k != f["k"]:
             raise ValueError("fused partitioned query: batch larger than the buffers of enable_fused(), or a different k")
         f["epoch"] += 1
@@ -165,15 +168,26 @@ class PartitionedIndex:
             sc.flags[p] = ct.cast(ct.c_void_p(f["base"][p] + f["flags_off"]), ct.POINTER(ct.c_uint))
         hb._check(hb.lib.hnsw_knn_query_scatter(self.index._h, ct.c_void_p(q_dev.data_ptr()), nq, self.index.dim, k, ct.byref(sc)))
         fn = hb.lib.hnsw_wait_and_merge_device if sync else hb.lib.hnsw_wait_and_merge_device_async
-        hb._check(fn(self.index._h, ct.c_void_p(f["own"] + f["flags_off"]), self.world, f["epoch"],
-                     ct.c_void_p(f["own"] + ids_off), ct.c_void_p(f["own"] + d_off), nq, k,
-                     ct.c_void_p(f["out_ids"].data_ptr()), ct.c_void_p(f["out_d"].data_ptr())))
+        rc = fn(self.index._h, ct.c_void_p(f["own"] + f["flags_off"]), self.world, f["epoch"],
+                ct.c_void_p(f["own"] + ids_off), ct.c_void_p(f["own"] + d_off), nq, k,
+                ct.c_void_p(f["out_ids"].data_ptr()), ct.c_void_p(f["out_d"].data_ptr()))
+        if rc < 0:
+            f["broken"] = True      # a peer never delivered: outputs are -1 / NaN, the exchange must be re-established
+            hb._check(rc)
         return f["out_ids"][:nq], f["out_d"][:nq]
 
     def sync(self) -> None:
         """Wait for the batches queued with knn_query_device(..., sync=False); raises if a peer never delivered."""
         from . import bindings as hb
-        hb._check(hb.lib.hnsw_partition_sync(self.index._h))
+        rc = hb.lib.hnsw_partition_sync(self.index._h)
+        if rc < 0 and self._fused is not None:
+            self._fused["broken"] = True
+        hb._check(rc)
+
+    def set_peer_timeout_ms(self, ms: int) -> None:
+        """How long the wait+merge kernel waits (wall time, on the device) for a peer GPU before it gives up: the batch's
+        outputs become -1 / NaN, sync() raises, and the exchange has to be re-established.  Default 10 s."""
+        self.index.set_tuning("peer_timeout_ms", int(ms))
 
     def knn_query_device(self, q_dev, k: int, sync: bool = True):
         """Queries already on this GPU (torch tensor [nq, dim] fp32) -> merged (ids, dists) torch tensors on the GPU.

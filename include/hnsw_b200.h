@@ -181,8 +181,12 @@ HNSW_API int hnsw_merge_topk_device(const int* dInIds, const float* dInDists, in
  *   hnsw_ipc_open    map a peer's buffer (cudaIpcOpenMemHandle); hnsw_ipc_close / hnsw_ipc_free undo them
  *   hnsw_knn_query_scatter      stream-ordered, does not synchronise; ids[p] / dists[p] are [world][count][k], flags[p] is
  *                               [world] unsigned; p = 0..world-1 includes this rank's own buffer
- *   hnsw_wait_and_merge_device  waits (bounded, on the device) until all `world` flags of this rank reached `epoch`,
- *                               merges its gather buffer into [count][k], synchronises; -1 if a peer never arrived
+ *   hnsw_wait_and_merge_device  ONE kernel: waits on the device until all `world` flags of this rank reached `epoch` -- at most
+ *                               `peer_timeout_ms` of wall time (hnsw_set_tuning, default 10000) --, merges its gather buffer into
+ *                               [count][k], synchronises; -1 if a peer never arrived.  In that case every output row of the
+ *                               batch is -1 / NaN (never stale data), later batches fail at once instead of waiting again, and
+ *                               the exchange must be set up again on all ranks (fresh buffers, epoch 0, a barrier): the late
+ *                               peer may still write into a buffer parity the waiter has moved past.
  * Epochs must increase by one per query; alternate two gather buffers by epoch parity. */
 #define HNSW_MAX_PEERS 16
 typedef struct hnsw_scatter {

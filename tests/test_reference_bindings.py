@@ -133,7 +133,7 @@ data = rng.random((700, 96), dtype=np.float32); q = rng.random((200, 96), dtype=
 ix = hnswindex.Index(96, metric='cosine'); ix.set_max_candidates(64); ix.set_min_nn(20)
 ids = np.array([ix.add([v])[0] for v in data])
 ki, kd = ix.knn_query(q, 10)
-ri, rd = ix.range_query(q[:20], 0.12)
+ri, rd = ix.range_query(q[:20], 0.21)
 ix.remove(ids[:1])
 ki2, kd2 = ix.knn_query(q, 10)
 np.savez({str(out_npz)!r}, ids=ids, ki=ki, kd=kd, ki2=ki2, kd2=kd2, rn=np.array([len(x) for x in ri]),
@@ -148,7 +148,7 @@ np.savez({str(out_npz)!r}, ids=ids, ki=ki, kd=kd, ki2=ki2, kd2=kd2, rn=np.array(
     ix = hnswindex.Index(96, metric="cosine"); ix.set_max_candidates(64); ix.set_min_nn(20)
     ids = np.array([ix.add([v])[0] for v in data])
     ki, kd = ix.knn_query(q, 10)
-    ri, rd = ix.range_query(q[:20], 0.12)
+    ri, rd = ix.range_query(q[:20], 0.21)
     ix.remove(ids[:1])
     ki2, kd2 = ix.knn_query(q, 10)
     assert ref["ki"].dtype == np.int32 and ref["kd"].dtype == np.float32 and ref["ki"].shape == (200, 10)   # bindings.py:506-521

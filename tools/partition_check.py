@@ -27,10 +27,15 @@ def main():
     hb.set_device(local)
     dim, k, total, nq = 64, 10, 40000, 3000
     rng = np.random.default_rng(7)
-    data = rng.standard_normal((total, dim)).astype(np.float32)
-    data /= np.linalg.norm(data, axis=1, keepdims=True)
-    queries = rng.standard_normal((3, nq, dim)).astype(np.float32)
-    queries /= np.linalg.norm(queries, axis=2, keepdims=True)
+    # the bench's C4 recipe: rank-16 structure + 0.25 noise, rows L2-normalised -- low intrinsic dimension like
+    # the real Deep descriptors, so that ef = 64 reaches the recall the partitioned mode is expected to deliver
+    A = rng.standard_normal((16, dim)).astype(np.float32)
+
+    def gen(n):
+        x = rng.standard_normal((n, 16)).astype(np.float32) @ A + 0.25 * rng.standard_normal((n, dim)).astype(np.float32)
+        return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    data = gen(total)
+    queries = gen(3 * nq).reshape(3, nq, dim)
     s, e = P.shard_range(total, rank, world)
     ix = hnswindex.Index(dim, "ucosine")
     ix.set_collection_size(e - s); ix.set_allow_removals(False)
@@ -48,7 +53,7 @@ def main():
     # recall against brute force over the whole data set
     truth = np.argsort(-(queries[0][:200] @ data.T), axis=1)[:, :k]
     rec = np.mean([len(set(gathered[0][0][i]) & set(truth[i])) / k for i in range(200)])
-    assert rec > 0.75, rec   # unstructured 64-d Gaussian data at ef = 64; search quality itself is covered by the parity tests
+    assert rec > 0.9, rec
     pix.disable_fused()
     again = pix.knn_query(queries[1], k)      # back on the all-gather path
     assert np.array_equal(again[0], gathered[1][0])
