@@ -325,7 +325,15 @@ def run_b200(args):
                      "pipelined_algorithmic_GBps": round(alg * args.steps / (dev_ms / 1e3) / 1e9, 1)})
         prof = ROOT / "profiles" / "search_kernel_traffic.json"
         if prof.exists() and args.workload == "c2":
-            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            # ncu's DRAM bytes are only quoted while the kernel's machine code is the one that was captured
+            tj = json.load(open(prof))
+            have = ge._load_build_module().kernel_sass_stamp(tj.get("kernel_mangled", ""))
+            if have is not None and have == tj.get("kernel_sass_sha256") and ef <= 64:
+                roof["traffic"] = tj.get("dram_bytes_per_launch")
+                roof["traffic_source"] = f"{tj.get('source')}; kernel SASS sha256 {have[:16]} matches the library of this run"
+            else:
+                roof["traffic_stale"] = ("profiles/search_kernel_traffic.json was captured from different machine code (or at another "
+                                         "search width) than this run's kernel: no traffic figure")
         # CPU baseline (N=1 only): repeat the 10k batch until ~10 s of work (max 5 passes)
         t_cpu, passes = 0.0, 0
         while world == 1 and t_cpu < 10.0 and passes < 5:

@@ -20,7 +20,7 @@ OBJ = HERE / "build"
 OUT_DIR = HERE / "hnswindex" / "artifacts" / "native" / "linux-x64"
 OUT = OUT_DIR / "HNSWIndex.Native.so"
 
-SOURCES = ["search_kernels.cu", "build_kernels.cu", "exact_kernels.cu", "exact_tf32_kernels.cu", "range_kernels.cu", "remove_kernels.cu", "partition_kernels.cu", "engine.cu", "capi.cu", "snapshot.cpp"]
+SOURCES = ["search_kernels.cu", "wide_kernels.cu", "build_kernels.cu", "exact_kernels.cu", "exact_tf32_kernels.cu", "range_kernels.cu", "remove_kernels.cu", "partition_kernels.cu", "engine.cu", "capi.cu", "snapshot.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo",
@@ -72,6 +72,25 @@ def build(force=False, verbose=False):
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp_file.write_text(stamp)
     return OUT
+
+
+C2_SEARCH_KERNEL = "_ZN4hnsw17knn_search_kernelILi0ELb0ELi7EEEvNS_9GraphViewEPKfiiiiiiiPiPfPjPNS_10QueryStatsES6_i"
+
+
+def kernel_sass_stamp(mangled=C2_SEARCH_KERNEL):
+    """sha256 of one kernel's SASS inside the built library (addresses and encodings stripped): identifies the exact machine
+    code an ncu capture was taken from, independent of edits elsewhere in csrc/.  None when cuobjdump or the kernel is missing."""
+    import re
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not OUT.exists() or not Path(tool).exists():
+        return None
+    r = subprocess.run([tool, "-sass", "-fun", mangled, str(OUT)], capture_output=True, text=True)
+    if r.returncode != 0:
+        return None
+    ins = re.findall(r"/\*[0-9a-f]{4,}\*/\s+(.*?);", r.stdout)
+    if len(ins) < 100:
+        return None
+    return hashlib.sha256("\n".join(ins).encode()).hexdigest()
 
 
 if __name__ == "__main__":

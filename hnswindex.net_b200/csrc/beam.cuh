@@ -152,7 +152,8 @@ __device__ __forceinline__ void compute_staged(const GraphView& g, Stager& stg, 
 //   bit 2: the visited table holds 16-bit tags (vis16_test_and_set): every id of the index is below vis_size * 65536
 //   bit 3: the list never exceeds 1024 entries (ef <= 1024): the binary-search insertion path is dead code
 //   bit 5: the search kernel attaches an exact per-warp visited set in global memory behind the shared-memory table
-constexpr int kSpecShortRows = 1, kSpecSmallList = 2, kSpecVis16 = 4, kSpecMidList = 8, kSpecGvis = 32;
+//   bit 6: the list is wide.cuh's non-shifting WideList (sorted main array + 32 pending keys in registers), layer 0 only
+constexpr int kSpecShortRows = 1, kSpecSmallList = 2, kSpecVis16 = 4, kSpecMidList = 8, kSpecGvis = 32, kSpecWideList = 64;
 
 template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, const int* ids, float* out,

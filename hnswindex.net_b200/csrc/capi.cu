@@ -429,6 +429,14 @@ int hnsw_get_build_profile(hnsw_handle handle, unsigned long long* out16, int re
     return 0;
     HNSW_CATCH(-1)
 }
+int hnsw_get_wide_profile(hnsw_handle handle, unsigned long long* out16, int reset) {
+    HNSW_TRY
+    if (!out16) throw std::invalid_argument("null output");
+    HNSW_CUDA_CHECK(cudaSetDevice(get(handle)->device()));
+    wide_profile(out16, reset != 0);
+    return 0;
+    HNSW_CATCH(-1)
+}
 int hnsw_set_tuning(hnsw_handle handle, const char* key, int value) {
     HNSW_TRY
     get(handle)->set_tuning(key ? key : "", value);

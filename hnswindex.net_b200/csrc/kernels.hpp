@@ -21,6 +21,14 @@ struct Tuning {
     int blocks_per_sm = 0;    // 0 = occupancy query
     int exact_tcgen05 = 1;    // exact_knn_tf32: pass A on tcgen05 / TMEM where the shape allows (rows <= 128 floats), else mma.sync;
                               // 2 = experimental warp-specialised tcgen05 kernel, 0 = always mma.sync
+    int wl_min_ef = 256;      // one-warp-per-query searches with ef at or above this keep their candidates in wide.cuh's non-shifting
+                              // list (0 = never): the shifting list of beam.cuh costs O(ef / 32) chunk moves per accepted candidate
+    int wide_min_ef = 1024;    // layer-0 searches with ef = max(MinNN, k) at or above this run on the CTA-per-query kernel with the
+                              // non-shifting list (wide_kernels.cu); 0 = never
+    int wide_warps = 0;       // warps per CTA of that kernel: the leader + helpers (0 = 2, or 3 for rows of more than 32 neighbours)
+    int wide_prefetch = 1;    // its helper warps evaluate the likely next expansion ahead of time (speculative, never changes results)
+    int wide_max_small_batch = 4;  // calls with at most this many queries use the CTA-per-query kernel whatever ef is: one query alone
+                                   // is answered ~15 % sooner (177 vs 215 us of kernel time at ef = 48 on the 1M x 128 index)
     int peer_timeout_ms = 10000;  // partitioned index: how long the wait+merge kernel waits for a peer GPU's results before it
                                   // gives up (error + poisoned outputs).  Wall time; raise it for very large / high-ef batches
     int flags = 2;            // bit 0: L2-prefetch rows of accepted candidates (no gain); bit 1: guess-row load
@@ -40,6 +48,13 @@ int device_sm_count();
 void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
                        unsigned* d_work_counter, QueryStats* d_stats, uint32_t* d_gvis, size_t gvis_words, const Tuning& t,
                        cudaStream_t stream);
+
+// K2w: the same search with one CTA per query and a list that does not shift per insertion (wide_kernels.cu); layer 0 only.
+// launch_knn_search routes to it when wide_search_applies().
+bool wide_search_applies(const GraphView& g, int nq, int ef, int layer, const Tuning& t);
+void wide_profile(unsigned long long out[16], bool reset);  // leader-side cycle / speculation counters of K2w (current device)
+void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int* d_ids, float* d_dists,
+                     unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream);
 
 // MultiLayerKnnQuery (HNSWIndex.cs:173-187): out_* are [nq][top_l + 1][k], rows of layers below min_layer all padding,
 // each row the layer's sorted result without its first entry.

@@ -11,7 +11,7 @@
 #include <algorithm>
 #include <mutex>
 
-#include "beam.cuh"
+#include "wide.cuh"
 #include "kernels.hpp"
 #include "launch.hpp"
 
@@ -51,13 +51,21 @@ knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
         const int target = ANY_LAYER ? layer : 0;
         for (int l = g.top_layer; l > target; --l) greedy_layer<METRIC, SPEC>(g, s, qn, l, cur, cur_d, lane, wc);
 
-        BeamState st;
-        beam_search<METRIC, SPEC>(g, s, qn, target, cur, cur_d, ef, st, lane, wc, ANY_LAYER ? 0 : flags);
+        int found;
+        if ((SPEC & kSpecWideList) && !ANY_LAYER) {
+            WideList L;
+            beam_search_wl<METRIC, SPEC>(g, s, qn, cur, cur_d, ef, L, lane, wc, flags);
+            found = L.n;
+        } else {
+            BeamState st;
+            beam_search<METRIC, SPEC>(g, s, qn, target, cur, cur_d, ef, st, lane, wc, ANY_LAYER ? 0 : flags);
+            found = st.n;
+        }
 
         for (int j = lane; j < k; j += 32) {
             int id = -1;
             float d = CUDART_NAN_F;
-            if (j < st.n) {
+            if (j < found) {
                 const u64 e = s.list[j];
                 id = key_id(e);
                 d = key_dist(e);
@@ -159,7 +167,7 @@ int pick_vis_size(int requested, int ef) {
     if (requested > 0) return std::max(64, pow2_at_least(requested));
     // The table only saves re-evaluations; shared memory per warp decides how many searches an SM keeps in
     // flight, and the kernel is latency-bound: 4*ef slots (+9 % evaluations at C2) beat 16*ef (+2.5 %) by 9 %.
-    return std::min(4096, std::max(256, pow2_at_least(4 * ef)));
+    return std::min(32768, std::max(256, pow2_at_least(4 * ef)));
 }
 
 // Persistent launch shape: `warps` independent warps per block (4, fewer when one warp's scratch is large),
@@ -173,6 +181,10 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
                        unsigned* d_work_counter, QueryStats* d_stats, uint32_t* d_gvis, size_t gvis_words, const Tuning& t,
                        cudaStream_t stream) {
     if (nq <= 0) return;
+    if (wide_search_applies(g, nq, ef, layer, t)) {
+        launch_knn_wide(metric, g, d_queries, nq, k, ef, d_ids, d_dists, d_work_counter, d_stats, t, stream);
+        return;
+    }
     const int vis = pick_vis_size(t.vis_size_search, ef);
     // 16-bit tags hold two entries per word: for the mid-size lists the same filter fits half the words (more warps per SM)
     const int vis_mid = std::max(256, vis / 2);
@@ -185,6 +197,19 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
         int warps = 0;                                                                                                          \
         if (layer == 0 && g.pitch <= kSegFloats && ef <= 64 && (long long)g.count <= ((long long)vis << 16)) {                  \
             constexpr int S = kSpecShortRows | kSpecSmallList | kSpecVis16;                                                     \
+            const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
+            knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
+                g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);                  \
+        } else if (layer == 0 && t.wl_min_ef > 0 && ef >= t.wl_min_ef && g.pitch <= kSegFloats &&                               \
+                   (long long)g.count <= ((long long)vis_mid << 16)) {                                                          \
+            /* wide.cuh: sorted main array + 32 pending keys in registers, merged in one pass: no per-insertion shifting */    \
+            constexpr int S = kSpecShortRows | kSpecWideList | kSpecVis16;                                                      \
+            const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);                 \
+            knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                                \
+                g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);              \
+        } else if (layer == 0 && t.wl_min_ef > 0 && ef >= t.wl_min_ef && g.pitch > kSegFloats && t.vis_global_search <= 0 &&    \
+                   (long long)g.count <= ((long long)vis << 16)) {                                                              \
+            constexpr int S = kSpecWideList | kSpecVis16;                                                                       \
             const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
                 g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);                  \

@@ -1,0 +1,432 @@
+// wide_kernels.cu -- K2w: KnnQuery with a WIDE beam, one CTA per query.
+//
+// Replaces the same reference code as search_kernels.cu (HNSWIndex.cs:107-137, GraphNavigator.cs:39-82,194-256) for
+// ef = max(MinNN, k) from a few hundred up to ~16k.  The reference's heaps grow without bound (BinaryHeap.cs:109-113), so
+// any MinNN costs it the same per step; the one-warp-per-query kernel does not scale that way: its sorted list shifts
+// O(ef / 32) chunks per accepted candidate and one warp's list + visited table leave 2-3 warps per SM at ef = 4096.
+// Here one CTA holds ONE query's state (query vector, candidate list, visited table) once:
+//   * warp 0 (the leader) owns the control flow of GraphNavigator.SearchLayerQuery: pick the closest unexpanded entry,
+//     read its adjacency row, filter it through the visited table, insert the evaluated neighbours in stored order
+//     (wide.cuh: sorted main array + 32-entry pending buffer in registers, merged in one pass);
+//   * ALL warps evaluate the distances of one expansion: warp w stages and reduces rows [16w, 16w + 16) of the fresh
+//     neighbours (stage.cuh / metric.cuh, bit-exact), so a layer-0 row of 2M = 32 neighbours is one pass for two warps
+//     and a 64-neighbour row (M = 32) one pass for four;
+//   * while the leader inserts, the other warps pull the adjacency row of the entry most likely to be expanded next and
+//     the vectors it points at into L2 (prefetch only: the traversal itself is unchanged).
+// The order of every decision (strict d < far re-read after each insertion, stored order, first occurrence on ties) is the
+// one of beam.cuh, so results and the nexp / row_words counters are identical to the one-warp kernel and to the oracle.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "kernels.hpp"
+#include "wide.cuh"
+
+namespace hnsw {
+
+constexpr int kCmdEval = 0, kCmdSpec = 1, kCmdDone = 2;
+
+// Leader-side profile of the CTA-per-query kernel, summed over all queries since the last reset (SM cycles of the leader
+// warp; two atomics per counter per QUERY, so it is always on): hnsw_get_wide_profile().
+//   0 queries  1 expansions  2 speculations issued  3 speculations used  4 cyc descent  5 cyc select + filter
+//   6 cyc waiting for a speculation  7 cyc waiting for an on-demand evaluation  8 cyc insert  9 cyc beam loop total  10 merges
+__device__ unsigned long long g_wide_prof[16];
+
+struct WideCtrl {
+    unsigned qi;       // query handled by this CTA
+    int cmd;           // what the helper warps do next (kCmd*)
+    int m;             // kCmdEval: number of ids in the authoritative list
+    int node;          // kCmdSpec: the node whose expansion is evaluated ahead of time
+    int buf;           // kCmdSpec: which of the two speculative buffers to fill
+    int spec_node[2];  // filled by the helpers: node and list length of each speculative buffer
+    int spec_m[2];
+    int pad;
+};
+
+// shared memory of one CTA: [helpers' stagers][q][list][visited table][auth ids | auth dists | 2 x (spec ids | spec dists)][ctrl]
+__host__ __device__ inline size_t wide_smem_bytes(int warps, int pitch, int ef, int vis_size, int cand_cap) {
+    size_t b = (size_t)(warps - 1) * kStageBytes;
+    b += (size_t)((pitch + 3) & ~3) * 4;
+    b += (size_t)((ef + 1) & ~1) * 8;
+    b += (size_t)vis_size * 4;
+    b += (size_t)cand_cap * 4 * 6;
+    b += sizeof(WideCtrl);
+    return (b + 127) & ~(size_t)127;
+}
+
+// read-only look at the visited table (the helpers' speculative filter): would test_and_set call `id` fresh?
+template <bool VIS16>
+__device__ __forceinline__ bool vis_would_be_fresh(const uint32_t* vis, int vis_size, int vis_shift, int id) {
+    if (VIS16) {
+        const uint32_t z = (uint32_t)id * 0x9E3779B1u, tag = z & 0xFFFFu;
+        const uint32_t w = vis[(z >> 16) & (uint32_t)(vis_size - 1)];
+        return tag == 0u || !((w & 0xFFFFu) == tag || (w >> 16) == tag);
+    }
+    const uint32_t tag = (uint32_t)id + 1u;
+    const uint32_t b = (tag * 0x9E3779B1u) >> vis_shift;
+    return !(vis[2 * b] == tag || vis[2 * b + 1] == tag);
+}
+
+// Leader / helper pipeline (2..4 warps per CTA, one CTA per query):
+//   warp 0, the LEADER, takes every decision of GraphNavigator.SearchLayerQuery in the reference's order: closest unexpanded
+//   entry, its row filtered through the visited table (the only place the table is written), candidates inserted in stored
+//   order with far re-read after each one (wide.cuh);
+//   warps 1.., the HELPERS, evaluate distances.  While the leader inserts the candidates of expansion i, the helpers already
+//   evaluate expansion i+1 SPECULATIVELY: the leader names the entry that will be expanded next unless one of the pending
+//   candidates lands in front of it; the helpers read that node's row, filter it through the table read-only (nobody writes
+//   the table during an insertion phase, so they see exactly what the leader will see), stage the fresh rows and reduce the
+//   distances into one of two speculative buffers.  When the leader then selects that very node and its own -- authoritative,
+//   table-updating -- filter yields the same id list, the distances are already there; otherwise (wrong guess, or the lists
+//   differ) the helpers evaluate the authoritative list on demand.  Nothing speculative ever reaches the list or the
+//   table: results and counters are those of the one-warp kernels, only the latency of gather + reduction moves off the
+//   leader's critical path.
+// SPEC: kSpecShortRows (rows fit one staging segment), kSpecVis16 (16-bit visited tags); SPECULATE: evaluate ahead
+template <int METRIC, int SPEC, bool SPECULATE>
+__global__ void __launch_bounds__(kThreads)
+knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int vis_size, int cand_cap, int* __restrict__ out_ids,
+                float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5, H = W - 1;
+    constexpr bool vis16 = (SPEC & kSpecVis16) != 0;
+
+    unsigned char* p = smem;
+    Stager stg;  // helpers: their own staging buffer; the leader borrows helper 1's for the descent (the helpers are idle then)
+    stager_init(stg, p + (size_t)(warp == 0 ? 0 : warp - 1) * kStageBytes, lane);
+    p += (size_t)H * kStageBytes;
+    float* q = reinterpret_cast<float*>(p);
+    p += (size_t)((g.pitch + 3) & ~3) * 4;
+    u64* list = reinterpret_cast<u64*>(p);
+    p += (size_t)((ef + 1) & ~1) * 8;
+    uint32_t* vis = reinterpret_cast<uint32_t*>(p);
+    p += (size_t)vis_size * 4;
+    int* cand_id = reinterpret_cast<int*>(p);
+    float* cand_dist = reinterpret_cast<float*>(p + (size_t)cand_cap * 4);
+    int* spec_id0 = reinterpret_cast<int*>(p + (size_t)cand_cap * 8);
+    p += (size_t)cand_cap * 24;
+    WideCtrl* ctrl = reinterpret_cast<WideCtrl*>(p);
+    const int vis_shift = 32 - (31 - __clz(vis_size >> 1));
+
+    // the leader's view of the shared scratch for the warp-level primitives of beam.cuh
+    WarpScratch s;
+    s.stg = stg;
+    s.q = q;
+    s.list = list;
+    s.vis = vis;
+    s.cand_id = cand_id;
+    s.cand_dist = cand_dist;
+    s.vis_size = vis_size;
+    s.vis_shift = vis_shift;
+    s.cap = ef;
+    s.gvis = nullptr;
+    s.gvis_size = 0;
+    s.gvis_shift = 0;
+
+    for (;;) {
+        __syncthreads();  // the previous query is finished by every warp
+        if (threadIdx.x == 0) ctrl->qi = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const unsigned qi = ctrl->qi;
+        if (qi >= (unsigned)nq) break;
+        const float* qsrc = queries + (size_t)qi * g.dim;
+        for (int i = threadIdx.x; i < g.pitch; i += blockDim.x) q[i] = i < g.dim ? __ldg(qsrc + i) : 0.f;
+        for (int i = threadIdx.x; i < vis_size; i += blockDim.x) vis[i] = 0u;
+        __syncthreads();
+        double qn = 0.0;
+        if (METRIC == COSINE) qn = pair_norm_sqrt(q, g.dim, lane & 1);  // every warp computes the same value
+
+        if (warp != 0) {
+            // ---------------- helpers: serve commands until the query is done
+            for (;;) {
+                __syncthreads();  // (X) a command is published
+                const int cmd = ctrl->cmd;
+                if (cmd == kCmdDone) break;
+                if (cmd == kCmdEval) {
+                    const int m = ctrl->m;
+                    for (int base = kStageRows * (warp - 1); base < m; base += kStageRows * H)
+                        batch_dist_to<METRIC, SPEC>(g, stg, q, qn, cand_id + base, cand_dist + base, min(kStageRows, m - base), lane);
+                } else {
+                    const int node = ctrl->node, b = ctrl->buf;
+                    int* sid = spec_id0 + (size_t)b * 2 * cand_cap;
+                    float* sd = reinterpret_cast<float*>(sid + cand_cap);
+                    if (warp == 1) {
+                        const int* row = g.adj0 + (size_t)node * g.stride0;
+                        int m = 0;
+                        for (int rb = 0; rb < g.stride0; rb += 32) {
+                            const int slot = rb + lane;
+                            const int nb = slot < g.stride0 ? __ldg(row + slot) : -1;
+                            const bool fresh = nb >= 0 && vis_would_be_fresh<vis16>(vis, vis_size, vis_shift, nb);
+                            const unsigned mk = __ballot_sync(FULL, fresh);
+                            if (fresh) sid[m + __popc(mk & ((1u << lane) - 1u))] = nb;
+                            m += __popc(mk);
+                        }
+                        if (lane == 0) {
+                            ctrl->spec_m[b] = m;
+                            ctrl->spec_node[b] = node;
+                        }
+                        __syncwarp();
+                    }
+                    if (H > 1) asm volatile("bar.sync 1, %0;" ::"r"(32 * H) : "memory");  // the helpers among themselves
+                    const int m = ctrl->spec_m[b];
+                    for (int base = kStageRows * (warp - 1); base < m; base += kStageRows * H)
+                        batch_dist_to<METRIC, SPEC>(g, stg, q, qn, sid + base, sd + base, min(kStageRows, m - base), lane);
+                }
+                __syncthreads();  // (Y) the command is served
+            }
+            continue;
+        }
+
+        // ---------------- leader
+        WarpCounters wc;
+        WideList L;
+        unsigned pf_issued = 0, pf_used = 0;
+        long long pf_sel = 0, pf_wspec = 0, pf_weval = 0, pf_ins = 0;
+        const long long t_start = clock64();
+        int cur = g.entry;
+        float cur_d = single_dist<METRIC, SPEC>(g, s, qn, cur, lane);
+        wc.ndist++;
+        for (int l = g.top_layer; l > 0; --l) greedy_layer<METRIC, SPEC>(g, s, qn, l, cur, cur_d, lane, wc);
+        wl_init(L, list, ef);
+        wl_insert(L, make_key(cur_d, cur), lane);
+        if (lane == 0) {
+            if (vis16) vis16_test_and_set(s, cur); else vis_test_and_set(s, cur);
+        }
+        __syncwarp();
+        int guess_id = -1, guess_nb = -1;
+        bool outstanding = false;  // a speculative command is being served
+        int spec_buf = 0;          // ... into this buffer
+        const long long t_beam = clock64();
+        for (;;) {
+            u64 e;
+            long long t0 = clock64();
+            const bool more = wl_select(L, lane, e);
+            if (!more) {
+                if (outstanding) __syncthreads();  // (Y) of the speculation nobody needs
+                break;
+            }
+            const int c = key_id(e);
+            // The speculation must be complete before the table is written again: the helpers' read-only filter has to see
+            // the table exactly as this (authoritative) filter is about to see it.
+            bool spec_ready = false;
+            if (outstanding) {
+                const long long tw = clock64();
+                __syncthreads();  // (Y)
+                pf_wspec += clock64() - tw;
+                t0 += clock64() - tw;
+                outstanding = false;
+                spec_ready = true;
+            }
+            // row of c: keep the neighbours not seen recently, in stored order (the authoritative, table-updating filter)
+            const int* row = g.adj0 + (size_t)c * g.stride0;
+            int m = 0, deg = 0;
+            for (int rb = 0; rb < g.stride0; rb += 32) {
+                const int slot = rb + lane;
+                int nb;
+                if (guess_id == c && rb == 0) nb = guess_nb;  // fetched under the previous insertion
+                else nb = slot < g.stride0 ? __ldg(row + slot) : -1;
+                deg += __popc(__ballot_sync(FULL, nb >= 0));
+                bool fresh = false;
+                if (nb >= 0) fresh = vis16 ? vis16_test_and_set(s, nb) : vis_test_and_set(s, nb);
+                const unsigned mk = __ballot_sync(FULL, fresh);
+                if (fresh) cand_id[m + __popc(mk & ((1u << lane) - 1u))] = nb;
+                m += __popc(mk);
+            }
+            __syncwarp();
+            wc.nexp++;
+            wc.row_words += deg + 1;
+            wc.ndist += m;
+            // distances: speculative buffer if it holds exactly this expansion, else on demand
+            const float* dist = cand_dist;
+            bool have = false;
+            if (spec_ready) {
+                if (ctrl->spec_node[spec_buf] == c && ctrl->spec_m[spec_buf] == m) {
+                    const int* sid = spec_id0 + (size_t)spec_buf * 2 * cand_cap;
+                    bool same = true;
+                    for (int j = lane; j < m; j += 32) same = same && sid[j] == cand_id[j];
+                    if (__all_sync(FULL, same)) {
+                        have = true;
+                        dist = reinterpret_cast<const float*>(sid + cand_cap);
+                        pf_used++;
+                    }
+                }
+            }
+            pf_sel += clock64() - t0;
+            if (!have && m > 0) {
+                const long long tw = clock64();
+                if (lane == 0) {
+                    ctrl->cmd = kCmdEval;
+                    ctrl->m = m;
+                }
+                __syncthreads();  // (X)
+                __syncthreads();  // (Y)
+                pf_weval += clock64() - tw;
+            }
+            const long long t_ins = clock64();
+            // the entry most likely to be expanded next, unless one of this expansion's candidates lands in front of it
+            u64 pk2;
+            const u64 pk = wl_peek(L, lane, &pk2);
+            guess_id = pk != ~0ull ? key_id(pk) : -1;
+            // the row of the entry after it will most likely be wanted one expansion later: pull it into L2 now
+            if (pk2 != ~0ull && lane == 0) {
+                const char* rp = reinterpret_cast<const char*>(g.adj0 + (size_t)key_id(pk2) * g.stride0);
+                for (int off = 0; off < g.stride0 * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+            }
+            if (guess_id >= 0) {
+                if (SPECULATE) {
+                    spec_buf ^= 1;
+                    if (lane == 0) {
+                        ctrl->cmd = kCmdSpec;
+                        ctrl->node = guess_id;
+                        ctrl->buf = spec_buf;
+                    }
+                    __syncthreads();  // (X)
+                    outstanding = true;
+                    pf_issued++;
+                }
+                guess_nb = lane < g.stride0 ? __ldg(g.adj0 + (size_t)guess_id * g.stride0 + lane) : -1;
+            }
+            if (m > 0) wl_insert_candidates(L, cand_id, dist, 0, m, lane);
+            pf_ins += clock64() - t_ins;
+        }
+        if (lane == 0) {
+            const long long t_end = clock64();
+            atomicAdd(&g_wide_prof[0], 1ull);
+            atomicAdd(&g_wide_prof[1], (unsigned long long)wc.nexp);
+            atomicAdd(&g_wide_prof[2], (unsigned long long)pf_issued);
+            atomicAdd(&g_wide_prof[3], (unsigned long long)pf_used);
+            atomicAdd(&g_wide_prof[4], (unsigned long long)(t_beam - t_start));
+            atomicAdd(&g_wide_prof[5], (unsigned long long)pf_sel);
+            atomicAdd(&g_wide_prof[6], (unsigned long long)pf_wspec);
+            atomicAdd(&g_wide_prof[7], (unsigned long long)pf_weval);
+            atomicAdd(&g_wide_prof[8], (unsigned long long)pf_ins);
+            atomicAdd(&g_wide_prof[9], (unsigned long long)(t_end - t_beam));
+        }
+        if (lane == 0) ctrl->cmd = kCmdDone;
+        __syncthreads();  // (X) releases the helpers to the next query
+
+        wl_merge(L, lane);
+        for (int j = lane; j < k; j += 32) {
+            int id = -1;
+            float d = CUDART_NAN_F;
+            if (j < L.n) {
+                const u64 ee = list[j];
+                id = key_id(ee);
+                d = key_dist(ee);
+            }
+            out_ids[(size_t)qi * k + j] = id;
+            out_dists[(size_t)qi * k + j] = d;
+        }
+        if (stats != nullptr && lane == 0) {
+            QueryStats qs;
+            qs.ndist = wc.ndist; qs.nexp = wc.nexp; qs.row_words = wc.row_words;
+            stats[qi] = qs;
+        }
+    }
+}
+
+static int pow2_floor(size_t v) {
+    int p = 1;
+    while ((size_t)p * 2 <= v) p <<= 1;
+    return p;
+}
+
+struct WideShape {
+    int per_sm, sms, max_optin;
+};
+
+template <typename Kern>
+static WideShape wide_shape(Kern kern, int threads, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void*, int, size_t>, WideShape> cache;
+    static std::map<std::pair<int, const void*>, size_t> optin;
+    int dev = 0;
+    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+    const void* fn = reinterpret_cast<const void*>(kern);
+    const auto key = std::make_tuple(dev, fn, threads, smem);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    WideShape sh;
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sh.max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&sh.sms, cudaDevAttrMultiProcessorCount, dev));
+    size_t& have = optin[std::make_pair(dev, fn)];
+    if (smem > have) {
+        HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    sh.per_sm = 0;
+    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sh.per_sm, kern, threads, smem));
+    if (sh.per_sm < 1) sh.per_sm = 1;
+    cache.emplace(key, sh);
+    return sh;
+}
+
+void wide_profile(unsigned long long out[16], bool reset) {
+    HNSW_CUDA_CHECK(cudaMemcpyFromSymbol(out, g_wide_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {};
+        HNSW_CUDA_CHECK(cudaMemcpyToSymbol(g_wide_prof, z, sizeof(z)));
+    }
+}
+
+bool wide_search_applies(const GraphView& g, int nq, int ef, int layer, const Tuning& t) {
+    if (layer != 0 || t.wide_min_ef <= 0) return false;
+    if (ef >= t.wide_min_ef) return true;
+    // tiny calls: a handful of queries cannot fill the GPU with one warp each; one CTA per query answers sooner
+    return t.wide_max_small_batch > 0 && nq <= t.wide_max_small_batch;
+}
+
+void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int* d_ids, float* d_dists,
+                     unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream) {
+    if (nq <= 0) return;
+    int dev = 0, max_optin = 0;
+    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+    HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int cand_cap = ((g.stride0 + 31) / 32) * 32;
+    // warps per CTA: the leader + 2 helpers (each evaluates half of a 32-neighbour row); the leader + 1 helper in the range where
+    // the shared memory of a second helper costs a resident query (measured on 1M x 128: 1024 -> 3 warps, 2048..4096 -> 2)
+    int warps = t.wide_warps > 0 ? t.wide_warps : ((g.stride0 > 32 || ef < 2048 || ef >= 8192) ? 3 : 2);
+    warps = std::max(2, std::min(kWarpsPerBlock, warps));
+    // visited table: 4 ef entries when they fit (the setting of the one-warp kernel), else what the shared memory leaves
+    int vis = t.vis_size_search > 0 ? std::max(64, pow2_floor((size_t)t.vis_size_search)) : std::max(256, pow2_floor((size_t)2 * ef));
+    const bool can16 = (long long)g.count <= (64ll << 16);
+    if (!can16 && t.vis_size_search <= 0) vis *= 2;  // 32-bit entries: one per word
+    while (vis > 64 && wide_smem_bytes(warps, g.pitch, ef, vis, cand_cap) > (size_t)max_optin) vis >>= 1;
+    const size_t smem = wide_smem_bytes(warps, g.pitch, ef, vis, cand_cap);
+    if (smem > (size_t)max_optin)
+        throw std::runtime_error("search width (MinNN / k) too large for shared memory: one query needs " + std::to_string(smem) +
+                                 " B, the SM offers " + std::to_string(max_optin));
+    const bool v16 = (long long)g.count <= ((long long)vis << 16);
+    const bool shortrows = g.pitch <= kSegFloats;
+    const bool prefetch = t.wide_prefetch != 0;  // speculative evaluation of the next expansion
+    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
+#define HNSW_WIDE_GO(M, S, P)                                                                                                      \
+    {                                                                                                                              \
+        const WideShape sh = wide_shape(knn_wide_kernel<M, S, P>, 32 * warps, smem);                                               \
+        int per_sm = sh.per_sm;                                                                                                    \
+        if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);                                                       \
+        const int grid = std::max(1, std::min(nq, sh.sms * per_sm));                                                               \
+        knn_wide_kernel<M, S, P><<<grid, 32 * warps, smem, stream>>>(g, d_queries, nq, k, ef, vis, cand_cap, d_ids, d_dists,       \
+                                                                     d_work_counter, d_stats);                                     \
+    }
+#define HNSW_WIDE_SPEC(M)                                                                                                          \
+    {                                                                                                                              \
+        if (shortrows && v16) { if (prefetch) HNSW_WIDE_GO(M, kSpecShortRows | kSpecVis16, true) else HNSW_WIDE_GO(M, kSpecShortRows | kSpecVis16, false) } \
+        else if (shortrows) { if (prefetch) HNSW_WIDE_GO(M, kSpecShortRows, true) else HNSW_WIDE_GO(M, kSpecShortRows, false) }     \
+        else if (v16) { if (prefetch) HNSW_WIDE_GO(M, kSpecVis16, true) else HNSW_WIDE_GO(M, kSpecVis16, false) }                   \
+        else { if (prefetch) HNSW_WIDE_GO(M, 0, true) else HNSW_WIDE_GO(M, 0, false) }                                              \
+    }
+    switch (metric) {
+        case SQ_EUCLID: HNSW_WIDE_SPEC(SQ_EUCLID) break;
+        case EUCLID: HNSW_WIDE_SPEC(EUCLID) break;
+        case COSINE: HNSW_WIDE_SPEC(COSINE) break;
+        default: HNSW_WIDE_SPEC(UCOSINE) break;
+    }
+#undef HNSW_WIDE_SPEC
+#undef HNSW_WIDE_GO
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace hnsw

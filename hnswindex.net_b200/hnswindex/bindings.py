@@ -96,6 +96,7 @@ def _load():
         "hnsw_get_info": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
         "hnsw_connected_components": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
         "hnsw_get_build_profile": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
+        "hnsw_get_wide_profile": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int]),
         "hnsw_set_tuning": (ct.c_int, [ct.c_void_p, ct.c_char_p, ct.c_int]),
         "hnsw_export_layer0": (ct.c_int, [ct.c_void_p, i32p, i32p, i32p, i32p]),
         "hnsw_export_layer": (ct.c_int, [ct.c_void_p, ct.c_int, i32p, i32p]),
@@ -412,6 +413,15 @@ class Index:
         out = (ct.c_ulonglong * 16)()
         _check(lib.hnsw_get_build_profile(self._h, out, int(reset)))
         return {f: int(out[i]) for i, f in enumerate(self._BUILD_PROFILE_FIELDS)}
+
+    _WIDE_PROFILE_FIELDS = ("queries", "expansions", "spec_issued", "spec_used", "cyc_descent", "cyc_select_filter", "cyc_wait_spec",
+                            "cyc_wait_eval", "cyc_insert", "cyc_beam")
+
+    def wide_profile(self, reset: bool = False) -> dict:
+        """Leader-warp counters of the CTA-per-query wide-beam kernel (SM cycles summed over queries)."""
+        out = (ct.c_ulonglong * 16)()
+        _check(lib.hnsw_get_wide_profile(self._h, out, int(reset)))
+        return {f: int(out[i]) for i, f in enumerate(self._WIDE_PROFILE_FIELDS)}
 
     def set_tuning(self, key: str, value: int) -> None:
         _check(lib.hnsw_set_tuning(self._h, key.encode(), int(value)))

@@ -226,8 +226,14 @@ HNSW_API int hnsw_get_stats(hnsw_handle handle, hnsw_stats* out);
  * cycles, overflow prunes, prune evaluations, lock-wait cycles, select-kernel warp cycles, reverse links, 0...}.
  * Cycles are per-warp SM clock cycles summed over warps. */
 HNSW_API int hnsw_get_build_profile(hnsw_handle handle, unsigned long long* out16, int reset);
+/* Profile of the CTA-per-query wide-beam search kernel on the handle's device since the last reset, 16 words: {queries,
+ * expansions, speculative evaluations issued, speculative evaluations used, then leader-warp SM cycles: descent, select +
+ * filter, waiting for a speculation, waiting for an on-demand evaluation, insertion, beam loop total, 0...}. */
+HNSW_API int hnsw_get_wide_profile(hnsw_handle handle, unsigned long long* out16, int reset);
 /* tuning knobs: "vis_size_search", "vis_size_build", "blocks_per_sm", "build_batch_max", "build_batch_ratio",
- * "flags", "zero_copy" (1 = page-locked caller buffers of hnsw_knn_query are accessed in place by the kernel) */
+ * "flags", "zero_copy" (1 = page-locked caller buffers of hnsw_knn_query are accessed in place by the kernel),
+ * "wl_min_ef" / "wide_min_ef" (search width from which the non-shifting list / the CTA-per-query kernel are used),
+ * "wide_warps", "wide_prefetch", "wide_max_small_batch", "peer_timeout_ms" */
 HNSW_API int hnsw_set_tuning(hnsw_handle handle, const char* key, int value);
 
 /* Copy the graph to host memory (tests / inspection).  levels[count]; rows0[count][stride0] (-1 padded).

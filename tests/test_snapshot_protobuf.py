@@ -234,7 +234,7 @@ def test_gpu_written_snapshot_parsed_by_google_protobuf(hnswindex, M, MP, tmp_pa
     n = len(levels)
     assert D.Length == n == 1500 and D.Capacity >= n and D.EntryPointId == entry == ix.entry_point()
     removed = set(int(i) for i in ids[5:400:9])
-    assert D.Count == n - len(removed) == ix.count()
+    assert D.Count == n - len(removed) == ix.count
     assert list(D.ActiveNodes) == list(ix.ids())
     assert list(D.RemovedIndexes) == [int(i) for i in ids[5:400:9]][::-1]
     upper = {l: ix.export_layer(l) for l in range(1, int(levels.max()) + 1)}
