@@ -35,16 +35,17 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "hnswindex.net_b200"))
 
 EF_GRID = [10, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096]
+EF_GRID_WIDE = EF_GRID + [6144, 8192, 12288, 16384, 20480, 24576]   # the reference's heaps have no ceiling (BinaryHeap.cs:109-113)
 DIM, RANK, K = 128, 16, 10
 M, EFC = 16, 200
 # the BASELINE configs that fit one GPU.  c2 is the one the metric is quoted on (the default).
 WORKLOADS = {
     "c2": dict(tag="C2", dim=128, rank=16, metric="sq_euclid", M=16, efc=200, k=10, dist_rate=None,
                metric_name="QPS at recall@10>=0.95, 1M x 128 sq_euclid", shape="SIFT-shaped (rank-16 + 0.25 noise)"),
-    "c2u": dict(tag="C2-uniform", dim=128, rank=0, metric="sq_euclid", M=16, efc=200, k=10, dist_rate=None,
+    "c2u": dict(tag="C2-uniform", dim=128, rank=0, metric="sq_euclid", M=16, efc=200, k=10, dist_rate=None, extra_nq=500, extra_steps=3,
                 metric_name="QPS at recall@10>=0.95, 1M x 128 sq_euclid, U[0,1) data (hard case of SURVEY 8d)",
                 shape="uniform U[0,1)^128 (the reference tests' distribution; intrinsic dimension 128)"),
-    "c3": dict(tag="C3", dim=960, rank=32, metric="cosine", M=32, efc=200, k=100, dist_rate=1.0 / math.log(32.0),
+    "c3": dict(tag="C3", dim=960, rank=32, metric="cosine", M=32, efc=200, k=100, dist_rate=1.0 / math.log(32.0), extra_steps=5,
                metric_name="QPS at recall@100>=0.95, 1M x 960 cosine (C3, GIST-shaped)", shape="GIST-shaped (rank-32 + 0.25 noise, not normalised)"),
 }
 
@@ -118,6 +119,35 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_REF_BINDINGS = None
+
+
+def reference_bindings():
+    """The reference's OWN bindings.py (installed byte for byte into baseline/_ref by __graft_entry__.build()), staged in a temp
+    dir with HNSWIndex.Native.so where its loader looks (bindings.py:15-41) and imported under another module name, so that it
+    does not collide with this repo's mirror package.  None when baseline/_ref is absent."""
+    global _REF_BINDINGS
+    if _REF_BINDINGS is not None:
+        return _REF_BINDINGS or None
+    import importlib.util
+    import shutil
+    src = ROOT / "baseline" / "_ref" / "hnswindex" / "bindings.py"
+    if not src.exists():
+        _REF_BINDINGS = False
+        return None
+    import hnswindex
+    td = Path(tempfile.mkdtemp(prefix="hnsw_ref_pkg_"))
+    native = td / "artifacts" / "native" / "linux-x64"
+    native.mkdir(parents=True)
+    shutil.copyfile(src, td / "bindings.py")
+    os.symlink(hnswindex.LIB_PATH, native / "HNSWIndex.Native.so")
+    spec = importlib.util.spec_from_file_location("hnswindex_reference_bindings", td / "bindings.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _REF_BINDINGS = mod
+    return mod
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -152,13 +182,84 @@ def run_b200(args):
         ge.build()
     if world > 1:
         dist.barrier()
-    import hnswindex
     from hnswindex import bindings as hb
     hb.set_device(local)
+
+    line = replicated_pass(args, args.workload, args.steps, args.warmup, headline=True)
+
+    # ---- N > 1: the partitioned mode (BASELINE config C4) on the same ranks, as a sub-record of this line
+    if world > 1 and not args.no_partitioned:
+        try:
+            part = partitioned_pass(args, steps=min(args.steps, 20), warmup=3)
+        except Exception as e:   # the headline line must still be printed; the failure is reported in its place
+            part = {"error": f"{type(e).__name__}: {e}"[:500]}
+            log(f"[bench] rank {rank}: partitioned pass failed: {e}")
+        if rank == 0:
+            line["partitioned"] = part
+
+    # ---- N = 1: the other named shapes of BASELINE.json as sub-records (each measured like the headline, fewer steps)
+    if world == 1 and args.workload == "c2" and args.extras:
+        others = {}
+        t_ex = time.time()
+        for name in [x for x in args.extras.split(",") if x]:
+            if time.time() - t_ex > args.extras_budget_s:
+                others[name] = {"skipped": f"extras budget of {args.extras_budget_s:.0f} s used up"}
+                continue
+            try:
+                ts = time.time()
+                if name == "c5":
+                    others["c5_build"] = build_pass(args, "c2", steps=2)
+                elif name in WORKLOADS and name != "c2":
+                    sub = replicated_pass(args, name, min(args.steps, WORKLOADS[name].get("extra_steps", 10)), 3, headline=False)
+                    others[name] = compact_record(sub)
+                log(f"[bench] extra workload {name}: {time.time() - ts:.1f}s")
+            except Exception as e:
+                others[name] = {"error": f"{type(e).__name__}: {e}"[:500]}
+                log(f"[bench] extra workload {name} failed: {e}")
+        line["other_workloads"] = others
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def compact_record(line):
+    """Sub-record of an extra workload: the numbers of its own JSON line without the boilerplate."""
+    cfg = line["config"]
+    keep = {k: v for k, v in cfg.items() if k.startswith("recall_at_") or k in ("ef", "workload", "index_nodes", "inserts_per_s",
+                                                                                "build_kernel_inserts_per_s", "build_gathered_GBps")}
+    return {"metric": line["metric"], "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "steps": line["steps"],
+            "e2e": line["e2e"], "roofline": line["roofline"], "cpu_baseline": line["cpu_baseline"], "clocks": line["clocks"],
+            "gpu_launches": line["gpu_launches"], **keep}
+
+
+def replicated_pass(args, workload, steps, warmup, headline):
+    """One workload of SURVEY 8(d) on a replicated graph (mode 1): build (untimed), pick ef, time `steps` query batches three
+    ways (queued device-resident = value, one by one = roofline, host buffers through the C ABI = e2e), oracle on the same
+    graph for the algorithmic bytes and the CPU baseline.  Returns the JSON line as a dict on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    import hnswindex
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    class _A:   # the pass reads steps / warmup / workload from here
+        pass
+    a = _A()
+    a.__dict__.update(vars(args))
+    a.steps, a.warmup, a.workload = steps, warmup, workload
+    args = a
 
     W = WORKLOADS[args.workload]
     DIM, RANK, K, M, EFC, METRIC = W["dim"], W["rank"], W["k"], W["M"], W["efc"], W["metric"]
     n, nq, nb = args.n, args.nq, args.query_batches
+    if not headline:
+        nq = min(nq, W.get("extra_nq", nq))
     data, queries = make_data(n, nq * nb, seed_q=4321 + 1000 * rank, dim=DIM, rank=RANK)
     snap = Path(args.snapshot_dir) / f"bench_{args.workload}_{n}.hnsw"
 
@@ -201,7 +302,7 @@ def run_b200(args):
         ix.set_min_nn(ef)
         return ix.knn_query(queries[:ns], K)[0]
     if rank == 0:
-        ef, rec = pick_ef(search_ef, truth, k=K)
+        ef, rec = pick_ef(search_ef, truth, grid=EF_GRID_WIDE if RANK <= 0 else EF_GRID, k=K)
         sel = torch.tensor([ef], dtype=torch.int32, device="cuda")
     else:
         sel = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -276,20 +377,29 @@ def run_b200(args):
     _, _, kms = timed(step_resident, args.steps, args.warmup, collect_kernel_ms=True)   # the same launches, timed one by one
     e2e_dev_ms, e2e_wall_ms, _ = timed(step_e2e, args.steps, args.warmup)
 
-    # ---- N > 1: the partitioned mode (BASELINE config C4) on the same ranks, as a sub-record of this line
-    part = None
-    if world > 1 and not args.no_partitioned:
-        try:
-            part = partitioned_pass(args, steps=min(args.steps, 20), warmup=3)
-        except Exception as e:   # the headline line must still be printed; the failure is reported in its place
-            part = {"error": f"{type(e).__name__}: {e}"[:500]}
-            log(f"[bench] rank {rank}: partitioned pass failed: {e}")
+    # ---- the same through the reference's OWN Python package: pageable numpy in, numpy out (what a user of the reference
+    #      switching libraries actually calls); the handle is the index built above
+    refb = reference_bindings()
+    q_np = [np.ascontiguousarray(queries[b * nq:(b + 1) * nq]) for b in range(nb)]
+    if refb is not None:
+        rix = refb.Index(DIM, metric=METRIC)
+        rix._h, rix._initialized = ix._h, True
+        pageable_api = "reference bindings.py Index.knn_query (unmodified package from baseline/_ref; pageable numpy in, numpy out)"
+    else:
+        rix = ix
+        pageable_api = "hnswindex mirror Index.knn_query (baseline/_ref absent; pageable numpy in, numpy out)"
+    page_out = {}
+
+    def step_pageable(i):
+        page_out["r"] = rix.knn_query(q_np[i % nb], K)
+    _, page_wall_ms, _ = timed(step_pageable, args.steps, args.warmup)
+    if refb is not None:
+        rix._h = None   # the handle belongs to `ix`
+    pid, pdist = page_out["r"]
+    assert pid.shape == (nq, K) and pid.dtype == np.int32 and pdist.dtype == np.float32
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        return None
 
     total_q = world * nq * args.steps
     value = total_q / (dev_ms / 1e3)
@@ -320,15 +430,16 @@ def run_b200(args):
         roof.update({"achieved": round(ach, 1), "peak": peak, "frac": round(ach / peak, 4), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "gathered_vector_GBps": round(bytes_vec / (kernel_ms / 1e3) / 1e9, 1),
                      "ndist_per_query": round(int(cnt[0]) / nq, 1), "nexp_per_query": round(int(cnt[1]) / nq, 1),
-                     "kernel": f"knn_search_kernel<{METRIC}>", "kernel_ms_avg": round(kernel_ms, 4),
+                     "kernel": (f"knn_search_kernel<{METRIC}>" if ef < 1024 else f"knn_wide_kernel<{METRIC}> (one CTA per query)"),
+                     "kernel_ms_avg": round(kernel_ms, 4),
                      # the queued batches of the timed region overlap in their tails: whole-region figure, for the record
                      "pipelined_algorithmic_GBps": round(alg * args.steps / (dev_ms / 1e3) / 1e9, 1)})
-        prof = ROOT / "profiles" / "search_kernel_traffic.json"
-        if prof.exists() and args.workload == "c2":
+        prof = ROOT / "profiles" / {"c2": "search_kernel_traffic.json", "c3": "search_kernel_traffic_c3.json"}.get(args.workload, "none")
+        if prof.exists() and nq == 10000:
             # ncu's DRAM bytes are only quoted while the kernel's machine code is the one that was captured
             tj = json.load(open(prof))
             have = ge._load_build_module().kernel_sass_stamp(tj.get("kernel_mangled", ""))
-            if have is not None and have == tj.get("kernel_sass_sha256") and ef <= 64:
+            if have is not None and have == tj.get("kernel_sass_sha256") and ef == (48 if args.workload == "c2" else 192):
                 roof["traffic"] = tj.get("dram_bytes_per_launch")
                 roof["traffic_source"] = f"{tj.get('source')}; kernel SASS sha256 {have[:16]} matches the library of this run"
             else:
@@ -336,7 +447,7 @@ def run_b200(args):
                                          "search width) than this run's kernel: no traffic figure")
         # CPU baseline (N=1 only): repeat the 10k batch until ~10 s of work (max 5 passes)
         t_cpu, passes = 0.0, 0
-        while world == 1 and t_cpu < 10.0 and passes < 5:
+        while world == 1 and t_cpu < (10.0 if headline else 3.0) and passes < 5:
             tc = time.perf_counter(); ref.knn_query(queries[:ncheck], K, threads=cores); t_cpu += time.perf_counter() - tc; passes += 1
         cpu = None if world > 1 else {"value": round(ncheck * passes / t_cpu, 1), "unit": "queries/s", "cores": cores, "kind": "port",
                "sample": f"{passes} x {ncheck} queries of batch 0 on the same GPU-built {n}-node graph, ef={ef}, all host threads "
@@ -362,19 +473,17 @@ def run_b200(args):
                    "l2_policy": f"inputs larger than L2: {n * (DIM * 4 + 2 * M * 4) / 1e6:.0f} MB graph vs 126 MB L2, "
                                 f"{nb} distinct query batches rotated", "graph_built_by": "GPU engine (hnsw_add)", **build_info},
         "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8,
-                "ms_per_step": round(e2e_wall_ms / args.steps, 4), "api": "hnsw_knn_query (C ABI, pinned host buffers)"},
+                "ms_per_step": round(e2e_wall_ms / args.steps, 4), "api": "hnsw_knn_query (C ABI, pinned host buffers)",
+                "pageable": {"value": round(total_q / (page_wall_ms / 1e3), 1), "unit": "queries/s",
+                             "ms_per_step": round(page_wall_ms / args.steps, 4), "api": pageable_api}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
         "wall_ms_per_step": round(wall_ms / args.steps, 4),
     }
-    if part is not None:
-        line["partitioned"] = part
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del ix
+    return line
 
 
 # ------------------------------------------------------------------------------------------- reference arm
@@ -619,17 +728,23 @@ def run_partitioned(args):
 
 # ------------------------------------------------------------------------------------------- construction (C5)
 def run_build(args):
-    """BASELINE config C5: batched GPU construction (hnsw_add) of the C2 data set vs the reference's Parallel.For Add
-    (oracle port on all host threads, bounded sample), with a recall-parity check.  Secondary workload, own metric name.
-    A step = one complete build of the n-node index."""
+    """`--mode build`: the C5 pass alone, printed as its own line (secondary workload, own metric name)."""
     import torch
     import __graft_entry__ as ge
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     if int(os.environ.get("RANK", "0")) != 0:
         return
     ge.build()
+    print(json.dumps(build_pass(args, args.workload, max(1, min(args.steps, 5)))), flush=True)
+
+
+def build_pass(args, workload, steps):
+    """BASELINE config C5: batched GPU construction (hnsw_add) of the C2 data set vs the reference's Parallel.For Add
+    (oracle port on all host threads, bounded sample), with a recall-parity check.
+    A step = one complete build of the n-node index.  Returns the JSON line as a dict."""
+    import torch
     import hnswindex
-    W = WORKLOADS[args.workload]
+    W = WORKLOADS[workload]
     DIM, RANK, K, M, EFC, METRIC = W["dim"], W["rank"], W["k"], W["M"], W["efc"], W["metric"]
     n = args.n
     data, queries = make_data(n, 2000, dim=DIM, rank=RANK)
@@ -645,7 +760,6 @@ def run_build(args):
         ix._create()
         return ix
 
-    steps = max(1, min(args.steps, 5))
     walls, kms, prof = [], [], None
     sampler = ClockSampler(0)
     for i in range(1 + steps):           # first build = warm-up (context, allocator)
@@ -691,7 +805,7 @@ def run_build(args):
                "sample": f"the first {sample} vectors of the same data set built by the oracle's threaded Add (Parallel.For stand-in, "
                          f"all host threads); insert cost grows ~log n, so the full-size CPU rate is lower still"}
         parity = {"nodes": sample, "ef": ef, f"recall_at_{K}_gpu_built": round(r_gpu, 4), f"recall_at_{K}_oracle_built": round(r_cpu, 4)}
-    print(json.dumps({
+    return ({
         "metric": f"build inserts/s, {n} x {DIM} {METRIC}, M={M}, efConstruction={EFC} (C5)", "value": round(n / (kernel_ms / 1e3), 1),
         "unit": "inserts/s", "n_gpus": 1, "steps": steps, "warmup": 1, "ms_per_step": round(kernel_ms, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -707,7 +821,7 @@ def run_build(args):
                      "bytes_model": "GPU-counted distance evaluations (search + heuristic + overflow prune) x dim x 4",
                      "ndist_per_insert": {"search": round(prof["ndist_search"] / n, 1), "heuristic": round(prof["ndist_select"] / n, 1),
                                           "overflow_prune": round(prof["ndist_prune"] / n, 1)}},
-        "cpu_baseline": cpu}), flush=True)
+        "cpu_baseline": cpu})
 
 
 def main():
@@ -729,6 +843,9 @@ def main():
     ap.add_argument("--build-sample", type=int, default=400_000, help="build mode: nodes the CPU oracle builds (bounded sample, ~10-15 s on 16 cores)")
     ap.add_argument("--n-per-rank", type=int, default=1_250_000)
     ap.add_argument("--no-partitioned", action="store_true", help="N > 1: skip the partitioned-index (C4) sub-record")
+    ap.add_argument("--extras", default="c5,c2u,c3", help="N = 1, workload c2: the other named shapes measured as sub-records "
+                    "(c5 = construction, c2u = uniform hard case, c3 = 1M x 960 cosine); '' = none")
+    ap.add_argument("--extras-budget-s", type=float, default=400.0, help="no further extra workload is started after this many seconds")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup

@@ -58,8 +58,8 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
 
         WarpCounters wc;
         int cur = g.entry;
-        float cur_d = single_dist<METRIC>(g, s, qn, cur, lane);
-        for (int layer = g.top_layer; layer > level; --layer) greedy_layer<METRIC>(g, s, qn, layer, cur, cur_d, lane, wc);
+        float cur_d = single_dist<METRIC, SPEC>(g, s, qn, cur, lane);
+        for (int layer = g.top_layer; layer > level; --layer) greedy_layer<METRIC, SPEC>(g, s, qn, layer, cur, cur_d, lane, wc);
         long long t1 = clock64();
         cyc_descent += t1 - t0;
 
@@ -82,7 +82,7 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
                 next_d = key_dist(s.list[st.n - 1]);
                 __syncwarp();
             } else {
-                nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, nd_select);
+                nsel = select_neighbors<METRIC, SPEC>(g, b, s.list, st.n, maxE, lane, nd_select);
                 next = key_id(s.list[0]);  // the closest candidate is always selected first
                 next_d = key_dist(s.list[0]);
             }
@@ -250,7 +250,14 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
 #define HNSW_LAUNCH_BUILD(M)                                                                                                    \
     {                                                                                                                           \
         int w1 = 0, w2 = 0;                                                                                                     \
-        if (vis16) {                                                                                                            \
+        if (vis16 && g.pitch <= kSegFloats && list_cap_sel <= 1024 && t.build_specialized != 0) {                                \
+            /* the C5 shape: rows of one staging segment, MaxCandidates <= 1024, 16-bit tags -- no long-row / large-list code */ \
+            constexpr int S = kSpecVis16 | kSpecShortRows | kSpecMidList;                                                       \
+            const int g1 = persistent_grid(build_select_kernel<M, S>, smem_sel, t, count, w1);                                 \
+            const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
+            build_select_kernel<M, S><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                 \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
+        } else if (vis16) {                                                                                                     \
             const int g1 = persistent_grid(build_select_kernel<M, kSpecVis16>, smem_sel, t, count, w1);                        \
             const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
             build_select_kernel<M, kSpecVis16><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                        \

@@ -153,11 +153,13 @@ __device__ __forceinline__ int select_neighbors_windowed(const GraphView& g, Bui
     return nsel;
 }
 
-template <int METRIC>
+// SPEC & kSpecShortRows: the caller knows at compile time that rows fit one staging segment (the long-row code is dropped)
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ int select_neighbors(const GraphView& g, BuildScratch& b, const u64* list, int n, int maxE, int lane, unsigned& ndist) {
 #ifndef HNSW_STAGE_BULK
-    if (g.pitch <= kSegFloats) return select_neighbors_windowed<METRIC>(g, b, list, n, maxE, lane, ndist);
+    if ((SPEC & kSpecShortRows) || g.pitch <= kSegFloats) return select_neighbors_windowed<METRIC>(g, b, list, n, maxE, lane, ndist);
 #endif
+    if (SPEC & kSpecShortRows) return 0;  // (unreachable)
     return select_neighbors_long<METRIC>(g, b, list, n, maxE, lane, ndist);
 }
 

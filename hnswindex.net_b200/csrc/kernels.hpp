@@ -17,6 +17,7 @@ struct Tuning {
     int build_overlap = 0;    // large insertion batches: run the link kernel on a second stream so that the next batch's select
                               // kernel fills the SM slots freed in the tails.  Off: -4.5 % build time, but the next batch
                               // then sees the previous batch's reverse links only partly and recall@10 drops 0.2 pt
+    int build_specialized = 1;  // the C5-shaped select kernel instantiation (short rows, MaxCandidates <= 1024, 16-bit tags)
     int async_overlap = 1;    // hnsw_knn_query_device_async alternates two streams (consecutive batches overlap in their tails)
     int blocks_per_sm = 0;    // 0 = occupancy query
     int exact_tcgen05 = 1;    // exact_knn_tf32: pass A on tcgen05 / TMEM where the shape allows (rows <= 128 floats), else mma.sync;

@@ -15,12 +15,17 @@ ix.set_min_nn(192)
 qd = [torch.from_numpy(q[i * 10000:(i + 1) * 10000]).cuda() for i in range(2)]
 ids = torch.empty((10000, 100), dtype=torch.int32, device="cuda"); dd = torch.empty((10000, 100), dtype=torch.float32, device="cuda")
 base = None
-for cfg in ({"vis_global_search": 32768}, {"vis_global_search": 0}, {"vis_global_search": 8192}, {"vis_global_search": 32768}):
+cfgs = [{"vis_size_search": 0}, {"vis_size_search": 2048}, {"vis_size_search": 4096}, {"vis_size_search": 8192},
+        {"vis_size_search": 0, "wl_min_ef": 1}, {"vis_size_search": 4096, "wl_min_ef": 1},
+        {"vis_size_search": 0, "wl_min_ef": 256, "wide_min_ef": 1, "wide_warps": 3}, {"wide_min_ef": 1, "wide_warps": 4},
+        {"wide_min_ef": 1, "wide_warps": 4, "vis_size_search": 4096}, {"wide_min_ef": 1024, "wide_warps": 0, "vis_size_search": 0}]
+for cfg in cfgs:
     for k, v in cfg.items(): ix.set_tuning(k, v)
     ix.enable_stats(True); ix.knn_query_device(qd[0].data_ptr(), 10000, 100, ids.data_ptr(), dd.data_ptr()); st = ix.stats(); ix.enable_stats(False)
     cur = ids.cpu().numpy().copy()
     if base is None: base = cur
     ms = []
-    for i in range(6):
+    for i in range(5):
         ix.knn_query_device(qd[i % 2].data_ptr(), 10000, 100, ids.data_ptr(), dd.data_ptr()); ms.append(ix.stats()["last_search_ms"])
-    print(json.dumps({"cfg": cfg, "kernel_ms": round(float(np.mean(ms[1:])), 2), "ndist_per_q": st["ndist"] / 10000, "same": float((cur == base).all(axis=1).mean())}), flush=True)
+    print(json.dumps({"cfg": cfg, "kernel_ms": round(float(np.mean(ms[1:])), 2), "qps": round(10000 / (float(np.mean(ms[1:])) / 1e3)), "ndist_per_q": st["ndist"] / 10000,
+                      "same": float((cur == base).all(axis=1).mean())}), flush=True)
