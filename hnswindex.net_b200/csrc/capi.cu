@@ -99,7 +99,7 @@ int hnsw_remove(hnsw_handle handle, const int* ids, int count) {
 }
 int hnsw_ids(hnsw_handle handle, int* outIds, int capacity) {
     HNSW_TRY
-    const std::vector<int>& a = get(handle)->active_ids();
+    const std::vector<int> a = get(handle)->active_ids();  // a copy taken under the index's lock
     for (int i = 0; i < (int)a.size() && i < capacity && outIds != nullptr; ++i) outIds[i] = a[i];
     return (int)a.size();
     HNSW_CATCH(-1)
@@ -228,7 +228,7 @@ int hnsw_set_min_nn(int v) { std::lock_guard<std::mutex> l(g_mu); g_pending.MinN
 int hnsw_set_allow_removals(bool v) { std::lock_guard<std::mutex> l(g_mu); g_pending.AllowRemovals = v; return 0; }
 
 // ------------------------------------------------------------------------------------ additions
-int hnsw_count(hnsw_handle handle) { return handle ? reinterpret_cast<Index*>(handle)->count() : -1; }
+int hnsw_count(hnsw_handle handle) { return handle ? reinterpret_cast<Index*>(handle)->count_locked() : -1; }
 int hnsw_dim(hnsw_handle handle) { return handle ? reinterpret_cast<Index*>(handle)->dim() : -1; }
 
 int hnsw_serialize(hnsw_handle handle, const char* path, int packed) {
@@ -253,7 +253,7 @@ int hnsw_index_set_min_nn(hnsw_handle handle, int minNN) {
 }
 int hnsw_index_get_params(hnsw_handle handle, int* ints7, double* rate) {
     HNSW_TRY
-    const Parameters& p = get(handle)->params();
+    const Parameters p = get(handle)->params();
     if (ints7) {
         ints7[0] = p.MaxEdges; ints7[1] = p.MinNN; ints7[2] = p.MaxCandidates; ints7[3] = p.RemoveMaxCandidates;
         ints7[4] = p.CollectionSize; ints7[5] = p.RandomSeed; ints7[6] = p.AllowRemovals ? 1 : 0;
@@ -443,27 +443,29 @@ int hnsw_set_tuning(hnsw_handle handle, const char* key, int value) {
     return 0;
     HNSW_CATCH(-1)
 }
-int hnsw_export_layer0(hnsw_handle handle, int* levels, int* rows0, int* stride0, int* entryPoint) {
+int hnsw_export_layer0_n(hnsw_handle handle, int maxNodes, int* levels, int* rows0, int* stride0, int* entryPoint) {
     HNSW_TRY
     Index* ix = get(handle);
     HostGraph g;
-    ix->export_graph(g);
+    ix->export_graph_locked(g, false);
     if (stride0) *stride0 = g.stride0;
     if (entryPoint) *entryPoint = g.entry;
-    if (levels) std::memcpy(levels, g.levels.data(), g.levels.size() * sizeof(int));
-    if (rows0) std::memcpy(rows0, g.adj0.data(), g.adj0.size() * sizeof(int));
+    const size_t n = (size_t)std::max(0, std::min(g.length, maxNodes));
+    if (levels) std::memcpy(levels, g.levels.data(), n * sizeof(int));
+    if (rows0) std::memcpy(rows0, g.adj0.data(), n * (size_t)g.stride0 * sizeof(int));
     return g.length;
     HNSW_CATCH(-1)
 }
-int hnsw_export_layer(hnsw_handle handle, int layer, int* rows, int* stride) {
+int hnsw_export_layer_n(hnsw_handle handle, int layer, int maxNodes, int* rows, int* stride) {
     HNSW_TRY
     if (layer < 1) throw std::invalid_argument("use hnsw_export_layer0 for layer 0");
     Index* ix = get(handle);
     HostGraph g;
-    ix->export_graph(g);
+    ix->export_graph_locked(g, false);
     if (stride) *stride = g.strideU;
+    const int n = std::max(0, std::min(g.length, maxNodes));
     if (rows)
-        for (int i = 0; i < g.length; ++i) {
+        for (int i = 0; i < n; ++i) {
             int* dst = rows + (size_t)i * g.strideU;
             if (g.levels[i] >= layer) std::memcpy(dst, g.adjU.data() + ((size_t)g.upper_off[i] + (layer - 1)) * g.strideU, (size_t)g.strideU * sizeof(int));
             else for (int j = 0; j < g.strideU; ++j) dst[j] = -1;
@@ -471,6 +473,10 @@ int hnsw_export_layer(hnsw_handle handle, int layer, int* rows, int* stride) {
     return g.length;
     HNSW_CATCH(-1)
 }
+int hnsw_export_layer0(hnsw_handle handle, int* levels, int* rows0, int* stride0, int* entryPoint) {
+    return hnsw_export_layer0_n(handle, 0x7FFFFFFF, levels, rows0, stride0, entryPoint);
+}
+int hnsw_export_layer(hnsw_handle handle, int layer, int* rows, int* stride) { return hnsw_export_layer_n(handle, layer, 0x7FFFFFFF, rows, stride); }
 int hnsw_snapshot_transcode(const char* inPath, const char* outPath, int packed) {
     HNSW_TRY
     if (!inPath || !outPath) throw std::invalid_argument("null path");

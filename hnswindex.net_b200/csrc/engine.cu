@@ -105,6 +105,15 @@ Index::~Index() {
     cudaFree(rq_keys_); cudaFree(rq_hash_); cudaFree(rq_small_); cudaFree(rq_dense_);
     cudaFree(rm_small_); cudaFree(rm_aff_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
+    for (QueryCtx& c : qctx_) {
+        cudaFree(c.d_q); cudaFree(c.d_ids); cudaFree(c.d_dists); cudaFree(c.d_stats); cudaFree(c.d_counters);
+        if (c.ev0) cudaEventDestroy(c.ev0);
+        if (c.ev1) cudaEventDestroy(c.ev1);
+        if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+        if (c.ev_join) cudaEventDestroy(c.ev_join);
+        if (c.stream) cudaStreamDestroy(c.stream);
+        if (c.aux) cudaStreamDestroy(c.aux);
+    }
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
@@ -159,7 +168,7 @@ GraphView Index::view() const {
 }
 
 void Index::build_profile(unsigned long long out[16], bool reset) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
     HNSW_CUDA_CHECK(cudaMemcpy(out, d_build_prof_, 16 * sizeof(u64), cudaMemcpyDeviceToHost));
@@ -234,7 +243,7 @@ void Index::ensure_search_gvis(int ef) {
 }
 
 void Index::set_stream(cudaStream_t s) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
     stream_ = s ? s : own_stream_;
@@ -245,7 +254,7 @@ void Index::set_stream(cudaStream_t s) {
 // ones the reference hands out when items are added one after another.
 // ---------------------------------------------------------------------------------------------
 int Index::add(const float* vectors, int count, int dim, int* out_ids) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
@@ -514,7 +523,7 @@ void Index::remove_chunk(const int* ids, int n) {
 }
 
 void Index::remove(const int* ids, int count) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (!params_.AllowRemovals) throw std::runtime_error("Removals are disabled in this index instance.");  // HNSWIndex.cs:85-86
     if (count <= 0) return;
@@ -566,9 +575,64 @@ static T* pinned_alias(const T* host) {
     return reinterpret_cast<T*>(a.devicePointer);
 }
 
+// ---- query contexts: stream + scratch of one in-flight hnsw_knn_query ----------------------------------------------
+int Index::acquire_ctx() {
+    std::unique_lock<std::mutex> l(ctx_mu_);
+    for (;;) {
+        for (int i = 0; i < kQueryContexts; ++i)
+            if (!qctx_[i].busy) {
+                qctx_[i].busy = true;
+                return i;
+            }
+        ctx_cv_.wait(l);
+    }
+}
+void Index::release_ctx(int i) {
+    {
+        std::lock_guard<std::mutex> l(ctx_mu_);
+        qctx_[i].busy = false;
+    }
+    ctx_cv_.notify_one();
+}
+// called by the thread that holds the context
+void Index::prepare_ctx(QueryCtx& c, int count, int k, bool want_stats) {
+    if (!c.created) {
+        HNSW_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        HNSW_CUDA_CHECK(cudaStreamCreateWithFlags(&c.aux, cudaStreamNonBlocking));
+        HNSW_CUDA_CHECK(cudaEventCreate(&c.ev0));
+        HNSW_CUDA_CHECK(cudaEventCreate(&c.ev1));
+        HNSW_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        HNSW_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+        HNSW_CUDA_CHECK(cudaMalloc(&c.d_counters, 16 * sizeof(unsigned)));
+        HNSW_CUDA_CHECK(cudaMemset(c.d_counters, 0, 16 * sizeof(unsigned)));
+        c.created = true;
+    }
+    const size_t qn = (size_t)count * dim_, on = (size_t)count * k;
+    if (qn > c.q_cap) { cudaFree(c.d_q); c.d_q = nullptr; c.q_cap = 0; HNSW_CUDA_CHECK(cudaMalloc(&c.d_q, qn * sizeof(float))); c.q_cap = qn; }
+    if (on > c.out_cap) {
+        cudaFree(c.d_ids); cudaFree(c.d_dists); c.d_ids = nullptr; c.d_dists = nullptr; c.out_cap = 0;
+        HNSW_CUDA_CHECK(cudaMalloc(&c.d_ids, on * sizeof(int)));
+        HNSW_CUDA_CHECK(cudaMalloc(&c.d_dists, on * sizeof(float)));
+        c.out_cap = on;
+    }
+    if (want_stats && (size_t)count > c.stats_cap) {
+        cudaFree(c.d_stats); c.d_stats = nullptr; c.stats_cap = 0;
+        HNSW_CUDA_CHECK(cudaMalloc(&c.d_stats, (size_t)count * sizeof(QueryStats)));
+        c.stats_cap = count;
+    }
+}
+
+// BatchKnnQuery (HNSWIndex.cs:129-137).  Runs under the SHARED lock: host threads calling it at the same time each get a
+// query context (stream, scratch, work counters) and their kernels share the GPU; Add / Remove / Serialize wait for them.
 void Index::knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists, int layer) {
-    std::lock_guard<std::mutex> lock(mu_);
-    join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
+    if (aux_dirty_.load()) {  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
+        Exclusive ex(mu_);
+        join_aux_locked(true);
+    }
+    // the optional global visited sets of long-row searches are one allocation per index: such calls stay exclusive
+    std::shared_lock<std::shared_mutex> shared(mu_, std::defer_lock);
+    Exclusive exclusive(mu_, std::defer_lock);
+    if (tuning_.vis_global_search > 0) exclusive.lock(); else shared.lock();
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) {  // HNSWIndex.cs:109
         fill_empty(out_ids, out_dists, (size_t)count * k);
@@ -577,61 +641,78 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
     // the reference indexes OutEdges[layer] of a node found on that layer: IndexOutOfRangeException beyond the top layer
     if (layer < 0 || layer > top_) throw std::out_of_range("layer " + std::to_string(layer) + " does not exist (top layer is " + std::to_string(top_) + ")");
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
-    ensure_dim(dim);
-    ensure_query_scratch(count, k);
-    if (collect_stats_) ensure_stats(count);
+    if (dim != dim_) throw std::invalid_argument("vector dimension " + std::to_string(dim) + " does not match the index dimension " + std::to_string(dim_));
+    const bool want_stats = collect_stats_;
+    const int ci = acquire_ctx();
+    struct Release {
+        Index* ix; int i;
+        ~Release() { ix->release_ctx(i); }
+    } release{this, ci};
+    QueryCtx& c = qctx_[ci];
+    prepare_ctx(c, count, k, want_stats);
+    cudaStream_t st0 = ci == 0 ? stream_ : c.stream;  // context 0 honours set_stream()
     const int ef = std::max(params_.MinNN, k);  // HNSWIndex.cs:115
     const float* q_src = zero_copy_ ? pinned_alias(queries) : nullptr;
     int* ids_dst = zero_copy_ ? pinned_alias(out_ids) : nullptr;
     float* d_dst = zero_copy_ ? pinned_alias(out_dists) : nullptr;
     const bool direct_out = ids_dst != nullptr && d_dst != nullptr;
-    int* ids_out = direct_out ? ids_dst : d_ids_;
-    float* d_out = direct_out ? d_dst : d_dists_;
-    ensure_search_gvis(ef);
+    int* ids_out = direct_out ? ids_dst : c.d_ids;
+    float* d_out = direct_out ? d_dst : c.d_dists;
+    if (exclusive.owns_lock()) ensure_search_gvis(ef);
     // Pageable queries (what numpy hands over through the reference's own bindings.py) are staged by the driver, and the
     // host thread is held while that happens: a large batch is therefore uploaded in four pieces, each piece's search
     // launched as soon as it is on the device and alternating between the two streams, so the upload of piece i+1 runs
     // under the search of piece i.
-    const int pieces = (!q_src && !collect_stats_ && layer == 0 && count >= 4096 && tuning_.async_overlap != 0 &&
+    const int pieces = (!q_src && !want_stats && layer == 0 && count >= 4096 && tuning_.async_overlap != 0 &&
                         tuning_.vis_global_search <= 0) ? 4 : 1;
-    HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    HNSW_CUDA_CHECK(cudaEventRecord(c.ev0, st0));
     if (pieces == 1) {
         if (!q_src) {
-            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, stream_));
-            q_src = d_q_;
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(c.d_q, queries, (size_t)count * dim * 4, cudaMemcpyHostToDevice, st0));
+            q_src = c.d_q;
         }
-        launch_knn_search((int)metric_, view(), q_src, count, k, ef, layer, ids_out, d_out, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr,
-                          d_gvis_search_, gvis_search_words_, tuning_, stream_);
-        stats_.search_launches += 1;
+        launch_knn_search((int)metric_, view(), q_src, count, k, ef, layer, ids_out, d_out, c.d_counters + 3, want_stats ? c.d_stats : nullptr,
+                          exclusive.owns_lock() ? d_gvis_search_ : nullptr, exclusive.owns_lock() ? gvis_search_words_ : 0, tuning_, st0);
     } else {
-        HNSW_CUDA_CHECK(cudaEventRecord(ev_fork_, stream_));
-        HNSW_CUDA_CHECK(cudaStreamWaitEvent(aux_stream_, ev_fork_, 0));
+        HNSW_CUDA_CHECK(cudaEventRecord(c.ev_fork, st0));
+        HNSW_CUDA_CHECK(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
         const GraphView g = view();
         for (int p = 0; p < pieces; ++p) {
             const int q0 = (int)((long long)count * p / pieces), q1 = (int)((long long)count * (p + 1) / pieces);
-            cudaStream_t st = (p & 1) ? aux_stream_ : stream_;
-            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_q_ + (size_t)q0 * dim, queries + (size_t)q0 * dim, (size_t)(q1 - q0) * dim * 4, cudaMemcpyHostToDevice, st));
-            launch_knn_search((int)metric_, g, d_q_ + (size_t)q0 * dim, q1 - q0, k, ef, 0, ids_out + (size_t)q0 * k, d_out + (size_t)q0 * k,
-                              d_counters_ + ((p & 1) ? 8 : 3), nullptr, nullptr, 0, tuning_, st);
-            stats_.search_launches += 1;
+            cudaStream_t st = (p & 1) ? c.aux : st0;
+            HNSW_CUDA_CHECK(cudaMemcpyAsync(c.d_q + (size_t)q0 * dim, queries + (size_t)q0 * dim, (size_t)(q1 - q0) * dim * 4, cudaMemcpyHostToDevice, st));
+            launch_knn_search((int)metric_, g, c.d_q + (size_t)q0 * dim, q1 - q0, k, ef, 0, ids_out + (size_t)q0 * k, d_out + (size_t)q0 * k,
+                              c.d_counters + ((p & 1) ? 8 : 3), nullptr, nullptr, 0, tuning_, st);
         }
-        HNSW_CUDA_CHECK(cudaEventRecord(ev_join_, aux_stream_));
-        HNSW_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join_, 0));
+        HNSW_CUDA_CHECK(cudaEventRecord(c.ev_join, c.aux));
+        HNSW_CUDA_CHECK(cudaStreamWaitEvent(st0, c.ev_join, 0));
     }
-    HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    HNSW_CUDA_CHECK(cudaEventRecord(c.ev1, st0));
     if (!direct_out) {
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists, d_dists_, (size_t)count * k * 4, cudaMemcpyDeviceToHost, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(out_ids, c.d_ids, (size_t)count * k * 4, cudaMemcpyDeviceToHost, st0));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(out_dists, c.d_dists, (size_t)count * k * 4, cudaMemcpyDeviceToHost, st0));
     }
-    HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    std::vector<QueryStats> hstats;
+    if (want_stats) {
+        hstats.resize(count);
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(hstats.data(), c.d_stats, (size_t)count * sizeof(QueryStats), cudaMemcpyDeviceToHost, st0));
+    }
+    HNSW_CUDA_CHECK(cudaStreamSynchronize(st0));
     float ms = 0.f;
-    HNSW_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
-    stats_.last_search_ms = ms;
-    if (collect_stats_) fetch_query_stats(count);
+    HNSW_CUDA_CHECK(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+    {
+        std::lock_guard<std::mutex> l(stats_mu_);
+        stats_.last_search_ms = ms;
+        stats_.search_launches += pieces;
+        if (want_stats) {
+            stats_.ndist = stats_.nexp = stats_.row_words = 0;
+            for (auto& q : hstats) { stats_.ndist += q.ndist; stats_.nexp += q.nexp; stats_.row_words += q.row_words; }
+        }
+    }
 }
 
 void Index::knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) throw std::runtime_error("knn_query_device on an empty index");
@@ -655,7 +736,7 @@ void Index::knn_query_device(const float* d_queries, int count, int dim, int k, 
 // MultiLayerKnnQuery (HNSWIndex.cs:173-187) for a batch of queries.  Returns the number of layers L = min(top, maxLayer) + 1;
 // outputs are [count][L][k] (pass null pointers to query L only).
 int Index::multilayer_knn_query(const float* queries, int count, int dim, int k, int max_layer, int min_layer, int* out_ids, float* out_dists) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (this->count() <= 0 || k < 1) return 0;  // HNSWIndex.cs:176
     if (max_layer < 0) throw std::out_of_range("maxLayer must not be negative");
@@ -680,7 +761,7 @@ int Index::multilayer_knn_query(const float* queries, int count, int dim, int k,
 // is picked up again after a join), so two consecutive batches overlap: the blocks of the later one fill the SM slots
 // that the persistent blocks of the earlier one give up in its tail.
 void Index::knn_query_device_async(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) throw std::runtime_error("knn_query_device_async on an empty index");
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
@@ -718,20 +799,20 @@ void Index::join_aux_locked(bool host_wait) {
 }
 
 void Index::async_join() {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     join_aux_locked(false);
 }
 
 void Index::synchronize() {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     join_aux_locked(true);
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
 void Index::knn_query_scatter(const float* d_queries, int count, int dim, int k, const ScatterArgs& sc) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) throw std::runtime_error("knn_query_scatter on an empty shard");
@@ -745,7 +826,7 @@ void Index::knn_query_scatter(const float* d_queries, int count, int dim, int k,
 void Index::wait_and_merge(const unsigned* d_flags, int world, unsigned epoch, const int* d_in_ids, const float* d_in_dists, int count, int k,
                            int* d_out_ids, float* d_out_dists, bool sync) {
     {
-        std::lock_guard<std::mutex> lock(mu_);
+        Exclusive lock(mu_);
         HNSW_CUDA_CHECK(cudaSetDevice(device_));
         int* d_err = reinterpret_cast<int*>(d_counters_ + 7);
         launch_wait_merge(d_flags, world, epoch, tuning_.peer_timeout_ms, d_err, d_in_ids, d_in_dists, count, k, d_out_ids, d_out_dists, stream_);
@@ -756,7 +837,7 @@ void Index::wait_and_merge(const unsigned* d_flags, int world, unsigned epoch, c
 
 // Wait for everything queued by knn_query_scatter / wait_and_merge and report a peer that never delivered.
 void Index::partition_sync() {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     int* d_err = reinterpret_cast<int*>(d_counters_ + 7);
     int err = 0;
@@ -771,7 +852,7 @@ void Index::partition_sync() {
 }
 
 void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) {
@@ -809,7 +890,7 @@ void Index::exact_scan_locked(const float* queries, int count, int k, int* out_i
 
 // K3b: tensor-core filter + bit-exact re-ranking; uncertified queries go through K3.  Same answers as exact_knn.
 int Index::exact_knn_tf32(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return 0;
     if (this->count() <= 0) {
@@ -872,7 +953,7 @@ int Index::exact_knn_tf32(const float* queries, int count, int dim, int k, int* 
 // BatchRangeQuery (HNSWIndex.cs:160-168)
 // ---------------------------------------------------------------------------------------------
 void Index::range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     out.assign((size_t)std::max(count, 0), {});
     if (count <= 0 || this->count() <= 0) return;  // HNSWIndex.cs:146
@@ -1007,7 +1088,7 @@ int median_like_reference(std::vector<int>& v) {  // HNSWInfo.cs:45-51
 }  // namespace
 
 std::vector<Index::LayerInfo> Index::get_info() {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     std::vector<LayerInfo> out;
     if (count() <= 0) return out;
@@ -1047,7 +1128,7 @@ std::vector<Index::LayerInfo> Index::get_info() {
 }
 
 std::vector<int> Index::connected_component_counts() {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     std::vector<int> counts;
     if (count() <= 0) return counts;
@@ -1079,8 +1160,14 @@ std::vector<int> Index::connected_component_counts() {
     return counts;
 }
 
+void Index::export_graph_locked(HostGraph& g, bool with_vectors) {
+    Exclusive lock(mu_);
+    join_aux_locked(true);
+    export_graph(g, with_vectors);
+}
+
 void Index::serialize(const std::string& path, bool packed) {
-    std::lock_guard<std::mutex> lock(mu_);
+    Exclusive lock(mu_);
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HostGraph g;
     export_graph(g);

@@ -13,7 +13,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -59,13 +62,13 @@ public:
     // HNSWIndex.Remove(List<int>) (HNSWIndex.cs:83-100); throws when AllowRemovals is false
     void remove(const int* ids, int count);
     // HNSWIndex.Ids() (HNSWIndex.cs:242-245): active ids in ActiveSet order
-    const std::vector<int>& active_ids() const { return active_dense_; }
+    std::vector<int> active_ids() { std::shared_lock<std::shared_mutex> l(mu_); return active_dense_; }
     // `layer`: HNSWIndex.cs:107/129 optional argument (0 = base layer)
     void knn_query(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists, int layer = 0);
     // MultiLayerKnnQuery (HNSWIndex.cs:173-187), batched; returns the layer count, outputs [count][layers][k]
     int multilayer_knn_query(const float* queries, int count, int dim, int k, int max_layer, int min_layer, int* out_ids, float* out_dists);
-    int top_layer() const { return top_; }
-    int entry_point() const { return entry_; }
+    int top_layer() { std::shared_lock<std::shared_mutex> l(mu_); return top_; }
+    int entry_point() { std::shared_lock<std::shared_mutex> l(mu_); return entry_; }
     // queries / outputs already resident in device memory of this index's GPU
     void knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists);
     // the same, only queued on the index's stream (several batches back to back); synchronize() waits for them
@@ -89,19 +92,20 @@ public:
     void range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out);
     void serialize(const std::string& path, bool packed);
 
-    int count() const { return (int)active_dense_.size(); }  // GraphData.Count: active (not removed) items
+    int count() const { return (int)active_dense_.size(); }  // GraphData.Count: active (not removed) items (callers hold mu_)
+    int count_locked() { std::shared_lock<std::shared_mutex> l(mu_); return (int)active_dense_.size(); }
     int length() const { return length_; }                     // GraphData.Length: slots in use
     int dim() const { return dim_; }
-    const Parameters& params() const { return params_; }
-    void set_min_nn(int v) { params_.MinNN = v; }
+    Parameters params() { std::shared_lock<std::shared_mutex> l(mu_); return params_; }
+    void set_min_nn(int v) { Exclusive l(mu_); params_.MinNN = v; }
     void set_tuning(const std::string& key, int value);
     // run on a caller-owned CUDA stream (e.g. torch's current stream) instead of the index's own
     void set_stream(cudaStream_t s);
-    void enable_stats(bool on) { collect_stats_ = on; }
-    IndexStats stats() const { return stats_; }
+    void enable_stats(bool on) { Exclusive l(mu_); collect_stats_ = on; }
+    IndexStats stats() { std::shared_lock<std::shared_mutex> g(mu_); std::lock_guard<std::mutex> l(stats_mu_); return stats_; }
     // cycle / work counters of the construction kernels since creation or the last reset (build_kernels.cu BuildProf)
     void build_profile(unsigned long long out[16], bool reset);
-    void export_graph(HostGraph& g, bool with_vectors = true);  // device -> host copy of the whole index
+    void export_graph_locked(HostGraph& g, bool with_vectors = true);  // device -> host copy of the whole index
 
     // HNSWInfo.LayerInfo (HNSWInfo.cs:19-53): degree statistics of one layer, computed from the exported adjacency
     struct LayerInfo {
@@ -115,6 +119,7 @@ public:
 
 private:
     void ensure_dim(int dim);
+    void export_graph(HostGraph& g, bool with_vectors = true);  // (caller holds mu_ exclusively)
     void exact_scan_locked(const float* queries, int count, int k, int* out_ids, float* out_dists);
     void ensure_capacity(int needed);
     void ensure_upper_rows(int needed);
@@ -183,10 +188,32 @@ private:
     cudaStream_t stream_ = nullptr, own_stream_ = nullptr, aux_stream_ = nullptr;
     cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
     unsigned async_seq_ = 0;
-    bool aux_dirty_ = false;   // work queued on aux_stream_ that the primary stream has not been joined with
+    std::atomic<bool> aux_dirty_{false};   // work queued on aux_stream_ that the primary stream has not been joined with
     void join_aux_locked(bool host_wait);
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
-    std::mutex mu_;
+    // Locking ("thread-safe per operation type", README.md:64-65 of the reference): mu_ is held SHARED by hnsw_knn_query -- any
+    // number of host threads search at once, each with its own stream and scratch (QueryCtx) -- and EXCLUSIVELY by everything
+    // that changes the index, its tuning or the primary scratch (Add, Remove, Serialize, the device-pointer entry points, ...).
+    std::shared_mutex mu_;
+    typedef std::unique_lock<std::shared_mutex> Exclusive;
+    struct QueryCtx {
+        cudaStream_t stream = nullptr, aux = nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+        float* d_q = nullptr;
+        int* d_ids = nullptr;
+        float* d_dists = nullptr;
+        QueryStats* d_stats = nullptr;
+        unsigned* d_counters = nullptr;  // [16]
+        size_t q_cap = 0, out_cap = 0, stats_cap = 0;
+        bool busy = false, created = false;
+    };
+    static constexpr int kQueryContexts = 4;
+    QueryCtx qctx_[kQueryContexts];  // [0] runs on stream_ (set_stream applies), the others on their own streams
+    std::mutex ctx_mu_, stats_mu_;
+    std::condition_variable ctx_cv_;
+    int acquire_ctx();
+    void release_ctx(int i);
+    void prepare_ctx(QueryCtx& c, int count, int k, bool want_stats);
 };
 
 }  // namespace hnsw

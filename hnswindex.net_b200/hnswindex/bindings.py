@@ -100,6 +100,8 @@ def _load():
         "hnsw_set_tuning": (ct.c_int, [ct.c_void_p, ct.c_char_p, ct.c_int]),
         "hnsw_export_layer0": (ct.c_int, [ct.c_void_p, i32p, i32p, i32p, i32p]),
         "hnsw_export_layer": (ct.c_int, [ct.c_void_p, ct.c_int, i32p, i32p]),
+        "hnsw_export_layer0_n": (ct.c_int, [ct.c_void_p, ct.c_int, i32p, i32p, i32p, i32p]),
+        "hnsw_export_layer_n": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, i32p, i32p]),
         "hnsw_snapshot_transcode": (ct.c_int, [ct.c_char_p, ct.c_char_p, ct.c_int]),
         "hnsw_version": (ct.c_char_p, []),
     }
@@ -427,22 +429,31 @@ class Index:
         _check(lib.hnsw_set_tuning(self._h, key.encode(), int(value)))
 
     def export_layer0(self):
-        """(levels[n], rows0[n, stride0] with -1 padding, entry point)."""
+        """(levels[n], rows0[n, stride0] with -1 padding, entry point).  Safe while other threads Add: the copy is bounded by
+        the buffers' size and repeated when the index grew in between."""
         stride, ep = ct.c_int(), ct.c_int()
-        n = lib.hnsw_export_layer0(self._h, None, None, ct.byref(stride), ct.byref(ep))
+        n = lib.hnsw_export_layer0_n(self._h, 0, None, None, ct.byref(stride), ct.byref(ep))
         _check(n)
-        levels = np.empty(n, dtype=np.int32)
-        rows = np.empty((n, stride.value), dtype=np.int32)
-        _check(lib.hnsw_export_layer0(self._h, _ip(levels), _ip(rows), ct.byref(stride), ct.byref(ep)))
-        return levels, rows, ep.value
+        while True:
+            levels = np.empty(n, dtype=np.int32)
+            rows = np.empty((n, stride.value), dtype=np.int32)
+            m = lib.hnsw_export_layer0_n(self._h, n, _ip(levels), _ip(rows), ct.byref(stride), ct.byref(ep))
+            _check(m)
+            if m <= n:
+                return levels[:m], rows[:m], ep.value
+            n = m
 
     def export_layer(self, layer: int):
         stride = ct.c_int()
-        n = lib.hnsw_export_layer(self._h, int(layer), None, ct.byref(stride))
+        n = lib.hnsw_export_layer_n(self._h, int(layer), 0, None, ct.byref(stride))
         _check(n)
-        rows = np.empty((n, stride.value), dtype=np.int32)
-        _check(lib.hnsw_export_layer(self._h, int(layer), _ip(rows), ct.byref(stride)))
-        return rows
+        while True:
+            rows = np.empty((n, stride.value), dtype=np.int32)
+            m = lib.hnsw_export_layer_n(self._h, int(layer), n, _ip(rows), ct.byref(stride))
+            _check(m)
+            if m <= n:
+                return rows[:m]
+            n = m
 
 
 def set_device(device: int) -> None:

@@ -14,8 +14,11 @@
  *
  * Errors never cross the ABI as exceptions: functions return -1 (or a null handle) and the text
  * is available from hnsw_get_last_error_utf8, as in HNSWIndexExports.cs:11-12,27-39.
- * Threading: as the reference (README.md:64-65) -- operations of one type may run concurrently
- * with each other; this implementation additionally serialises calls on one handle internally.
+ * Threading: as the reference (README.md:64-65) -- operations of one type may run concurrently with each other.  Every
+ * handle carries a reader/writer lock: hnsw_knn_query / hnsw_knn_query_layer and the read-only accessors (hnsw_ids,
+ * hnsw_count, hnsw_top_layer, hnsw_entry_point, hnsw_get_stats, hnsw_index_get_params) take it shared -- concurrent
+ * hnsw_knn_query calls from several host threads each run on their own stream and scratch and overlap on the GPU --, every
+ * other call on the handle takes it exclusively, so mixing operation types from different threads is safe too (they queue).
  */
 #ifndef HNSW_B200_H
 #define HNSW_B200_H
@@ -237,10 +240,14 @@ HNSW_API int hnsw_get_wide_profile(hnsw_handle handle, unsigned long long* out16
 HNSW_API int hnsw_set_tuning(hnsw_handle handle, const char* key, int value);
 
 /* Copy the graph to host memory (tests / inspection).  levels[count]; rows0[count][stride0] (-1 padded).
- * Pass NULL pointers to query sizes only.  Returns count, or -1. */
+ * Pass NULL pointers to query sizes only.  Returns count, or -1.  These are two-call interfaces (size, then copy): when
+ * another thread may Add in between, use the _n forms, which copy at most maxNodes nodes and return the current count
+ * (call again with larger buffers when it exceeds maxNodes). */
 HNSW_API int hnsw_export_layer0(hnsw_handle handle, int* levels, int* rows0, int* stride0, int* entryPoint);
+HNSW_API int hnsw_export_layer0_n(hnsw_handle handle, int maxNodes, int* levels, int* rows0, int* stride0, int* entryPoint);
 /* rows of one upper layer: rows[count][strideU], all -1 for nodes below that layer */
 HNSW_API int hnsw_export_layer(hnsw_handle handle, int layer, int* rows, int* stride);
+HNSW_API int hnsw_export_layer_n(hnsw_handle handle, int layer, int maxNodes, int* rows, int* stride);
 
 /* Host-only: read a snapshot file and write it again (packed or unpacked).  Exercises the codec
  * without a GPU; used by the CPU test-suite. */
