@@ -244,6 +244,7 @@ void Index::ensure_search_gvis(int ef) {
 
 void Index::set_stream(cudaStream_t s) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
     stream_ = s ? s : own_stream_;
@@ -255,6 +256,7 @@ void Index::set_stream(cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
@@ -288,17 +290,36 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
     if (nnew == 0) return count;
     const int first = length_;
     ensure_capacity(first + nfresh);
+    // ---- commit point.  Everything above can fail without a trace (the level draws are consumed, as in the reference).  From
+    // here on the host bookkeeping (slots, levels, active set, upper rows) runs ahead of the device work; if that work fails
+    // (allocation, launch, a node lock that could not be taken) the index no longer describes a linked graph, so the handle
+    // is marked unusable instead of answering from a half-inserted batch.
     removed_stack_.resize(stack_top);
+    try {
+        add_committed(vectors, count, dim, lv, ids_new, src_row, nfresh, nreused);
+    } catch (const std::exception& e) {
+        poisoned_ = e.what();
+        throw std::runtime_error(std::string("Add failed after the index had been modified; the handle is unusable now (free it and "
+                                             "rebuild or deserialize): ") + e.what());
+    }
+    return count;
+}
 
+void Index::check_usable() const {
+    if (!poisoned_.empty())
+        throw std::runtime_error("this index is unusable: an earlier Add failed half-way (" + poisoned_ + "); free it and rebuild or deserialize");
+}
+
+void Index::add_committed(const float* vectors, int count, int dim, const std::vector<int>& lv, const std::vector<int>& ids_new,
+                          const std::vector<int>& src_row, int nfresh, int nreused) {
+    const int nnew = (int)ids_new.size();
+    const int first = length_;
     // vectors -> slab rows
     if (nreused == 0 && nnew == count) {
         HNSW_CUDA_CHECK(cudaMemcpy2DAsync(d_vectors_ + (size_t)first * pitch_, (size_t)pitch_ * 4, vectors, (size_t)dim * 4, (size_t)dim * 4,
                                           (size_t)nnew, cudaMemcpyHostToDevice, stream_));
-    } else {
-        for (int j = 0; j < nnew; ++j)
-            HNSW_CUDA_CHECK(cudaMemcpyAsync(d_vectors_ + (size_t)ids_new[j] * pitch_, vectors + (size_t)src_row[j] * dim, (size_t)dim * 4,
-                                            cudaMemcpyHostToDevice, stream_));
     }
+    // (re-used slots / dropped items: the batch is staged once and scattered by a kernel further down, together with the levels)
     // NewNode (GraphData.cs:224-242): rows for layers 0..level.  A reused slot gets fresh upper rows; its layer-0 row was
     // emptied when the old item was removed.
     levels_.resize(first + nfresh);
@@ -319,20 +340,34 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
         new_ids_cap_ = nnew;
     }
     HNSW_CUDA_CHECK(cudaMemcpyAsync(d_new_ids_, ids_new.data(), (size_t)nnew * 4, cudaMemcpyHostToDevice, stream_));
-    if (nreused == 0) {
+    if (nreused == 0 && nnew == count) {
         HNSW_CUDA_CHECK(cudaMemcpyAsync(d_levels_ + first, levels_.data() + first, (size_t)nfresh * 4, cudaMemcpyHostToDevice, stream_));
         HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_ + first, upper_off_.data() + first, (size_t)nfresh * 4, cudaMemcpyHostToDevice, stream_));
         if (metric_ == COSINE) launch_item_norms(d_vectors_, pitch_, dim_, first, nfresh, d_norms_, stream_);
-    } else {
-        const size_t n = levels_.size();
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_levels_, levels_.data(), n * 4, cudaMemcpyHostToDevice, stream_));
-        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_, upper_off_.data(), n * 4, cudaMemcpyHostToDevice, stream_));
-        launch_set_rm_index(d_rm_index_, d_new_ids_, nnew, false, -1, stream_);  // alive again
-        if (metric_ == COSINE) {
-            if (nfresh > 0) launch_item_norms(d_vectors_, pitch_, dim_, first, nfresh, d_norms_, stream_);
-            for (int j = 0; j < nnew; ++j)
-                if (ids_new[j] < first) launch_item_norms(d_vectors_, pitch_, dim_, ids_new[j], 1, d_norms_, stream_);
+    }
+    if (nreused > 0 || nnew != count) {
+        // One staged copy of the input batch, then a kernel scatters every accepted row to its slot and records the level and
+        // first upper row of exactly the touched ids; norms in one launch over the id list (re-adding 100k items after removals
+        // used to cost 100k copies + 100k one-item launches and a re-upload of the whole level arrays).
+        std::vector<int> meta((size_t)nnew * 3);
+        for (int j = 0; j < nnew; ++j) {
+            meta[j] = src_row[j];
+            meta[(size_t)nnew + j] = lv[j];
+            meta[(size_t)2 * nnew + j] = upper_off_[ids_new[j]];
         }
+        float* d_stage = nullptr;
+        int* d_meta = nullptr;
+        HNSW_CUDA_CHECK(cudaMallocAsync(&d_stage, (size_t)count * dim * sizeof(float), stream_));
+        HNSW_CUDA_CHECK(cudaMallocAsync(&d_meta, meta.size() * sizeof(int), stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_stage, vectors, (size_t)count * dim * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        HNSW_CUDA_CHECK(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        launch_scatter_new_items(d_stage, d_meta, d_new_ids_, d_meta + nnew, d_meta + 2 * (size_t)nnew, nnew, dim, pitch_, d_vectors_, d_levels_,
+                                 d_upper_off_, stream_);
+        launch_set_rm_index(d_rm_index_, d_new_ids_, nnew, false, -1, stream_);  // alive again
+        if (metric_ == COSINE) launch_item_norms_ids(d_vectors_, pitch_, dim_, d_new_ids_, nnew, d_norms_, stream_);
+        HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));  // `meta` and the caller's buffer are read by the copies above
+        HNSW_CUDA_CHECK(cudaFreeAsync(d_stage, stream_));
+        HNSW_CUDA_CHECK(cudaFreeAsync(d_meta, stream_));
     }
     length_ = first + nfresh;
 
@@ -398,7 +433,6 @@ int Index::add(const float* vectors, int count, int dim, int* out_ids) {
         HNSW_CUDA_CHECK(cudaMemset(d_counters_ + 2, 0, sizeof(int)));
         throw std::runtime_error("build: a node lock could not be acquired (index may be inconsistent)");
     }
-    return count;
 }
 
 // ActiveSet.cs:69-93
@@ -524,6 +558,7 @@ void Index::remove_chunk(const int* ids, int n) {
 
 void Index::remove(const int* ids, int count) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (!params_.AllowRemovals) throw std::runtime_error("Removals are disabled in this index instance.");  // HNSWIndex.cs:85-86
     if (count <= 0) return;
@@ -633,6 +668,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
     std::shared_lock<std::shared_mutex> shared(mu_, std::defer_lock);
     Exclusive exclusive(mu_, std::defer_lock);
     if (tuning_.vis_global_search > 0) exclusive.lock(); else shared.lock();
+    check_usable();
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) {  // HNSWIndex.cs:109
         fill_empty(out_ids, out_dists, (size_t)count * k);
@@ -713,6 +749,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
 
 void Index::knn_query_device(const float* d_queries, int count, int dim, int k, int* d_ids, float* d_dists) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) throw std::runtime_error("knn_query_device on an empty index");
@@ -737,6 +774,7 @@ void Index::knn_query_device(const float* d_queries, int count, int dim, int k, 
 // outputs are [count][L][k] (pass null pointers to query L only).
 int Index::multilayer_knn_query(const float* queries, int count, int dim, int k, int max_layer, int min_layer, int* out_ids, float* out_dists) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (this->count() <= 0 || k < 1) return 0;  // HNSWIndex.cs:176
     if (max_layer < 0) throw std::out_of_range("maxLayer must not be negative");
@@ -813,6 +851,7 @@ void Index::synchronize() {
 
 void Index::knn_query_scatter(const float* d_queries, int count, int dim, int k, const ScatterArgs& sc) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) throw std::runtime_error("knn_query_scatter on an empty shard");
@@ -853,6 +892,7 @@ void Index::partition_sync() {
 
 void Index::exact_knn(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) {
@@ -891,6 +931,7 @@ void Index::exact_scan_locked(const float* queries, int count, int k, int* out_i
 // K3b: tensor-core filter + bit-exact re-ranking; uncertified queries go through K3.  Same answers as exact_knn.
 int Index::exact_knn_tf32(const float* queries, int count, int dim, int k, int* out_ids, float* out_dists) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     if (count <= 0 || k < 1) return 0;
     if (this->count() <= 0) {
@@ -954,6 +995,7 @@ int Index::exact_knn_tf32(const float* queries, int count, int dim, int k, int* 
 // ---------------------------------------------------------------------------------------------
 void Index::range_query(const float* queries, int count, int dim, float range, std::vector<std::vector<std::pair<float, int>>>& out) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     out.assign((size_t)std::max(count, 0), {});
     if (count <= 0 || this->count() <= 0) return;  // HNSWIndex.cs:146
@@ -1089,6 +1131,7 @@ int median_like_reference(std::vector<int>& v) {  // HNSWInfo.cs:45-51
 
 std::vector<Index::LayerInfo> Index::get_info() {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     std::vector<LayerInfo> out;
     if (count() <= 0) return out;
@@ -1129,6 +1172,7 @@ std::vector<Index::LayerInfo> Index::get_info() {
 
 std::vector<int> Index::connected_component_counts() {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     std::vector<int> counts;
     if (count() <= 0) return counts;
@@ -1162,12 +1206,14 @@ std::vector<int> Index::connected_component_counts() {
 
 void Index::export_graph_locked(HostGraph& g, bool with_vectors) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);
     export_graph(g, with_vectors);
 }
 
 void Index::serialize(const std::string& path, bool packed) {
     Exclusive lock(mu_);
+    check_usable();
     join_aux_locked(true);  // batches still queued on the auxiliary stream (knn_query_device_async) finish first
     HostGraph g;
     export_graph(g);

@@ -119,6 +119,10 @@ public:
 
 private:
     void ensure_dim(int dim);
+    void check_usable() const;   // throws when an earlier Add failed after its commit point
+    void add_committed(const float* vectors, int count, int dim, const std::vector<int>& lv, const std::vector<int>& ids_new,
+                       const std::vector<int>& src_row, int nfresh, int nreused);
+    std::string poisoned_;
     void export_graph(HostGraph& g, bool with_vectors = true);  // (caller holds mu_ exclusively)
     void exact_scan_locked(const float* queries, int count, int k, int* out_ids, float* out_dists);
     void ensure_capacity(int needed);

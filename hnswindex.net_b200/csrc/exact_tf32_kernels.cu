@@ -1004,7 +1004,7 @@ void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_querie
         if (use_tcgen05) {                                                                                                      \
             const size_t tsmem = tc5_scan_smem(g.dim, kp);                                                                      \
             HNSW_CUDA_CHECK(cudaFuncSetAttribute(exact_tc5_scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)); \
-            if (tcgen05_mode == 2) { /* experimental warp-specialised variant */                                                \
+            if (tcgen05_mode == 2) { /* warp-specialised variant (default)      */                                                \
                 HNSW_CUDA_CHECK(cudaFuncSetAttribute(exact_tc5ws_scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)); \
                 exact_tc5ws_scan_kernel<M><<<dim3(chunks, (nq + tc5::kM - 1) / tc5::kM), 2 * tc5::kM, tsmem, stream>>>(g, d_queries, nq, kp, chunk_items, d_xaux, d_part); \
             } else                                                                                                              \

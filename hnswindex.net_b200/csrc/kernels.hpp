@@ -20,8 +20,9 @@ struct Tuning {
     int build_specialized = 1;  // the C5-shaped select kernel instantiation (short rows, MaxCandidates <= 1024, 16-bit tags)
     int async_overlap = 1;    // hnsw_knn_query_device_async alternates two streams (consecutive batches overlap in their tails)
     int blocks_per_sm = 0;    // 0 = occupancy query
-    int exact_tcgen05 = 1;    // exact_knn_tf32: pass A on tcgen05 / TMEM where the shape allows (rows <= 128 floats), else mma.sync;
-                              // 2 = experimental warp-specialised tcgen05 kernel, 0 = always mma.sync
+    int exact_tcgen05 = 2;    // exact_knn_tf32: pass A on tcgen05 / TMEM where the shape allows (rows <= 128 floats), else mma.sync;
+                              // 2 = warp-specialised kernel (4 producer + 4 consumer warps; 49.8 ms for 10k x 1M x 128 on B200),
+                              // 1 = the earlier 4-warp tcgen05 kernel (68.8 ms), 0 = always mma.sync
     int wl_min_ef = 256;      // one-warp-per-query searches with ef at or above this keep their candidates in wide.cuh's non-shifting
                               // list (0 = never): the shifting list of beam.cuh costs O(ef / 32) chunk moves per accepted candidate
     int wide_min_ef = 1024;    // layer-0 searches with ef = max(MinNN, k) at or above this run on the CTA-per-query kernel with the
@@ -64,6 +65,10 @@ void launch_multilayer_search(int metric, const GraphView& g, const float* d_que
 
 // per-item sqrt((double)normA) in the cosine metric's accumulation order
 void launch_item_norms(const float* d_vectors, int pitch, int dim, int first, int count, double* d_norm_sqrt, cudaStream_t stream);
+void launch_item_norms_ids(const float* d_vectors, int pitch, int dim, const int* d_ids, int count, double* d_norm_sqrt, cudaStream_t stream);
+// Add into re-used slots: rows src_row[j] of the staged batch d_src [.][dim] -> slab rows d_ids[j]; levels / upper_off of those ids
+void launch_scatter_new_items(const float* d_src, const int* d_src_row, const int* d_ids, const int* d_lv, const int* d_uoff, int n, int dim,
+                              int pitch, float* d_vectors, int* d_levels, int* d_upper_off, cudaStream_t stream);
 
 // K4+K5: for the new nodes d_new_ids[0..count): descent, per-layer beam search (ef = MaxCandidates) against the
 // graph as it stands, relative-neighbour selection, write the node's own rows.
@@ -97,7 +102,7 @@ int exact_tf32_candidates(int k);
 int exact_tf32_block_queries(int dim, int k);  // 64 / 32 / 16, or 0 when dim / k do not fit the variant
 size_t exact_tf32_scratch_bytes(int nq, int k, int count);
 // tcgen05_mode: 0 = mma.sync; 1 = pass A as tcgen05.mma kind::tf32 with the accumulator in TMEM (rows <= 128 floats, else
-// the mma.sync kernel); 2 = the experimental warp-specialised tcgen05 kernel (not yet run on a GPU)
+// the mma.sync kernel); 2 = the warp-specialised tcgen05 kernel (4 producer + 4 consumer warps; the default)
 bool exact_tcgen05_supported(int dim, int k);
 void launch_exact_knn_tf32(int metric, const GraphView& g, const float* d_queries, int nq, int k, int* d_ids, float* d_dists, int* d_fail,
                            void* d_scratch, size_t scratch_bytes, bool refresh_aux, int tcgen05_mode, cudaStream_t stream);

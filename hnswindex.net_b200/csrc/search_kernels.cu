@@ -150,6 +150,34 @@ __global__ void item_norms_kernel(const float* __restrict__ vectors, int pitch, 
     if (active && (lane & 1) == 0) norm_sqrt[id] = r;
 }
 
+// the same for a list of ids (slots re-used by Add after removals)
+__global__ void item_norms_ids_kernel(const float* __restrict__ vectors, int pitch, int dim, const int* __restrict__ ids, int count,
+                                      double* __restrict__ norm_sqrt) {
+    const int lane = threadIdx.x & 31;
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const bool active = pair < count;
+    const int id = __ldg(ids + (active ? pair : 0));
+    const double r = pair_norm_sqrt(vectors + (size_t)id * pitch, dim, lane & 1);
+    if (active && (lane & 1) == 0) norm_sqrt[id] = r;
+}
+
+// Add into re-used slots: one warp per new item copies row src_row[j] of the staged input batch into slab row ids[j]
+// (padding floats zeroed) and records the item's level and first upper row.
+__global__ void scatter_new_items_kernel(const float* __restrict__ src, const int* __restrict__ src_row, const int* __restrict__ ids,
+                                         const int* __restrict__ lv, const int* __restrict__ uoff, int n, int dim, int pitch,
+                                         float* __restrict__ vectors, int* __restrict__ levels, int* __restrict__ upper_off) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= n) return;
+    const int id = __ldg(ids + j);
+    const float* s = src + (size_t)__ldg(src_row + j) * dim;
+    float* d = vectors + (size_t)id * pitch;
+    for (int i = lane; i < pitch; i += 32) d[i] = i < dim ? __ldg(s + i) : 0.f;
+    if (lane == 0) {
+        levels[id] = __ldg(lv + j);
+        upper_off[id] = __ldg(uoff + j);
+    }
+}
+
 int device_sm_count() {
     int dev = 0, sms = 0;
     HNSW_CUDA_CHECK(cudaGetDevice(&dev));
@@ -280,6 +308,23 @@ void launch_multilayer_search(int metric, const GraphView& g, const float* d_que
         default: HNSW_LAUNCH_ML(UCOSINE) break;
     }
 #undef HNSW_LAUNCH_ML
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_item_norms_ids(const float* d_vectors, int pitch, int dim, const int* d_ids, int count, double* d_norm_sqrt, cudaStream_t stream) {
+    if (count <= 0) return;
+    const int threads = 256;
+    item_norms_ids_kernel<<<(count * 2 + threads - 1) / threads, threads, 0, stream>>>(d_vectors, pitch, dim, d_ids, count, d_norm_sqrt);
+    HNSW_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_scatter_new_items(const float* d_src, const int* d_src_row, const int* d_ids, const int* d_lv, const int* d_uoff, int n, int dim,
+                              int pitch, float* d_vectors, int* d_levels, int* d_upper_off, cudaStream_t stream) {
+    if (n <= 0) return;
+    const int threads = 256;
+    const long long blocks = ((long long)n * 32 + threads - 1) / threads;
+    scatter_new_items_kernel<<<(unsigned)blocks, threads, 0, stream>>>(d_src, d_src_row, d_ids, d_lv, d_uoff, n, dim, pitch, d_vectors, d_levels,
+                                                                      d_upper_off);
     HNSW_CUDA_CHECK(cudaGetLastError());
 }
 

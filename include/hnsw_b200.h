@@ -169,7 +169,7 @@ HNSW_API int hnsw_exact_knn_tf32(hnsw_handle handle, const float* queries, int c
 /* With hnsw_set_tuning(handle, "exact_tcgen05", 1) the GEMM of hnsw_exact_knn_tf32 runs as tcgen05.mma kind::tf32 with the
  * accumulator in tensor memory instead of mma.sync, for the shapes this returns 1 for (rows of at most 128 floats and a
  * k whose candidate lists fit in shared memory); other shapes keep using the mma.sync kernel.  -1 on error.
- * ("exact_tcgen05": 1 is the default, 0 forces mma.sync, 2 selects an experimental warp-specialised tcgen05 kernel.) */
+ * ("exact_tcgen05": 2 = warp-specialised tcgen05 kernel, the default; 1 = the earlier 4-warp tcgen05 kernel; 0 forces mma.sync.) */
 HNSW_API int hnsw_exact_tcgen05_supported(int dim, int k);
 
 /* Merge `parts` per-partition top-k results (device memory, [parts][count][k], rows ascending,

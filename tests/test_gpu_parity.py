@@ -699,3 +699,44 @@ def test_range_query_exports_agree(hnswindex):
         finally:
             hnswindex.lib.hnsw_free_results(ids_pp, dists_pp, n)
     assert max(len(x) for x in ix.range_query(q, 5.0)[0]) == 6000     # everything is in range: > 2048 keys per query
+
+
+def test_failed_add_poisons_the_handle(hnswindex):
+    # Add commits its host bookkeeping before the device work; when that work fails the handle must not keep
+    # answering from a half-inserted batch.  MaxCandidates far beyond what one warp's shared memory holds makes the first
+    # insertion batch fail at launch.
+    rng = np.random.default_rng(1)
+    ix = hnswindex.Index(16, "sq_euclid")
+    ix.set_max_candidates(200000)
+    with pytest.raises(RuntimeError, match="Add failed after the index had been modified"):
+        ix.add(rng.random((50, 16), dtype=np.float32))
+    with pytest.raises(RuntimeError, match="unusable"):
+        ix.knn_query(rng.random((3, 16), dtype=np.float32), 2)
+    with pytest.raises(RuntimeError, match="unusable"):
+        ix.add(rng.random((3, 16), dtype=np.float32))
+    # a healthy index next to it is unaffected
+    ok = hnswindex.Index(16, "sq_euclid")
+    ids = ok.add(rng.random((50, 16), dtype=np.float32))
+    assert len(ids) == 50 and ok.knn_query(rng.random((3, 16), dtype=np.float32), 2)[0].shape == (3, 2)
+
+
+def test_readd_into_removed_slots_in_one_call(hnswindex, oracle):
+    # slot re-use goes through one staged copy + a scatter kernel: ids, vectors (exact top-1 = itself), norms (cosine) and levels
+    rng = np.random.default_rng(2)
+    data = rng.random((6000, 40), dtype=np.float32)
+    ix = hnswindex.Index(40, "cosine")
+    ix.set_collection_size(8000); ix.set_min_nn(32)
+    ids = ix.add(data)
+    gone = ids[100:3100]
+    ix.remove(gone)
+    fresh = rng.random((3500, 40), dtype=np.float32)
+    new_ids = ix.add(fresh)                      # 3000 re-used slots (most recently removed first) + 500 new ones
+    assert new_ids[:3000].tolist() == gone[::-1].tolist() and new_ids[3000:].tolist() == list(range(6000, 6500))
+    e_ids, e_d = ix.exact_knn(fresh, 1)
+    assert np.array_equal(e_ids[:, 0], new_ids) and np.abs(e_d[:, 0]).max() < 1e-6
+    g_ids, _ = ix.knn_query(fresh, 1)
+    assert (g_ids[:, 0] == new_ids).mean() > 0.9
+    levels, rows0, _ = ix.export_layer0()
+    assert (rows0[new_ids] >= 0).sum(axis=1).min() >= 1          # every re-added node is linked
+    ref_levels = oracle.draw_levels(31337, 1.0 / np.log(16.0), 9500)
+    assert levels[new_ids].tolist() == list(ref_levels[6000:9500])  # the level stream continues where the first Add stopped

@@ -2,8 +2,9 @@
 GPU tests of the tensor-core exact top-k (hnsw_exact_knn_tf32, csrc/exact_tf32_kernels.cu): a 3xTF32 GEMM ranks all
 pairs approximately, k + slack candidates per query are evaluated with the bit-exact metric, uncertified queries go
 through the FFMA scan -- so the answers must equal hnsw_exact_knn's to the bit (which test_gpu_parity.py pins on the
-oracle's brute force).  The GEMM exists twice: tcgen05.mma + TMEM (rows of at most 128 floats, tuning key
-"exact_tcgen05" = 1, the default) and mma.sync (every other shape, or "exact_tcgen05" = 0); both are covered.
+oracle's brute force).  The GEMM exists three times: tcgen05.mma + TMEM for rows of at most 128 floats -- warp-specialised
+(4 producer + 4 consumer warps, tuning key "exact_tcgen05" = 2, the default) and the earlier 4-warp kernel (= 1) -- and
+mma.sync (every other shape, or "exact_tcgen05" = 0); all three are covered.
 """
 import time
 
@@ -37,13 +38,13 @@ def _same(ix, q, k):
     """scan == tensor-core variant for both GEMM kernels; returns the larger number of fall-backs"""
     a_ids, a_d = ix.exact_knn(q, k)
     fb = 0
-    for tcgen05 in (1, 0):
+    for tcgen05 in (2, 1, 0):
         ix.set_tuning("exact_tcgen05", tcgen05)
         b_ids, b_d = ix.exact_knn(q, k, tensor_cores=True)
         assert np.array_equal(a_ids, b_ids), f"ids differ in {(a_ids != b_ids).any(axis=1).sum()} of {len(q)} rows (tcgen05={tcgen05})"
         assert np.array_equal(a_d.view(np.uint32), b_d.view(np.uint32)), f"distances are not bit-identical (tcgen05={tcgen05})"
         fb = max(fb, ix.last_exact_fallbacks)
-    ix.set_tuning("exact_tcgen05", 1)
+    ix.set_tuning("exact_tcgen05", 2)
     return fb
 
 

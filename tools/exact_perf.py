@@ -33,7 +33,7 @@ out = {"n": n, "nq": nq, "dim": 128}
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 for k in (10,) if reps == 1 else (10, 100):
     ref = None
-    for name, tc, t5 in (("scan", False, 0), ("mma_sync", True, 0), ("tcgen05", True, 1)):
+    for name, tc, t5 in (("scan", False, 0), ("mma_sync", True, 0), ("tcgen05", True, 1), ("tcgen05_ws", True, 2)):
         ix.set_tuning("exact_tcgen05", t5)
         ix.exact_knn(q[:64], k, tensor_cores=tc)
         best = 1e9
