@@ -18,6 +18,7 @@ struct Tuning {
                               // kernel fills the SM slots freed in the tails.  Off: -4.5 % build time, but the next batch
                               // then sees the previous batch's reverse links only partly and recall@10 drops 0.2 pt
     int build_specialized = 1;  // the C5-shaped select kernel instantiation (short rows, MaxCandidates <= 1024, 16-bit tags)
+    int sync_pieces = 0;      // hnsw_knn_query: pieces a large batch is split into, alternating two streams (0 = 2 for page-locked, 4 for pageable buffers)
     int async_overlap = 1;    // hnsw_knn_query_device_async alternates two streams (consecutive batches overlap in their tails)
     int blocks_per_sm = 0;    // 0 = occupancy query
     int exact_tcgen05 = 2;    // exact_knn_tf32: pass A on tcgen05 / TMEM where the shape allows (rows <= 128 floats), else mma.sync;
