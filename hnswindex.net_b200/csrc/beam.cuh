@@ -53,7 +53,7 @@ struct WarpCounters {
 __host__ __device__ inline size_t warp_scratch_bytes(int pitch, int cap, int vis_size, int cand_cap) {
     size_t b = kStageBytes;
     b += (size_t)((pitch + 3) & ~3) * 4;
-    b += (size_t)cap * 8;
+    b += ((size_t)cap * 8 + 15) & ~(size_t)15;  // the visited table behind the list stays 16-byte aligned
     b += (size_t)vis_size * 4;
     b += (size_t)cand_cap * 8;
     return (b + 127) & ~(size_t)127;
@@ -66,7 +66,7 @@ __device__ __forceinline__ WarpScratch carve_scratch(unsigned char* base, int pi
     s.q = reinterpret_cast<float*>(base);
     base += (size_t)((pitch + 3) & ~3) * 4;
     s.list = reinterpret_cast<u64*>(base);
-    base += (size_t)cap * 8;
+    base += ((size_t)cap * 8 + 15) & ~(size_t)15;
     s.vis = reinterpret_cast<uint32_t*>(base);
     base += (size_t)vis_size * 4;
     s.cand_id = reinterpret_cast<int*>(base);

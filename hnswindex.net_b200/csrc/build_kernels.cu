@@ -28,8 +28,9 @@ enum BuildProf : int {
     BP_CYC_LINK, BP_CYC_PRUNE, BP_PRUNES, BP_NDIST_PRUNE, BP_CYC_LOCK, BP_CYC_SELECT_KERNEL, BP_LINKS, BP_WORDS
 };
 
-template <int METRIC, int SPEC>
-__global__ void __launch_bounds__(kThreads, 4)
+// WARPS = warps per block: 4, or 3 with six blocks per SM (18 instead of 16 resident warps; needs <= 112 registers)
+template <int METRIC, int SPEC, int WARPS = 4>
+__global__ void __launch_bounds__(32 * WARPS, WARPS == 3 ? 6 : 4)
 build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int efc, int list_cap, int vis_size, int cand_cap,
                     int sel_cap, unsigned* work_counter, u64* prof, uint32_t* gvis, int gvis_slots) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -254,9 +255,27 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
             /* the C5 shape: rows of one staging segment, MaxCandidates <= 1024, 16-bit tags -- no long-row / large-list code */ \
             constexpr int S = kSpecVis16 | kSpecShortRows | kSpecMidList;                                                       \
             const int g1 = persistent_grid(build_select_kernel<M, S>, smem_sel, t, count, w1);                                 \
-            const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
-            build_select_kernel<M, S><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                 \
-                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
+            /* three-warp blocks when six of them fit where four four-warp blocks do */                                         \
+            int per3 = 0;                                                                                                        \
+            if (w1 == 4 && t.build_warps3 != 0 && smem_sel * 3 <= (size_t)48 * 1024 * 4) {                                      \
+                static bool optin3 = false;                                                                                      \
+                if (!optin3) {                                                                                                   \
+                    HNSW_CUDA_CHECK(cudaFuncSetAttribute(build_select_kernel<M, S, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+                    optin3 = true;                                                                                               \
+                }                                                                                                                \
+                HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, build_select_kernel<M, S, 3>, 96, smem_sel * 3)); \
+            }                                                                                                                    \
+            int per4 = 0;                                                                                                        \
+            HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per4, build_select_kernel<M, S>, 128, smem_sel * 4)); \
+            if (per3 * 3 > per4 * 4 && t.blocks_per_sm <= 0) {                                                                  \
+                const int g3 = std::max(1, std::min((count + 2) / 3, device_sm_count() * per3));                                \
+                build_select_kernel<M, S, 3><<<g3, 96, smem_sel * 3, stream>>>(                                                 \
+                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, nullptr, 0); \
+            } else {                                                                                                             \
+                const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                \
+                build_select_kernel<M, S><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                             \
+                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
+            }                                                                                                                    \
         } else if (vis16) {                                                                                                     \
             const int g1 = persistent_grid(build_select_kernel<M, kSpecVis16>, smem_sel, t, count, w1);                        \
             const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \

@@ -13,15 +13,24 @@ struct BuildScratch {
 
 
 
+// The heuristic's two vector slots are only live between two beam searches, when the visited table is dead (every beam
+// search starts by clearing it): when the table is large enough the slots live inside it (1 KB per warp at dim 128, which
+// is what lets 18 instead of 16 warps of the select kernel share an SM).
+__host__ __device__ inline bool cvec_in_vis(int pitch, int vis_size) { return (size_t)vis_size * 4 >= (size_t)((pitch + 3) & ~3) * 8; }
 __host__ __device__ inline size_t build_scratch_bytes(int pitch, int cap, int vis_size, int cand_cap, int sel_cap) {
-    return warp_scratch_bytes(pitch, cap, vis_size, cand_cap) + (((size_t)((pitch + 3) & ~3) * 8 + (size_t)sel_cap * 4 + 127) & ~(size_t)127);
+    const size_t cvec = cvec_in_vis(pitch, vis_size) ? 0 : (size_t)((pitch + 3) & ~3) * 8;
+    return warp_scratch_bytes(pitch, cap, vis_size, cand_cap) + ((cvec + (size_t)sel_cap * 4 + 127) & ~(size_t)127);
 }
 __device__ __forceinline__ BuildScratch carve_build(unsigned char* base, int pitch, int cap, int vis_size, int cand_cap, int sel_cap, int lane) {
     BuildScratch b;
     b.s = carve_scratch(base, pitch, cap, vis_size, cand_cap, lane);
     base += warp_scratch_bytes(pitch, cap, vis_size, cand_cap);
-    b.cvec = reinterpret_cast<float*>(base);
-    base += (size_t)((pitch + 3) & ~3) * 8;
+    if (cvec_in_vis(pitch, vis_size)) {
+        b.cvec = reinterpret_cast<float*>(b.s.vis);  // 16-byte aligned (carve_scratch)
+    } else {
+        b.cvec = reinterpret_cast<float*>(base);
+        base += (size_t)((pitch + 3) & ~3) * 8;
+    }
     b.sel = reinterpret_cast<int*>(base);
     return b;
 }
