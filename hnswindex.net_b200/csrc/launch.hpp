@@ -40,19 +40,28 @@ inline LaunchShape launch_shape(Kern kern, size_t smem_per_warp) {
     int max_optin = 0;
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&shape.sms, cudaDevAttrMultiProcessorCount, dev));
-    shape.warps = kWarpsPerBlock;
-    while (shape.warps > 1 && smem_per_warp * shape.warps > (size_t)max_optin) --shape.warps;  // 4, 3, 2 or 1 warps per block
-    const size_t smem = smem_per_warp * shape.warps;
-    if (smem > (size_t)max_optin)
+    int wmax = kWarpsPerBlock;
+    while (wmax > 1 && smem_per_warp * wmax > (size_t)max_optin) --wmax;  // 4, 3, 2 or 1 warps per block
+    if (smem_per_warp * wmax > (size_t)max_optin)
         throw std::runtime_error("search width / MaxCandidates / MaxEdges too large for shared memory: one warp needs " +
-                                 std::to_string(smem) + " B, the SM offers " + std::to_string(max_optin));
+                                 std::to_string(smem_per_warp * wmax) + " B, the SM offers " + std::to_string(max_optin));
     size_t& have = optin[std::make_pair(dev, fn)];
-    if (smem > have) {
-        HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        have = smem;
+    if (smem_per_warp * wmax > have) {
+        HNSW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_per_warp * wmax)));
+        have = smem_per_warp * wmax;
     }
+    // Blocks of fewer warps waste less of the SM's shared memory to granularity (one warp's scratch is 10-80 KB): take the
+    // block size with the most resident WARPS, the larger block on ties (the C2 hot path stays at 5 x 4).
+    shape.warps = wmax;
     shape.per_sm = 0;
-    HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shape.per_sm, kern, 32 * shape.warps, smem));
+    for (int w = wmax; w >= 1; --w) {
+        int per = 0;
+        HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, 32 * w, smem_per_warp * w));
+        if (per * w > shape.per_sm * shape.warps) {
+            shape.warps = w;
+            shape.per_sm = per;
+        }
+    }
     if (shape.per_sm < 1) shape.per_sm = 1;
     cache.emplace(key, shape);
     return shape;
