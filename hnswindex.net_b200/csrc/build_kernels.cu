@@ -32,7 +32,7 @@ enum BuildProf : int {
 template <int METRIC, int SPEC, int WARPS = 4>
 __global__ void __launch_bounds__(32 * WARPS, WARPS == 3 ? 6 : 4)
 build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int efc, int list_cap, int vis_size, int cand_cap,
-                    int sel_cap, unsigned* work_counter, u64* prof, uint32_t* gvis, int gvis_slots) {
+                    int sel_cap, unsigned* work_counter, u64* prof, uint32_t* gvis, int gvis_slots, int flags) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, vis_size, cand_cap, sel_cap);
@@ -67,7 +67,7 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
         for (int layer = min(level, g.top_layer); layer >= 0; --layer) {
             BeamState st;
             t0 = clock64();
-            beam_search<METRIC, SPEC>(g, s, qn, layer, cur, cur_d, efc, st, lane, wc);
+            beam_search<METRIC, SPEC>(g, s, qn, layer, cur, cur_d, efc, st, lane, wc, flags);
             t1 = clock64();
             cyc_search += t1 - t0;
             const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
@@ -141,57 +141,73 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __rest
     unsigned n_prunes = 0, nd_prune = 0, n_links = 0;
     const long long t_begin = clock64();
 
+    // one reverse link: append v to the row of n on `layer`, or re-run the heuristic when the row is full
+    auto link_one = [&](int v, int n, int layer) {
+        const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
+        const long long tl = clock64();
+        if (!lock_node(g.locks, n, lane, error_flag)) return;
+        cyc_lock += clock64() - tl;
+        ++n_links;
+        int stride;
+        int* row = row_ptr_mut(g, n, layer, stride);
+        // current row of n, read past L1 (other SMs update it under the same lock)
+        int cnt = 0;
+        for (int rb = 0; rb < stride; rb += 32) {
+            const int slot = rb + lane;
+            const int nb = slot < stride ? __ldcg(row + slot) : -1;
+            if (nb >= 0) s.cand_id[slot] = nb;
+            cnt += __popc(__ballot_sync(FULL, nb >= 0));
+        }
+        __syncwarp();
+        if (cnt < maxE) {
+            if (lane == 0) row[cnt] = v;  // EdgeList.Add, GraphConnector.cs:207
+        } else {
+            // PruneOverflow (GraphConnector.cs:222-262): heuristic over the row plus the new link
+            const long long tp = clock64();
+            ++n_prunes;
+            if (lane == 0) s.cand_id[cnt] = v;
+            const int m = cnt + 1;
+            load_vector(g, n, s.q, lane);
+            double nn = 0.0;
+            if (METRIC == COSINE) nn = __ldg(g.norm_sqrt + n);
+            batch_dist<METRIC>(g, s, nn, m, lane);
+            nd_prune += m;
+            BeamState st;
+            st.n = 0; st.ef = list_cap; st.far_ord = 0xFFFFFFFFu; st.cursor = 0;
+            for (int j = 0; j < m; ++j) list_insert(s.list, st, make_key(s.cand_dist[j], s.cand_id[j]), lane);
+            const int nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, nd_prune);
+            for (int j = lane; j < stride; j += 32) row[j] = j < nsel ? b.sel[j] : -1;
+            cyc_prune += clock64() - tp;
+        }
+        unlock_node(g.locks, n, lane);
+    };
+
+    // Work items: [0, count x stride0) = one (new node, layer-0 slot) pair each -- a reverse link is a short, latency-bound
+    // critical section (lock, read the row, append or prune), so a warp per PAIR instead of a warp per node walking its
+    // 32 slots one after another keeps ~30x more of them in flight and balances the rare, long prunes; a new node's own
+    // rows are never a link target inside its batch, so the pairs are independent.  [count x stride0, + count) = the upper
+    // layers of one new node each (6 % of the nodes have any).
+    const unsigned pairs = (unsigned)count * (unsigned)g.stride0;
     for (;;) {
         unsigned wi = 0;
         if (lane == 0) wi = atomicAdd(work_counter, 1u);
         wi = __shfl_sync(FULL, wi, 0);
-        if (wi >= (unsigned)count) break;
-        const int v = __ldg(new_ids + wi);
-        const int level = __ldg(levels + v);
-
-        for (int layer = min(level, g.top_layer); layer >= 0; --layer) {
-            const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
-            int vstride;
-            const int* vrow = row_ptr_mut(g, v, layer, vstride);
-            for (int t = 0; t < vstride; ++t) {
-                const int n = __ldcg(vrow + t);
-                if (n < 0) break;
-                const long long tl = clock64();
-                if (!lock_node(g.locks, n, lane, error_flag)) continue;
-                cyc_lock += clock64() - tl;
-                ++n_links;
-                int stride;
-                int* row = row_ptr_mut(g, n, layer, stride);
-                // current row of n, read past L1 (other SMs update it under the same lock)
-                int cnt = 0;
-                for (int rb = 0; rb < stride; rb += 32) {
-                    const int slot = rb + lane;
-                    const int nb = slot < stride ? __ldcg(row + slot) : -1;
-                    if (nb >= 0) s.cand_id[slot] = nb;
-                    cnt += __popc(__ballot_sync(FULL, nb >= 0));
+        if (wi >= pairs + (unsigned)count) break;
+        if (wi < pairs) {
+            const int v = __ldg(new_ids + wi / (unsigned)g.stride0);
+            const int n = __ldcg(g.adj0 + (size_t)v * g.stride0 + wi % (unsigned)g.stride0);
+            if (n >= 0) link_one(v, n, 0);
+        } else {
+            const int v = __ldg(new_ids + (wi - pairs));
+            const int level = __ldg(levels + v);
+            for (int layer = min(level, g.top_layer); layer >= 1; --layer) {
+                int vstride;
+                const int* vrow = row_ptr_mut(g, v, layer, vstride);
+                for (int t = 0; t < vstride; ++t) {
+                    const int n = __ldcg(vrow + t);
+                    if (n < 0) break;
+                    link_one(v, n, layer);
                 }
-                __syncwarp();
-                if (cnt < maxE) {
-                    if (lane == 0) row[cnt] = v;  // EdgeList.Add, GraphConnector.cs:207
-                } else {
-                    // PruneOverflow (GraphConnector.cs:222-262): heuristic over the row plus the new link
-                    const long long tp = clock64();
-                    ++n_prunes;
-                    if (lane == 0) s.cand_id[cnt] = v;
-                    const int m = cnt + 1;
-                    load_vector(g, n, s.q, lane);
-                    double nn = 0.0;
-                    if (METRIC == COSINE) nn = __ldg(g.norm_sqrt + n);
-                    batch_dist<METRIC>(g, s, nn, m, lane);
-                    nd_prune += m;
-                    BeamState st;
-                    st.n = 0; st.ef = list_cap; st.far_ord = 0xFFFFFFFFu; st.cursor = 0;
-                    for (int j = 0; j < m; ++j) list_insert(s.list, st, make_key(s.cand_dist[j], s.cand_id[j]), lane);
-                    const int nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, nd_prune);
-                    for (int j = lane; j < stride; j += 32) row[j] = j < nsel ? b.sel[j] : -1;
-                    cyc_prune += clock64() - tp;
-                }
-                unlock_node(g.locks, n, lane);
             }
         }
         __syncwarp();
@@ -270,28 +286,28 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
             if (per3 * 3 > per4 * 4 && t.blocks_per_sm <= 0) {                                                                  \
                 const int g3 = std::max(1, std::min((count + 2) / 3, device_sm_count() * per3));                                \
                 build_select_kernel<M, S, 3><<<g3, 96, smem_sel * 3, stream>>>(                                                 \
-                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, nullptr, 0); \
+                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, nullptr, 0, t.build_flags); \
             } else {                                                                                                             \
                 const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                \
                 build_select_kernel<M, S><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                             \
-                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
+                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots, t.build_flags); \
             }                                                                                                                    \
         } else if (vis16) {                                                                                                     \
             const int g1 = persistent_grid(build_select_kernel<M, kSpecVis16>, smem_sel, t, count, w1);                        \
             const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
             build_select_kernel<M, kSpecVis16><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                        \
-                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots, t.build_flags); \
         } else {                                                                                                                \
             const int g1 = persistent_grid(build_select_kernel<M, 0>, smem_sel, t, count, w1);                                 \
             const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
             build_select_kernel<M, 0><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                 \
-                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots); \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots, t.build_flags); \
         }                                                                                                                       \
         if (link_stream != stream) { /* the links of this batch follow its select kernel, on their own stream */             \
             HNSW_CUDA_CHECK(cudaEventRecord(select_done, stream));                                                             \
             HNSW_CUDA_CHECK(cudaStreamWaitEvent(link_stream, select_done, 0));                                                 \
         }                                                                                                                       \
-        const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, count, w2);                                         \
+        const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, (int)std::min<long long>((long long)count * (g.stride0 + 1), 1 << 30), w2);                                         \
         build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, link_stream>>>(g, d_levels, d_new_ids, count, list_cap_link,      \
                                                                            cand_cap, sel_cap, d_work_counter + 1, err,        \
                                                                            d_build_prof);                                      \

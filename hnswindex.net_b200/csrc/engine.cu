@@ -139,6 +139,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "build_overlap") tuning_.build_overlap = value;
     else if (key == "build_specialized") tuning_.build_specialized = value;
     else if (key == "build_warps3") tuning_.build_warps3 = value;
+    else if (key == "build_flags") tuning_.build_flags = value;
     else if (key == "exact_tcgen05") tuning_.exact_tcgen05 = value;
     else if (key == "wl_min_ef") tuning_.wl_min_ef = value;
     else if (key == "wide_min_ef") tuning_.wide_min_ef = value;

@@ -17,6 +17,7 @@ struct Tuning {
     int build_overlap = 0;    // large insertion batches: run the link kernel on a second stream so that the next batch's select
                               // kernel fills the SM slots freed in the tails.  Off: -4.5 % build time, but the next batch
                               // then sees the previous batch's reverse links only partly and recall@10 drops 0.2 pt
+    int build_flags = 2;        // beam-search flags of the construction search (bit 0: L2-prefetch rows of accepted candidates, bit 1: guess-row load)
     int build_warps3 = 1;       // select kernel as 6 blocks of 3 warps per SM instead of 4 of 4 when registers and shared memory allow
     int build_specialized = 1;  // the C5-shaped select kernel instantiation (short rows, MaxCandidates <= 1024, 16-bit tags)
     int sync_pieces = 0;      // hnsw_knn_query: pieces a large batch is split into, alternating two streams (0 = 2 for page-locked, 4 for pageable buffers)
