@@ -550,9 +550,11 @@ def run_reference(args):
         "metric": W["metric_name"], "value": round(value, 1), "unit": "queries/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        # the same workload string as the B200 arm prints (the arms differ in who built the graph and in the sample size,
+        # which have their own keys)
         "config": {"workload": f"{W['tag']}: {n} x {DIM} fp32 {METRIC} {W['shape']}, M={M}, efConstruction={EFC}, "
-                               f"k={K}, MinNN(ef)={ef} = smallest grid value with recall@{K}>=0.95; each step = {sample} queries",
-                   f"recall_at_{K}": round(rec, 4), "ef": ef, "index_nodes": n, "graph_built_by": built_by},
+                               f"{nq}-query batch per GPU per step, k={K}, MinNN(ef)={ef} = smallest grid value with recall@{K}>=0.95",
+                   f"recall_at_{K}": round(rec, 4), "ef": ef, "index_nodes": n, "queries_per_step_per_gpu": sample, "graph_built_by": built_by},
         "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} queries per step on the {n}-node graph; C++ restatement of the reference "
                                    f"(the .NET runtime is not available), Parallel.For stand-in on all host threads"},
