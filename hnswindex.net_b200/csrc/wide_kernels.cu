@@ -83,14 +83,19 @@ __device__ __forceinline__ bool vis_would_be_fresh(const uint32_t* vis, int vis_
 //   differ) the helpers evaluate the authoritative list on demand.  Nothing speculative ever reaches the list or the
 //   table: results and counters are those of the one-warp kernels, only the latency of gather + reduction moves off the
 //   leader's critical path.
-// SPEC: kSpecShortRows (rows fit one staging segment), kSpecVis16 (16-bit visited tags); SPECULATE: evaluate ahead
+// SPEC: kSpecShortRows (rows fit one staging segment), kSpecVis16 (16-bit visited tags), kSpecGvis (the visited set is an
+// EXACT bitmap of this CTA in global memory -- bitmap + (size_t)blockIdx.x * bitmap_words, one bit per node, L2-resident:
+// one atomicOr per neighbour instead of a shared-memory table, no re-evaluations at all, and the shared memory of the table
+// goes to more resident queries); SPECULATE: evaluate ahead
 template <int METRIC, int SPEC, bool SPECULATE>
 __global__ void __launch_bounds__(kThreads)
 knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, int ef, int vis_size, int cand_cap, int* __restrict__ out_ids,
-                float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats) {
+                float* __restrict__ out_dists, unsigned* work_counter, QueryStats* stats, uint32_t* bitmap, int bitmap_words) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5, H = W - 1;
     constexpr bool vis16 = (SPEC & kSpecVis16) != 0;
+    constexpr bool gvis = (SPEC & kSpecGvis) != 0;
+    uint32_t* bm = gvis ? bitmap + (size_t)blockIdx.x * bitmap_words : nullptr;
 
     unsigned char* p = smem;
     Stager stg;  // helpers: their own staging buffer; the leader borrows helper 1's for the descent (the helpers are idle then)
@@ -133,6 +138,11 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
         const float* qsrc = queries + (size_t)qi * g.dim;
         for (int i = threadIdx.x; i < g.pitch; i += blockDim.x) q[i] = i < g.dim ? __ldg(qsrc + i) : 0.f;
         for (int i = threadIdx.x; i < vis_size; i += blockDim.x) vis[i] = 0u;
+        if (gvis) {
+            uint4* b4 = reinterpret_cast<uint4*>(bm);
+            for (int i = threadIdx.x; i < (bitmap_words >> 2); i += blockDim.x) __stcg(b4 + i, make_uint4(0u, 0u, 0u, 0u));
+            __threadfence();
+        }
         __syncthreads();
         double qn = 0.0;
         if (METRIC == COSINE) qn = pair_norm_sqrt(q, g.dim, lane & 1);  // every warp computes the same value
@@ -157,7 +167,11 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
                         for (int rb = 0; rb < g.stride0; rb += 32) {
                             const int slot = rb + lane;
                             const int nb = slot < g.stride0 ? __ldg(row + slot) : -1;
-                            const bool fresh = nb >= 0 && vis_would_be_fresh<vis16>(vis, vis_size, vis_shift, nb);
+                            bool fresh = nb >= 0;
+                            if (fresh) {
+                                if (gvis) fresh = !((__ldcg(bm + (nb >> 5)) >> (nb & 31)) & 1u);
+                                else fresh = vis_would_be_fresh<vis16>(vis, vis_size, vis_shift, nb);
+                            }
                             const unsigned mk = __ballot_sync(FULL, fresh);
                             if (fresh) sid[m + __popc(mk & ((1u << lane) - 1u))] = nb;
                             m += __popc(mk);
@@ -191,7 +205,9 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
         wl_init(L, list, ef);
         wl_insert(L, make_key(cur_d, cur), lane);
         if (lane == 0) {
-            if (vis16) vis16_test_and_set(s, cur); else vis_test_and_set(s, cur);
+            if (gvis) atomicOr(bm + (cur >> 5), 1u << (cur & 31));
+            else if (vis16) vis16_test_and_set(s, cur);
+            else vis_test_and_set(s, cur);
         }
         __syncwarp();
         int guess_id = -1, guess_nb = -1;
@@ -228,7 +244,10 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
                 else nb = slot < g.stride0 ? __ldg(row + slot) : -1;
                 deg += __popc(__ballot_sync(FULL, nb >= 0));
                 bool fresh = false;
-                if (nb >= 0) fresh = vis16 ? vis16_test_and_set(s, nb) : vis_test_and_set(s, nb);
+                if (nb >= 0) {
+                    if (gvis) fresh = !((atomicOr(bm + (nb >> 5), 1u << (nb & 31)) >> (nb & 31)) & 1u);
+                    else fresh = vis16 ? vis16_test_and_set(s, nb) : vis_test_and_set(s, nb);
+                }
                 const unsigned mk = __ballot_sync(FULL, fresh);
                 if (fresh) cand_id[m + __popc(mk & ((1u << lane) - 1u))] = nb;
                 m += __popc(mk);
@@ -386,8 +405,10 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int cand_cap = ((g.stride0 + 31) / 32) * 32;
     // warps per CTA: the leader + 2 helpers (each evaluates half of a 32-neighbour row); the leader + 1 helper in the range where
-    // the shared memory of a second helper costs a resident query (measured on 1M x 128: 1024 -> 3 warps, 2048..4096 -> 2)
-    int warps = t.wide_warps > 0 ? t.wide_warps : ((g.stride0 > 32 || ef < 2048 || ef >= 8192) ? 3 : 2);
+    // the shared memory of a second helper costs a resident query (measured on 1M x 128: 1024 -> 3 warps, 2048..4095 -> 2; with the
+    // visited set in global memory -- from 4096 -- the second helper fits again)
+    const bool bitmap_range = t.wide_prefetch != 0 && t.wide_bitmap_min_ef > 0 && ef >= t.wide_bitmap_min_ef;
+    int warps = t.wide_warps > 0 ? t.wide_warps : ((g.stride0 > 32 || ef < 2048 || ef >= 8192 || bitmap_range) ? 3 : 2);
     warps = std::max(2, std::min(kWarpsPerBlock, warps));
     // visited table: 4 ef entries when they fit (the setting of the one-warp kernel), else what the shared memory leaves
     int vis = t.vis_size_search > 0 ? std::max(64, pow2_floor((size_t)t.vis_size_search)) : std::max(256, pow2_floor((size_t)2 * ef));
@@ -401,7 +422,38 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     const bool v16 = (long long)g.count <= ((long long)vis << 16);
     const bool shortrows = g.pitch <= kSegFloats;
     const bool prefetch = t.wide_prefetch != 0;  // speculative evaluation of the next expansion
+    // exact bitmap in global memory instead of the shared-memory table (speculating kernels, wide beams)
+    const bool use_bitmap = prefetch && t.wide_bitmap_min_ef > 0 && ef >= t.wide_bitmap_min_ef;
+    const int bitmap_words = use_bitmap ? ((g.count + 127) / 128) * 4 : 0;
+    size_t smem_bm = 0;
+    if (use_bitmap) {
+        smem_bm = wide_smem_bytes(warps, g.pitch, ef, 0, cand_cap);
+        if (smem_bm > (size_t)max_optin) throw std::runtime_error("search width (MinNN / k) too large for shared memory");
+    }
+    uint32_t* d_bitmap = nullptr;
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
+#define HNSW_WIDE_BM(M, S)                                                                                                         \
+    {                                                                                                                              \
+        const WideShape sh = wide_shape(knn_wide_kernel<M, S, true>, 32 * warps, smem_bm);                                         \
+        int per_sm = sh.per_sm;                                                                                                    \
+        if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);                                                       \
+        const int grid = std::max(1, std::min(nq, sh.sms * per_sm));                                                               \
+        HNSW_CUDA_CHECK(cudaMallocAsync(&d_bitmap, (size_t)grid * bitmap_words * sizeof(uint32_t), stream));                       \
+        knn_wide_kernel<M, S, true><<<grid, 32 * warps, smem_bm, stream>>>(g, d_queries, nq, k, ef, 0, cand_cap, d_ids, d_dists,   \
+                                                                           d_work_counter, d_stats, d_bitmap, bitmap_words);       \
+        HNSW_CUDA_CHECK(cudaGetLastError());                                                                                       \
+        HNSW_CUDA_CHECK(cudaFreeAsync(d_bitmap, stream));                                                                          \
+    }
+    if (use_bitmap) {
+        switch (metric) {
+            case SQ_EUCLID: if (shortrows) HNSW_WIDE_BM(SQ_EUCLID, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(SQ_EUCLID, kSpecGvis) break;
+            case EUCLID: if (shortrows) HNSW_WIDE_BM(EUCLID, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(EUCLID, kSpecGvis) break;
+            case COSINE: if (shortrows) HNSW_WIDE_BM(COSINE, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(COSINE, kSpecGvis) break;
+            default: if (shortrows) HNSW_WIDE_BM(UCOSINE, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(UCOSINE, kSpecGvis) break;
+        }
+        return;
+    }
+#undef HNSW_WIDE_BM
 #define HNSW_WIDE_GO(M, S, P)                                                                                                      \
     {                                                                                                                              \
         const WideShape sh = wide_shape(knn_wide_kernel<M, S, P>, 32 * warps, smem);                                               \
@@ -409,7 +461,7 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
         if (t.blocks_per_sm > 0) per_sm = std::min(per_sm, t.blocks_per_sm);                                                       \
         const int grid = std::max(1, std::min(nq, sh.sms * per_sm));                                                               \
         knn_wide_kernel<M, S, P><<<grid, 32 * warps, smem, stream>>>(g, d_queries, nq, k, ef, vis, cand_cap, d_ids, d_dists,       \
-                                                                     d_work_counter, d_stats);                                     \
+                                                                     d_work_counter, d_stats, nullptr, 0);                         \
     }
 #define HNSW_WIDE_SPEC(M)                                                                                                          \
     {                                                                                                                              \

@@ -95,6 +95,13 @@ def test_wide_kernel_variants_agree(hnswindex, oracle, tmp_path):
                         assert c == base                              # same table -> same number of evaluations, too
                     else:
                         assert c[0] >= int(oc[0])
+        for warps in (2, 3):                                          # exact visited bitmap in global memory: no re-evaluations
+            ids, d, c = _query(gpu, queries, 10, ef, wide_min_ef=1, wide_warps=warps, wide_prefetch=1, wide_bitmap_min_ef=1, vis_size_search=0)
+            _assert_identical(ids, d, o_ids, o_d, min_same=1.0)
+            # expansions and rows exactly the reference's; evaluations too, up to the few per query the oracle counts
+            # differently during the descent (it re-evaluates the entry of every upper layer)
+            assert c[1:] == (int(oc[1]), int(oc[2])) and 0 <= int(oc[0]) - c[0] <= 8 * len(queries), (c, oc)
+        gpu.set_tuning("wide_bitmap_min_ef", 0)
         for vis in (0, 64):                                           # the one-warp kernel on the non-shifting list
             ids, d, c = _query(gpu, queries, 10, ef, wide_min_ef=0, wl_min_ef=1, vis_size_search=vis)
             _assert_identical(ids, d, o_ids, o_d, min_same=1.0)

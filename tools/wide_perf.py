@@ -47,8 +47,11 @@ for ef in efs:
     row = {"ef": ef}
     base_ids = None
     for name, tn in (("warp", dict(wide_min_ef=0, wl_min_ef=0)), ("wl", dict(wide_min_ef=0, wl_min_ef=1)),
-                     ("wide2", dict(wide_min_ef=1, wide_warps=2, wide_prefetch=0)), ("wide2s", dict(wide_min_ef=1, wide_warps=2, wide_prefetch=1)),
-                     ("wide3s", dict(wide_min_ef=1, wide_warps=3, wide_prefetch=1))):
+                     ("wide2s", dict(wide_min_ef=1, wide_warps=2, wide_prefetch=1, wide_bitmap_min_ef=0)),
+                     ("wide3s", dict(wide_min_ef=1, wide_warps=3, wide_prefetch=1, wide_bitmap_min_ef=0)),
+                     ("bm2", dict(wide_min_ef=1, wide_warps=2, wide_prefetch=1, wide_bitmap_min_ef=1)),
+                     ("bm3", dict(wide_min_ef=1, wide_warps=3, wide_prefetch=1, wide_bitmap_min_ef=1)),
+                     ("bm4", dict(wide_min_ef=1, wide_warps=4, wide_prefetch=1, wide_bitmap_min_ef=1))):
         if name == "warp" and ef > 4096:
             continue
         try:
@@ -57,7 +60,7 @@ for ef in efs:
             row[name] = str(e)[:60]
             continue
         row[name] = round(qps)
-        if name.startswith("wide"):
+        if name.startswith("wide") or name.startswith("bm"):
             pr = ix.wide_profile(reset=True)
             ex = max(1, pr["expansions"])
             row[name + "_prof"] = {"hit": round(pr["spec_used"] / max(1, pr["spec_issued"]), 3), "issued": round(pr["spec_issued"] / ex, 3),
