@@ -126,6 +126,21 @@ def test_wide_kernel_small_and_ragged(hnswindex, oracle, tmp_path):
             assert np.array_equal(g_d[~np.isnan(g_d)].view(np.uint32), o_d[~np.isnan(o_d)].view(np.uint32))
 
 
+def test_small_calls_take_the_latency_path_with_identical_answers(hnswindex, oracle, tmp_path):
+    # calls of at most 4 queries run on the CTA-per-query kernel (default tuning), whatever ef is
+    data = sift_like(30000)
+    queries = sift_like(40, seed=11)
+    ref, path = _oracle_graph(oracle, tmp_path, "sq_euclid", data, "wlat", max_candidates=100, collection_size=30000)
+    gpu = hnswindex.Index.deserialize("sq_euclid", path)
+    for ef in (5, 48, 300):
+        ref.set_min_nn(ef); gpu.set_min_nn(ef)
+        o_ids, o_d = ref.knn_query(queries, 10, threads=8)
+        for n in (1, 2, 3, 4):
+            for start in range(0, 40 - n, 7):
+                g_ids, g_d = gpu.knn_query(queries[start:start + n], 10)
+                assert np.array_equal(g_ids, o_ids[start:start + n]) and np.array_equal(g_d.view(np.uint32), o_d[start:start + n].view(np.uint32))
+
+
 def test_default_routing_uses_the_wide_kernel_for_wide_beams(hnswindex, oracle, tmp_path):
     # the default tuning: register list up to 64, non-shifting list above, CTA-per-query kernel for the widest beams
     data = sift_like(8000)
