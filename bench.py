@@ -395,6 +395,37 @@ def replicated_pass(args, workload, steps, warmup, headline):
     _, page_wall_ms, _ = timed(step_pageable, args.steps, args.warmup)
     if refb is not None:
         rix._h = None   # the handle belongs to `ix`
+    # ---- and from several host threads at once ("thread-safe per operation type", README.md:64-65 of the reference):
+    #      hnsw_knn_query holds the index's lock shared and runs on its own stream + scratch, so the calls overlap on the GPU
+    nthreads = 2
+    tq = [torch.from_numpy(queries[(t % nb) * nq:((t % nb) + 1) * nq]).pin_memory() for t in range(nthreads)]
+    ti = [torch.empty((nq, K), dtype=torch.int32).pin_memory() for _ in range(nthreads)]
+    td = [torch.empty((nq, K), dtype=torch.float32).pin_memory() for _ in range(nthreads)]
+    per_thread = max(10, args.steps)
+    go = threading.Barrier(nthreads + 1)
+
+    def thread_body(t):
+        def call():
+            rc = hnswindex.lib.hnsw_knn_query(ix._h, ct.cast(tq[t].data_ptr(), f32p), nq, DIM, K, ct.cast(ti[t].data_ptr(), i32p),
+                                              ct.cast(td[t].data_ptr(), f32p))
+            assert rc == 0, hnswindex.last_error()
+        for _ in range(2):
+            call()
+        go.wait()
+        for _ in range(per_thread):
+            call()
+    ths = [threading.Thread(target=thread_body, args=(t,)) for t in range(nthreads)]
+    for th in ths:
+        th.start()
+    go.wait()
+    t_c = time.perf_counter()
+    for th in ths:
+        th.join()
+    conc_ms = (time.perf_counter() - t_c) * 1e3
+    ct_t = torch.tensor([conc_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ct_t, op=dist.ReduceOp.MAX)
+    conc_ms = float(ct_t.item())
     pid, pdist = page_out["r"]
     assert pid.shape == (nq, K) and pid.dtype == np.int32 and pdist.dtype == np.float32
 
@@ -475,7 +506,10 @@ def replicated_pass(args, workload, steps, warmup, headline):
         "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 8,
                 "ms_per_step": round(e2e_wall_ms / args.steps, 4), "api": "hnsw_knn_query (C ABI, pinned host buffers)",
                 "pageable": {"value": round(total_q / (page_wall_ms / 1e3), 1), "unit": "queries/s",
-                             "ms_per_step": round(page_wall_ms / args.steps, 4), "api": pageable_api}},
+                             "ms_per_step": round(page_wall_ms / args.steps, 4), "api": pageable_api},
+                "concurrent": {"value": round(world * nq * per_thread * nthreads / (conc_ms / 1e3), 1), "unit": "queries/s", "host_threads": nthreads,
+                               "calls_per_thread": per_thread, "api": "hnsw_knn_query (C ABI, pinned host buffers) called from "
+                               f"{nthreads} host threads at once on one handle"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
