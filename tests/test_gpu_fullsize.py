@@ -68,6 +68,19 @@ def test_c2_oracle_on_the_gpu_written_snapshot(built, oracle, tmp_path):
     same = (g_ids == o_ids).all(axis=1).mean()
     assert same >= 0.995, same                                                   # north_star: >= 99.5 %
     assert np.array_equal(g_d.view(np.uint32), o_d.view(np.uint32))              # bit-identical distances
+    # wide beams at the full size (round 2): the non-shifting list (ef 300), the CTA-per-query kernel with speculative
+    # evaluation (1024) and with the exact visited bitmap (4096), and the latency path (one query per call) -- same lists,
+    # same distance bits as the oracle on the same file
+    for ef, nq in ((300, 400), (1024, 200), (4096, 64)):
+        ref.set_min_nn(ef); ix.set_min_nn(ef)
+        o_i, o_dd = ref.knn_query(sample[:nq], 10, threads=16)
+        g_i, g_dd = ix.knn_query(sample[:nq], 10)
+        assert (g_i == o_i).all(axis=1).mean() >= 0.995, ef
+        assert np.array_equal(g_dd.view(np.uint32), o_dd.view(np.uint32)), ef
+    ref.set_min_nn(48); ix.set_min_nn(48)
+    for j in range(5):
+        g_i, g_dd = ix.knn_query(sample[j], 10)
+        assert np.array_equal(g_i[0], o_ids[j]) and np.array_equal(g_dd[0].view(np.uint32), o_d[j].view(np.uint32))
     # brute force agrees too (sample of 32 queries: the oracle scans 1M vectors per query)
     e_ids, e_d = ix.exact_knn(sample[:32], 10)
     b_ids, b_d = ref.exact_knn(sample[:32], 10, threads=16)
