@@ -441,8 +441,9 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
         HNSW_CUDA_CHECK(cudaMallocAsync(&d_bitmap, (size_t)grid * bitmap_words * sizeof(uint32_t), stream));                       \
         knn_wide_kernel<M, S, true><<<grid, 32 * warps, smem_bm, stream>>>(g, d_queries, nq, k, ef, 0, cand_cap, d_ids, d_dists,   \
                                                                            d_work_counter, d_stats, d_bitmap, bitmap_words);       \
-        HNSW_CUDA_CHECK(cudaGetLastError());                                                                                       \
+        const cudaError_t launch_err = cudaGetLastError(); /* the bitmap goes back to the pool whether or not the launch took */ \
         HNSW_CUDA_CHECK(cudaFreeAsync(d_bitmap, stream));                                                                          \
+        HNSW_CUDA_CHECK(launch_err);                                                                                               \
     }
     if (use_bitmap) {
         switch (metric) {
