@@ -32,9 +32,10 @@ struct Tuning {
                               // non-shifting list (wide_kernels.cu); 0 = never
     int wide_warps = 0;       // warps per CTA of that kernel: the leader + helpers (0 = 2, or 3 for rows of more than 32 neighbours)
     int wide_prefetch = 1;    // its helper warps evaluate the likely next expansion ahead of time (speculative, never changes results)
-    int wide_bitmap_min_ef = 4096;  // CTA-per-query searches at or above this width keep an EXACT visited bitmap in global memory (one bit per
-                                    // node per resident query, L2-resident) instead of the shared-memory table: no re-evaluations, and the table's
-                                    // shared memory goes to more resident queries (ef 4096: 18k -> 30k QPS, 8192: 4.0k -> 6.8k); 0 = never
+    int wide_bitmap_min_ef = 2048;  // CTA-per-query searches at or above this width keep an EXACT visited bitmap in global memory (one bit per
+                                    // node per resident query, L2-resident) instead of the shared-memory table: no re-evaluations, no duplicate
+                                    // look-ups, and the table's shared memory goes to more resident queries (3 000-query batches on 1M x 128:
+                                    // ef 2048 69k -> 88k QPS, 4096 24.5k -> 32.8k, 8192 4.6k -> 12.0k); 0 = never
     int wide_max_small_batch = 4;  // calls with at most this many queries use the CTA-per-query kernel whatever ef is: one query alone
                                    // is answered ~15 % sooner (177 vs 215 us of kernel time at ef = 48 on the 1M x 128 index)
     int peer_timeout_ms = 10000;  // partitioned index: how long the wait+merge kernel waits for a peer GPU's results before it

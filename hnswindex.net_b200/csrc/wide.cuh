@@ -236,6 +236,9 @@ __device__ __forceinline__ bool wl_contains(const WideList& L, u64 key, int lane
 // visited table let through a second time passes that test only if it is still in the set (far only shrinks), so every
 // candidate that passes is looked up by (distance bits, id) in the pending buffer (one vote) and in the main array
 // (wl_contains) before it is inserted.
+// EXACT_VISITED: the caller's visited set never forgets (global bitmap), so no node is evaluated twice and the lookups are
+// skipped.
+template <bool EXACT_VISITED = false>
 __device__ __forceinline__ void wl_insert_candidates(WideList& L, const int* cand_id, const float* cand_dist, int lo, int hi, int lane) {
     for (int jb = lo; jb < hi; jb += 32) {
         const int j = jb + lane;
@@ -249,8 +252,10 @@ __device__ __forceinline__ void wl_insert_candidates(WideList& L, const int* can
             const int src = __ffs(mk) - 1;
             const u64 kn = __shfl_sync(FULL, mykey, src);
             if (lane == src) pending = false;
-            if (__any_sync(FULL, lane < L.pc && (L.pend >> 1) == (kn >> 1))) continue;  // already pending
-            if (wl_contains(L, kn, lane)) continue;                                      // already in the array
+            if (!EXACT_VISITED) {
+                if (__any_sync(FULL, lane < L.pc && (L.pend >> 1) == (kn >> 1))) continue;  // already pending
+                if (wl_contains(L, kn, lane)) continue;                                      // already in the array
+            }
             wl_insert(L, kn, lane);
         }
     }

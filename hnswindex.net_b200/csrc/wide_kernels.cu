@@ -306,7 +306,7 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
                 }
                 guess_nb = lane < g.stride0 ? __ldg(g.adj0 + (size_t)guess_id * g.stride0 + lane) : -1;
             }
-            if (m > 0) wl_insert_candidates(L, cand_id, dist, 0, m, lane);
+            if (m > 0) wl_insert_candidates<gvis>(L, cand_id, dist, 0, m, lane);
             pf_ins += clock64() - t_ins;
         }
         if (lane == 0) {
@@ -405,10 +405,10 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int cand_cap = ((g.stride0 + 31) / 32) * 32;
     // warps per CTA: the leader + 2 helpers (each evaluates half of a 32-neighbour row); the leader + 1 helper in the range where
-    // the shared memory of a second helper costs a resident query (measured on 1M x 128: 1024 -> 3 warps, 2048..4095 -> 2; with the
-    // visited set in global memory -- from 4096 -- the second helper fits again)
+    // the shared memory of a second helper costs a resident query (measured on 1M x 128 with 3 000-query batches: 1024 -> 3 warps;
+    // from 2048, where the visited set moves to global memory, leader + 1 helper: 2048 87.7k vs 74.3k QPS, 8192 12.0k vs 8.1k)
     const bool bitmap_range = t.wide_prefetch != 0 && t.wide_bitmap_min_ef > 0 && ef >= t.wide_bitmap_min_ef;
-    int warps = t.wide_warps > 0 ? t.wide_warps : ((g.stride0 > 32 || ef < 2048 || ef >= 8192 || bitmap_range) ? 3 : 2);
+    int warps = t.wide_warps > 0 ? t.wide_warps : (bitmap_range ? (g.stride0 > 32 ? 3 : 2) : ((g.stride0 > 32 || ef < 2048 || ef >= 8192) ? 3 : 2));
     warps = std::max(2, std::min(kWarpsPerBlock, warps));
     // visited table: 4 ef entries when they fit (the setting of the one-warp kernel), else what the shared memory leaves
     int vis = t.vis_size_search > 0 ? std::max(64, pow2_floor((size_t)t.vis_size_search)) : std::max(256, pow2_floor((size_t)2 * ef));
