@@ -405,9 +405,11 @@ def replicated_pass(args, workload, steps, warmup, headline):
     go = threading.Barrier(nthreads + 1)
 
     def thread_body(t):
-        def call():
-            rc = hnswindex.lib.hnsw_knn_query(ix._h, ct.cast(tq[t].data_ptr(), f32p), nq, DIM, K, ct.cast(ti[t].data_ptr(), i32p),
-                                              ct.cast(td[t].data_ptr(), f32p))
+        pq, pi, pd = ct.cast(tq[t].data_ptr(), f32p), ct.cast(ti[t].data_ptr(), i32p), ct.cast(td[t].data_ptr(), f32p)
+        fn, h = hnswindex.lib.hnsw_knn_query, ix._h
+
+        def call():   # (pointers prepared outside: the GIL is only held for the ctypes call set-up)
+            rc = fn(h, pq, nq, DIM, K, pi, pd)
             assert rc == 0, hnswindex.last_error()
         for _ in range(2):
             call()
