@@ -147,6 +147,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "wide_prefetch") tuning_.wide_prefetch = value;
     else if (key == "wide_max_small_batch") tuning_.wide_max_small_batch = value;
     else if (key == "wide_bitmap_min_ef") tuning_.wide_bitmap_min_ef = value;
+    else if (key == "wide_bitmap_max_nodes") tuning_.wide_bitmap_max_nodes = value;
     else if (key == "peer_timeout_ms") tuning_.peer_timeout_ms = std::max(1, value);
     else if (key == "remove_batch_max") remove_batch_max_ = std::max(1, value);
     else if (key == "remove_batch_ratio") remove_batch_ratio_ = std::max(1, value);

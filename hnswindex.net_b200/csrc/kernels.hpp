@@ -35,7 +35,8 @@ struct Tuning {
     int wide_bitmap_min_ef = 2048;  // CTA-per-query searches at or above this width keep an EXACT visited bitmap in global memory (one bit per
                                     // node per resident query, L2-resident) instead of the shared-memory table: no re-evaluations, no duplicate
                                     // look-ups, and the table's shared memory goes to more resident queries (3 000-query batches on 1M x 128:
-                                    // ef 2048 69k -> 88k QPS, 4096 24.5k -> 32.8k, 8192 4.6k -> 12.0k); 0 = never
+                                    // ef 2048 69k -> 101k QPS, 4096 24.5k -> 40k, 8192 4.6k -> 14.2k); 0 = never
+    int wide_bitmap_max_nodes = 2097152;  // ... only for indexes up to this many nodes (the bitmaps of all resident queries should stay in L2)
     int wide_max_small_batch = 4;  // calls with at most this many queries use the CTA-per-query kernel whatever ef is: one query alone
                                    // is answered ~15 % sooner (177 vs 215 us of kernel time at ef = 48 on the 1M x 128 index)
     int peer_timeout_ms = 10000;  // partitioned index: how long the wait+merge kernel waits for a peer GPU's results before it

@@ -43,6 +43,7 @@ struct WideCtrl {
     int buf;           // kCmdSpec: which of the two speculative buffers to fill
     int spec_node[2];  // filled by the helpers: node and list length of each speculative buffer
     int spec_m[2];
+    int spec_deg[2];   // ... and the degree of that node (for the row_words counter)
     int pad;
 };
 
@@ -163,10 +164,11 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
                     float* sd = reinterpret_cast<float*>(sid + cand_cap);
                     if (warp == 1) {
                         const int* row = g.adj0 + (size_t)node * g.stride0;
-                        int m = 0;
+                        int m = 0, deg = 0;
                         for (int rb = 0; rb < g.stride0; rb += 32) {
                             const int slot = rb + lane;
                             const int nb = slot < g.stride0 ? __ldg(row + slot) : -1;
+                            deg += __popc(__ballot_sync(FULL, nb >= 0));
                             bool fresh = nb >= 0;
                             if (fresh) {
                                 if (gvis) fresh = !((__ldcg(bm + (nb >> 5)) >> (nb & 31)) & 1u);
@@ -178,6 +180,7 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
                         }
                         if (lane == 0) {
                             ctrl->spec_m[b] = m;
+                            ctrl->spec_deg[b] = deg;
                             ctrl->spec_node[b] = node;
                         }
                         __syncwarp();
@@ -234,9 +237,28 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
                 outstanding = false;
                 spec_ready = true;
             }
+            int m = 0, deg = 0;
+            const int* ids_use = cand_id;
+            const float* dist = cand_dist;
+            bool have = false;
+            if (gvis && spec_ready && ctrl->spec_node[spec_buf] == c) {
+                // Exact bitmap + the guessed node: the helpers filtered this very row against the bitmap as it still is (only
+                // this warp writes it, and only here), so their list IS the authoritative one.  The bits are set with
+                // fire-and-forget reductions -- no L2 round trip on the leader's critical path -- and the row is not read again.
+                const int* sid = spec_id0 + (size_t)spec_buf * 2 * cand_cap;
+                m = ctrl->spec_m[spec_buf];
+                deg = ctrl->spec_deg[spec_buf];
+                for (int j = lane; j < m; j += 32) {
+                    const int id = sid[j];
+                    atomicOr(bm + (id >> 5), 1u << (id & 31));
+                }
+                ids_use = sid;
+                dist = reinterpret_cast<const float*>(sid + cand_cap);
+                have = true;
+                pf_used++;
+            } else {
             // row of c: keep the neighbours not seen recently, in stored order (the authoritative, table-updating filter)
             const int* row = g.adj0 + (size_t)c * g.stride0;
-            int m = 0, deg = 0;
             for (int rb = 0; rb < g.stride0; rb += 32) {
                 const int slot = rb + lane;
                 int nb;
@@ -253,13 +275,12 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
                 m += __popc(mk);
             }
             __syncwarp();
+            }
             wc.nexp++;
             wc.row_words += deg + 1;
             wc.ndist += m;
             // distances: speculative buffer if it holds exactly this expansion, else on demand
-            const float* dist = cand_dist;
-            bool have = false;
-            if (spec_ready) {
+            if (!have && spec_ready) {
                 if (ctrl->spec_node[spec_buf] == c && ctrl->spec_m[spec_buf] == m) {
                     const int* sid = spec_id0 + (size_t)spec_buf * 2 * cand_cap;
                     bool same = true;
@@ -306,7 +327,7 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
                 }
                 guess_nb = lane < g.stride0 ? __ldg(g.adj0 + (size_t)guess_id * g.stride0 + lane) : -1;
             }
-            if (m > 0) wl_insert_candidates<gvis>(L, cand_id, dist, 0, m, lane);
+            if (m > 0) wl_insert_candidates<gvis>(L, ids_use, dist, 0, m, lane);
             pf_ins += clock64() - t_ins;
         }
         if (lane == 0) {
@@ -407,7 +428,9 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     // warps per CTA: the leader + 2 helpers (each evaluates half of a 32-neighbour row); the leader + 1 helper in the range where
     // the shared memory of a second helper costs a resident query (measured on 1M x 128 with 3 000-query batches: 1024 -> 3 warps;
     // from 2048, where the visited set moves to global memory, leader + 1 helper: 2048 87.7k vs 74.3k QPS, 8192 12.0k vs 8.1k)
-    const bool bitmap_range = t.wide_prefetch != 0 && t.wide_bitmap_min_ef > 0 && ef >= t.wide_bitmap_min_ef;
+    // (one bit per node per resident query must stay L2-resident: up to 2M nodes = 256 KB per query, ~190 MB for a full grid at
+    // the measured sizes would already spill -- larger indexes keep the shared-memory table)
+    const bool bitmap_range = t.wide_prefetch != 0 && t.wide_bitmap_min_ef > 0 && ef >= t.wide_bitmap_min_ef && g.count <= t.wide_bitmap_max_nodes;
     int warps = t.wide_warps > 0 ? t.wide_warps : (bitmap_range ? (g.stride0 > 32 ? 3 : 2) : ((g.stride0 > 32 || ef < 2048 || ef >= 8192) ? 3 : 2));
     warps = std::max(2, std::min(kWarpsPerBlock, warps));
     // visited table: 4 ef entries when they fit (the setting of the one-warp kernel), else what the shared memory leaves
@@ -423,7 +446,7 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     const bool shortrows = g.pitch <= kSegFloats;
     const bool prefetch = t.wide_prefetch != 0;  // speculative evaluation of the next expansion
     // exact bitmap in global memory instead of the shared-memory table (speculating kernels, wide beams)
-    const bool use_bitmap = prefetch && t.wide_bitmap_min_ef > 0 && ef >= t.wide_bitmap_min_ef;
+    const bool use_bitmap = bitmap_range;
     const int bitmap_words = use_bitmap ? ((g.count + 127) / 128) * 4 : 0;
     size_t smem_bm = 0;
     if (use_bitmap) {
