@@ -241,17 +241,21 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
             const int* ids_use = cand_id;
             const float* dist = cand_dist;
             bool have = false;
-            if (gvis && spec_ready && ctrl->spec_node[spec_buf] == c) {
-                // Exact bitmap + the guessed node: the helpers filtered this very row against the bitmap as it still is (only
-                // this warp writes it, and only here), so their list IS the authoritative one.  The bits are set with
-                // fire-and-forget reductions -- no L2 round trip on the leader's critical path -- and the row is not read again.
+            if (spec_ready && ctrl->spec_node[spec_buf] == c) {
+                // The guessed node: the helpers filtered this very row against the visited set as it still is (only this warp
+                // writes it, and only here), so their list IS the authoritative one.  The leader only records the new ids --
+                // bitmap: fire-and-forget reductions, no L2 round trip on its critical path; table: one LDS + STS per id -- and
+                // does not read the row again.
                 const int* sid = spec_id0 + (size_t)spec_buf * 2 * cand_cap;
                 m = ctrl->spec_m[spec_buf];
                 deg = ctrl->spec_deg[spec_buf];
                 for (int j = lane; j < m; j += 32) {
                     const int id = sid[j];
-                    atomicOr(bm + (id >> 5), 1u << (id & 31));
+                    if (gvis) atomicOr(bm + (id >> 5), 1u << (id & 31));
+                    else if (vis16) vis16_test_and_set(s, id);
+                    else vis_test_and_set(s, id);
                 }
+                __syncwarp();
                 ids_use = sid;
                 dist = reinterpret_cast<const float*>(sid + cand_cap);
                 have = true;
@@ -425,13 +429,12 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     HNSW_CUDA_CHECK(cudaGetDevice(&dev));
     HNSW_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int cand_cap = ((g.stride0 + 31) / 32) * 32;
-    // warps per CTA: the leader + 2 helpers (each evaluates half of a 32-neighbour row); the leader + 1 helper in the range where
-    // the shared memory of a second helper costs a resident query (measured on 1M x 128 with 3 000-query batches: 1024 -> 3 warps;
-    // from 2048, where the visited set moves to global memory, leader + 1 helper: 2048 87.7k vs 74.3k QPS, 8192 12.0k vs 8.1k)
-    // (one bit per node per resident query must stay L2-resident: up to 2M nodes = 256 KB per query, ~190 MB for a full grid at
-    // the measured sizes would already spill -- larger indexes keep the shared-memory table)
+    // warps per CTA: the leader + 1 helper (2 helpers for rows of more than 32 neighbours).  With full 10k-query batches on
+    // 1M x 128 a second helper never pays for the resident queries its staging buffer costs (ef 1024: 254k vs 242k QPS)
+    // exact visited bitmap in global memory instead of the shared-memory table: one bit per node per resident query must stay
+    // L2-resident, so only up to wide_bitmap_max_nodes (2M nodes = 256 KB per query); larger indexes keep the table
     const bool bitmap_range = t.wide_prefetch != 0 && t.wide_bitmap_min_ef > 0 && ef >= t.wide_bitmap_min_ef && g.count <= t.wide_bitmap_max_nodes;
-    int warps = t.wide_warps > 0 ? t.wide_warps : (bitmap_range ? (g.stride0 > 32 ? 3 : 2) : ((g.stride0 > 32 || ef < 2048 || ef >= 8192) ? 3 : 2));
+    int warps = t.wide_warps > 0 ? t.wide_warps : (g.stride0 > 32 ? 3 : 2);
     warps = std::max(2, std::min(kWarpsPerBlock, warps));
     // visited table: 4 ef entries when they fit (the setting of the one-warp kernel), else what the shared memory leaves
     int vis = t.vis_size_search > 0 ? std::max(64, pow2_floor((size_t)t.vis_size_search)) : std::max(256, pow2_floor((size_t)2 * ef));

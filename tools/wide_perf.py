@@ -34,7 +34,7 @@ def run(ef, reps=3, **tuning):
         ix.set_tuning(k, v)
     ix.set_min_nn(ef)
     best = 1e9
-    m = min(nq, max(3000, int(nq * 256 / max(ef, 256))))    # keep a run short at huge ef
+    m = nq if ef <= 2048 else min(nq, max(3000, int(nq * 256 / ef)))    # keep a run short at huge ef
     for _ in range(reps):
         ix.knn_query_device(q_dev.data_ptr(), m, 10, ids.data_ptr(), d.data_ptr())
         best = min(best, ix.stats()["last_search_ms"])
