@@ -201,12 +201,9 @@ void launch_wait_merge(const unsigned* d_flags, int world, unsigned epoch, int t
                        const float* d_in_dists, int nq, int k, int* d_out_ids, float* d_out_dists, cudaStream_t stream) {
     if (nq <= 0) return;
     if (world < 1 || world > 32) throw std::invalid_argument("wait_merge: world size out of range");
-    static size_t optin = 0;
     const size_t msmem = (size_t)kWarpsPerBlock * k * 8;
-    if (msmem > optin) {
+    if (msmem > 48 * 1024)  // (per device and per call: only k > 1536 needs the opt-in at all)
         HNSW_CUDA_CHECK(cudaFuncSetAttribute(wait_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-        optin = msmem;
-    }
     const unsigned long long timeout_ns = (unsigned long long)std::max(1, timeout_ms) * 1000000ull;
     wait_merge_kernel<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, msmem, stream>>>(d_flags, world, epoch, timeout_ns, d_error, d_in_ids,
                                                                                               d_in_dists, nq, k, d_out_ids, d_out_dists);
