@@ -274,11 +274,8 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
             /* three-warp blocks when six of them fit where four four-warp blocks do */                                         \
             int per3 = 0;                                                                                                        \
             if (w1 == 4 && t.build_warps3 != 0 && smem_sel * 3 <= (size_t)48 * 1024 * 4) {                                      \
-                static bool optin3 = false;                                                                                      \
-                if (!optin3) {                                                                                                   \
-                    HNSW_CUDA_CHECK(cudaFuncSetAttribute(build_select_kernel<M, S, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-                    optin3 = true;                                                                                               \
-                }                                                                                                                \
+                if (smem_sel * 3 > (size_t)48 * 1024) /* per device, per launch: cheap next to a batch */                       \
+                    HNSW_CUDA_CHECK(cudaFuncSetAttribute(build_select_kernel<M, S, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_sel * 3))); \
                 HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, build_select_kernel<M, S, 3>, 96, smem_sel * 3)); \
             }                                                                                                                    \
             int per4 = 0;                                                                                                        \
