@@ -28,14 +28,14 @@ struct Tuning {
                               // 1 = the earlier 4-warp tcgen05 kernel (68.8 ms), 0 = always mma.sync
     int wl_min_ef = 256;      // one-warp-per-query searches with ef at or above this keep their candidates in wide.cuh's non-shifting
                               // list (0 = never): the shifting list of beam.cuh costs O(ef / 32) chunk moves per accepted candidate
-    int wide_min_ef = 768;     // layer-0 searches with ef = max(MinNN, k) at or above this run on the CTA-per-query kernel with the
+    int wide_min_ef = 384;     // layer-0 searches with ef = max(MinNN, k) at or above this run on the CTA-per-query kernel with the
                               // non-shifting list (wide_kernels.cu); 0 = never
     int wide_warps = 0;       // warps per CTA of that kernel: the leader + helpers (0 = 2, or 3 for rows of more than 32 neighbours)
     int wide_prefetch = 1;    // its helper warps evaluate the likely next expansion ahead of time (speculative, never changes results)
-    int wide_bitmap_min_ef = 1280;  // CTA-per-query searches at or above this width keep an EXACT visited bitmap in global memory (one bit per
+    int wide_bitmap_min_ef = 1024;  // CTA-per-query searches at or above this width keep an EXACT visited bitmap in global memory (one bit per
                                     // node per resident query, L2-resident) instead of the shared-memory table: no re-evaluations, no duplicate
                                     // look-ups, and the table's shared memory goes to more resident queries (3 000-query batches on 1M x 128:
-                                    // ef 1536 148k -> 191k QPS, 2048 86k -> 112k, 4096 24.5k -> 40k, 8192 4.6k -> 14.2k; 1024: 254k vs 251k); 0 = never
+                                    // ef 1024 255k -> 299-333k QPS, 2048 85k -> 133k, 4096 25.7k -> 40k, 8192 4.3k -> 13.8k; below 1024 the table wins); 0 = never
     int wide_bitmap_max_nodes = 2097152;  // ... only for indexes up to this many nodes (the bitmaps of all resident queries should stay in L2)
     int wide_max_small_batch = 4;  // calls with at most this many queries use the CTA-per-query kernel whatever ef is: one query alone
                                    // is answered ~15 % sooner (177 vs 215 us of kernel time at ef = 48 on the 1M x 128 index)

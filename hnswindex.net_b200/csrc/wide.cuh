@@ -77,7 +77,7 @@ __device__ __forceinline__ int lane_lower_bound(const u64* a, int n, u64 key) {
 // increasing positions; the main entries fill the remaining positions in order.  So for an output chunk of 32 positions
 // one OR-reduction of the lanes' P_j bits gives the chunk's "pending slot" mask, and main entry -> position is a popcount:
 // no per-entry search.  Chunks are handled from the top down (a chunk's sources lie at or below its own positions, i.e.
-// never in a chunk that was already overwritten), two chunks per iteration so that their shared-memory latencies overlap.
+// never in a chunk that was already overwritten), four chunks per iteration so that their shared-memory latencies overlap.
 __device__ __forceinline__ void wl_merge(WideList& L, int lane) {
     const int n = L.n, pc = L.pc;
     if (pc == 0) return;
@@ -92,21 +92,28 @@ __device__ __forceinline__ void wl_merge(WideList& L, int lane) {
         occ = __reduce_or_sync(FULL, (off >= 0 && off < 32) ? (1u << off) : 0u);
         below = __popc(__ballot_sync(FULL, off < 0));  // pending slots in lower chunks (lanes >= pc have P = INT_MAX)
     };
-    for (int c = (total - 1) >> 5; c >= c_lo; c -= 2) {
-        unsigned occ0, occ1 = 0u;
-        int bel0, bel1 = 0;
-        chunk_src(c, occ0, bel0);
-        const bool two = c - 1 >= c_lo;
-        if (two) chunk_src(c - 1, occ1, bel1);
-        const int o0 = (c << 5) + lane, o1 = ((c - 1) << 5) + lane;
-        const bool m0 = o0 < total && o0 >= P0 && !((occ0 >> lane) & 1u);
-        const bool m1 = two && o1 >= P0 && !((occ1 >> lane) & 1u);
-        u64 x0 = 0ull, x1 = 0ull;
-        if (m0) x0 = L.main[o0 - bel0 - __popc(occ0 & ((1u << lane) - 1u))];
-        if (m1) x1 = L.main[o1 - bel1 - __popc(occ1 & ((1u << lane) - 1u))];
-        __syncwarp();  // both chunks' sources are in registers before any position is overwritten
-        if (m0) L.main[o0] = x0;
-        if (m1) L.main[o1] = x1;
+    // four chunks per iteration: their shared-memory round trips overlap (a merge of a 16k-entry list is 512 chunks)
+    for (int c = (total - 1) >> 5; c >= c_lo; c -= 4) {
+        u64 x[4];
+        bool mv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int cc = c - u;
+            mv[u] = false;
+            x[u] = 0ull;
+            if (cc >= c_lo) {  // warp-uniform
+                unsigned occ;
+                int bel;
+                chunk_src(cc, occ, bel);
+                const int o = (cc << 5) + lane;
+                mv[u] = o < total && o >= P0 && !((occ >> lane) & 1u);
+                if (mv[u]) x[u] = L.main[o - bel - __popc(occ & ((1u << lane) - 1u))];
+            }
+        }
+        __syncwarp();  // all four chunks' sources are in registers before any position is overwritten
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (mv[u]) L.main[((c - u) << 5) + lane] = x[u];
         __syncwarp();
     }
     if (lane < pc) L.main[P] = L.pend;

@@ -108,7 +108,7 @@ def test_wide_kernel_variants_agree(hnswindex, oracle, tmp_path):
             ids, d, c = _query(gpu, queries, 10, ef, wide_min_ef=0, wl_min_ef=1, vis_size_search=vis)
             _assert_identical(ids, d, o_ids, o_d, min_same=1.0)
             assert c[1] == int(oc[1]) and c[2] == int(oc[2])
-        gpu.set_tuning("wl_min_ef", 256); gpu.set_tuning("wide_min_ef", 768)
+        gpu.set_tuning("wl_min_ef", 256); gpu.set_tuning("wide_min_ef", 384)
         gpu.set_tuning("vis_size_search", 0); gpu.set_tuning("wide_warps", 0); gpu.set_tuning("wide_prefetch", 1)
 
 
@@ -149,7 +149,7 @@ def test_default_routing_uses_the_wide_kernel_for_wide_beams(hnswindex, oracle, 
     queries = sift_like(64, seed=7)
     ref, path = _oracle_graph(oracle, tmp_path, "sq_euclid", data, "wd", max_candidates=100)
     gpu = hnswindex.Index.deserialize("sq_euclid", path)
-    for ef in (64, 65, 255, 256, 767, 768, 1279, 1280, 2048, 5000):
+    for ef in (64, 65, 255, 256, 383, 384, 1023, 1024, 2048, 5000):
         ref.set_min_nn(ef); gpu.set_min_nn(ef)
         o_ids, o_d = ref.knn_query(queries, 10, threads=8)
         g_ids, g_d = gpu.knn_query(queries, 10)
