@@ -24,7 +24,8 @@ ix.add(data)
 tn = {"warp": dict(wide_min_ef=0, wl_min_ef=0), "wl": dict(wide_min_ef=0, wl_min_ef=1),
       "wide1": dict(wide_min_ef=1, wide_warps=1, wide_prefetch=0), "wide2p": dict(wide_min_ef=1, wide_warps=2, wide_prefetch=1),
       "wide4p": dict(wide_min_ef=1, wide_warps=4, wide_prefetch=1), "wide2s": dict(wide_min_ef=1, wide_warps=2, wide_prefetch=1),
-      "wide3s": dict(wide_min_ef=1, wide_warps=3, wide_prefetch=1), "wide2": dict(wide_min_ef=1, wide_warps=2, wide_prefetch=0)}[variant]
+      "wide3s": dict(wide_min_ef=1, wide_warps=3, wide_prefetch=1), "wide2": dict(wide_min_ef=1, wide_warps=2, wide_prefetch=0),
+      "bm2": dict(wide_min_ef=1, wide_warps=2, wide_prefetch=1, wide_bitmap_min_ef=1), "default": dict()}[variant]
 for k, v in tn.items():
     ix.set_tuning(k, v)
 ix.set_min_nn(ef)
