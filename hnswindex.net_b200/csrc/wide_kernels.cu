@@ -1,18 +1,16 @@
 // wide_kernels.cu -- K2w: KnnQuery with a WIDE beam, one CTA per query.
 //
 // Replaces the same reference code as search_kernels.cu (HNSWIndex.cs:107-137, GraphNavigator.cs:39-82,194-256) for
-// ef = max(MinNN, k) from a few hundred up to ~16k.  The reference's heaps grow without bound (BinaryHeap.cs:109-113), so
-// any MinNN costs it the same per step; the one-warp-per-query kernel does not scale that way: its sorted list shifts
-// O(ef / 32) chunks per accepted candidate and one warp's list + visited table leave 2-3 warps per SM at ef = 4096.
-// Here one CTA holds ONE query's state (query vector, candidate list, visited table) once:
-//   * warp 0 (the leader) owns the control flow of GraphNavigator.SearchLayerQuery: pick the closest unexpanded entry,
-//     read its adjacency row, filter it through the visited table, insert the evaluated neighbours in stored order
-//     (wide.cuh: sorted main array + 32-entry pending buffer in registers, merged in one pass);
-//   * ALL warps evaluate the distances of one expansion: warp w stages and reduces rows [16w, 16w + 16) of the fresh
-//     neighbours (stage.cuh / metric.cuh, bit-exact), so a layer-0 row of 2M = 32 neighbours is one pass for two warps
-//     and a 64-neighbour row (M = 32) one pass for four;
-//   * while the leader inserts, the other warps pull the adjacency row of the entry most likely to be expanded next and
-//     the vectors it points at into L2 (prefetch only: the traversal itself is unchanged).
+// ef = max(MinNN, k) from a few hundred up to ~24k, and for calls of a handful of queries.  The reference's heaps grow
+// without bound (BinaryHeap.cs:109-113), so any MinNN costs it the same per step; the one-warp-per-query kernel does not
+// scale that way: its sorted list shifts O(ef / 32) chunks per accepted candidate and one warp's list + visited table leave
+// 2-3 warps per SM at ef = 4096.  Here one CTA holds ONE query's state (query vector, candidate list, visited set) once:
+//   * warp 0 (the LEADER) owns the control flow of GraphNavigator.SearchLayerQuery: pick the closest unexpanded entry,
+//     filter its adjacency row through the visited set, insert the evaluated neighbours in stored order (wide.cuh: sorted
+//     main array + 32-entry pending buffer in registers, merged in one pass);
+//   * the other warps (HELPERS, one by default) evaluate distances -- and they evaluate the NEXT expansion ahead of time,
+//     while the leader still inserts the current one (see the comment above the kernel);
+//   * the visited set is the shared-memory table of beam.cuh or, from ef 1024, an exact bitmap in global memory.
 // The order of every decision (strict d < far re-read after each insertion, stored order, first occurrence on ties) is the
 // one of beam.cuh, so results and the nexp / row_words counters are identical to the one-warp kernel and to the oracle.
 #include <math_constants.h>
@@ -32,7 +30,8 @@ constexpr int kCmdEval = 0, kCmdSpec = 1, kCmdDone = 2;
 // Leader-side profile of the CTA-per-query kernel, summed over all queries since the last reset (SM cycles of the leader
 // warp; two atomics per counter per QUERY, so it is always on): hnsw_get_wide_profile().
 //   0 queries  1 expansions  2 speculations issued  3 speculations used  4 cyc descent  5 cyc select + filter
-//   6 cyc waiting for a speculation  7 cyc waiting for an on-demand evaluation  8 cyc insert  9 cyc beam loop total  10 merges
+//   6 cyc waiting for a speculation  7 cyc waiting for an on-demand evaluation  8 cyc insert  9 cyc beam loop total
+// (the compiler may move the clock reads across the barriers: the split between 5..8 is indicative, 9 is exact)
 __device__ unsigned long long g_wide_prof[16];
 
 struct WideCtrl {
