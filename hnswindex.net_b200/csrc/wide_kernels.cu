@@ -78,11 +78,12 @@ __device__ __forceinline__ bool vis_would_be_fresh(const uint32_t* vis, int vis_
 //   evaluate expansion i+1 SPECULATIVELY: the leader names the entry that will be expanded next unless one of the pending
 //   candidates lands in front of it; the helpers read that node's row, filter it through the table read-only (nobody writes
 //   the table during an insertion phase, so they see exactly what the leader will see), stage the fresh rows and reduce the
-//   distances into one of two speculative buffers.  When the leader then selects that very node and its own -- authoritative,
-//   table-updating -- filter yields the same id list, the distances are already there; otherwise (wrong guess, or the lists
-//   differ) the helpers evaluate the authoritative list on demand.  Nothing speculative ever reaches the list or the
-//   table: results and counters are those of the one-warp kernels, only the latency of gather + reduction moves off the
-//   leader's critical path.
+//   distances into one of two speculative buffers.  When the leader then selects that very node, the helpers' id list IS
+//   what its own filter would produce (same row, same visited set: only the leader writes the set, and only in this step),
+//   so it takes the list and the distances over and merely records the new ids in the set; otherwise (wrong guess) it
+//   filters the row itself and the helpers evaluate that list on demand.  A wrong guess leaves no trace -- nothing of it
+//   reaches the list or the visited set --, so results and counters are those of the one-warp kernels; only the latency of
+//   row + filter + gather + reduction moves off the leader's critical path.
 // SPEC: kSpecShortRows (rows fit one staging segment), kSpecVis16 (16-bit visited tags), kSpecGvis (the visited set is an
 // EXACT bitmap of this CTA in global memory -- bitmap + (size_t)blockIdx.x * bitmap_words, one bit per node, L2-resident:
 // one atomicOr per neighbour instead of a shared-memory table, no re-evaluations at all, and the shared memory of the table
