@@ -283,19 +283,7 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
             wc.nexp++;
             wc.row_words += deg + 1;
             wc.ndist += m;
-            // distances: speculative buffer if it holds exactly this expansion, else on demand
-            if (!have && spec_ready) {
-                if (ctrl->spec_node[spec_buf] == c && ctrl->spec_m[spec_buf] == m) {
-                    const int* sid = spec_id0 + (size_t)spec_buf * 2 * cand_cap;
-                    bool same = true;
-                    for (int j = lane; j < m; j += 32) same = same && sid[j] == cand_id[j];
-                    if (__all_sync(FULL, same)) {
-                        have = true;
-                        dist = reinterpret_cast<const float*>(sid + cand_cap);
-                        pf_used++;
-                    }
-                }
-            }
+            // distances: taken over from the speculation above, else evaluated on demand
             pf_sel += clock64() - t0;
             if (!have && m > 0) {
                 const long long tw = clock64();
