@@ -157,3 +157,23 @@ np.savez({str(out_npz)!r}, ids=ids, ki=ki, kd=kd, ki2=ki2, kd2=kd2, rn=np.array(
     assert np.array_equal(ref["ki2"], ki2) and np.array_equal(ref["kd2"].view(np.uint32), kd2.view(np.uint32))
     assert np.array_equal(ref["rn"], np.array([len(x) for x in ri])) and ref["rn"].sum() > 0
     assert np.array_equal(ref["ri"], np.concatenate(ri)) and np.array_equal(ref["rd"], np.concatenate(rd))
+
+
+@pytest.mark.gpu
+def test_reference_readme_example_runs_verbatim(tmp_path):
+    """README.md:80-96 of the reference (BASELINE config[0]): the example as printed there, through the reference's package."""
+    site = stage_reference_package(tmp_path)
+    example = REF_INSTALL / "readme_example.py"
+    if not example.exists():
+        pytest.skip("baseline/_ref/readme_example.py is absent")
+    code = example.read_text(encoding="utf-8")
+    assert "index.knn_query(vectors, k=1)" in code and "Index(dim=128" in code
+    r = run_py(site, code + """
+import numpy as np
+assert ids.shape == (2000, 1) and distances.shape == (2000, 1) and ids.dtype == np.int32 and distances.dtype == np.float32
+hit = ids[:, 0] == np.arange(2000)
+print('SELF_RECALL', hit.mean(), float(np.abs(distances[hit, 0]).max()))
+""")
+    assert r.returncode == 0, r.stdout + r.stderr
+    rec, dmax = [float(x) for x in r.stdout.strip().splitlines()[-1].split()[1:]]
+    assert rec > 0.85 and dmax < 1e-5            # recall_test.py:15's bar; a vector is at distance 0 from itself
