@@ -14,6 +14,11 @@
 //   link_kernel   : for every selected neighbour n, under a per-node spin lock (atomicCAS on
 //                   locks[n]), append the new id to n's row, re-running the heuristic on
 //                   overflow so MaxEdges(layer) is honoured.
+// Tail fill (default): a warp of the select kernel handles ~6 insertions of ~1.7 ms each per full batch, so for the last
+// ~10 % of the kernel's time the SMs drain.  The link kernel is therefore a programmatic dependent launch: its blocks move
+// into the slots the first finishing select blocks leave, and each work item waits for its node's ready flag (written by the
+// select warp after the node's rows) instead of for the whole select kernel.  The last insertions of a batch can then see
+// reverse links of its first ones -- as threads of the reference's Parallel.For do.
 #include <algorithm>
 
 #include "build_scratch.cuh"
@@ -32,8 +37,12 @@ enum BuildProf : int {
 template <int METRIC, int SPEC, int WARPS = 4>
 __global__ void __launch_bounds__(32 * WARPS, WARPS == 3 ? 6 : 4)
 build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int efc, int list_cap, int vis_size, int cand_cap,
-                    int sel_cap, unsigned* work_counter, u64* prof, uint32_t* gvis, int gvis_slots, int flags) {
+                    int sel_cap, unsigned* work_counter, u64* prof, uint32_t* gvis, int gvis_slots, int flags, int* ready, int epoch) {
     extern __shared__ __align__(128) unsigned char smem[];
+    // Tail fill (ready != null): the link kernel that follows in the stream is a programmatic dependent launch.  Its blocks
+    // may become resident as soon as every block of THIS grid has started, i.e. into the slots the first finishing select
+    // blocks leave, and each of its work items waits for its node's ready flag instead of for this whole kernel.
+    if (ready != nullptr) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, vis_size, cand_cap, sel_cap);
     BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, vis_size, cand_cap, sel_cap, lane);
@@ -96,6 +105,13 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
             cur_d = next_d;
         }
         nd_search += wc.ndist;
+        if (ready != nullptr) {
+            // every lane's row stores, then the flag (release).  Indexed by node id, not by batch position: `v` is live here
+            // anyway, while a position kept across the searches costs the 96-register build of this kernel a factor 2.4
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready + v), "r"(epoch) : "memory");
+        }
         __syncwarp();
     }
     if (lane == 0 && n_items > 0) {
@@ -131,7 +147,7 @@ __device__ __forceinline__ void unlock_node(int* locks, int n, int lane) {
 template <int METRIC>
 __global__ void __launch_bounds__(kThreads, 4)
 build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int list_cap, int cand_cap, int sel_cap,
-                  unsigned* work_counter, int* error_flag, u64* prof) {
+                  unsigned* work_counter, int* error_flag, u64* prof, const int* ready, int epoch) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, 64, cand_cap, sel_cap);
@@ -152,14 +168,19 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __rest
         int* row = row_ptr_mut(g, n, layer, stride);
         // current row of n, read past L1 (other SMs update it under the same lock)
         int cnt = 0;
+        bool dup = false;
         for (int rb = 0; rb < stride; rb += 32) {
             const int slot = rb + lane;
             const int nb = slot < stride ? __ldcg(row + slot) : -1;
             if (nb >= 0) s.cand_id[slot] = nb;
             cnt += __popc(__ballot_sync(FULL, nb >= 0));
+            dup = dup || __any_sync(FULL, nb == v);
         }
         __syncwarp();
-        if (cnt < maxE) {
+        if (dup) {
+            // only with tail fill: n is a node of this very batch that had already been linked to v (v's link reached n's row
+            // first and was then read back as one of n's own targets) -- the edge exists, nothing to do
+        } else if (cnt < maxE) {
             if (lane == 0) row[cnt] = v;  // EdgeList.Add, GraphConnector.cs:207
         } else {
             // PruneOverflow (GraphConnector.cs:222-262): heuristic over the row plus the new link
@@ -193,12 +214,26 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __rest
         if (lane == 0) wi = atomicAdd(work_counter, 1u);
         wi = __shfl_sync(FULL, wi, 0);
         if (wi >= pairs + (unsigned)count) break;
+        const int v = __ldg(new_ids + (wi < pairs ? wi / (unsigned)g.stride0 : wi - pairs));
+        if (ready != nullptr) {  // tail fill: this node's rows may still be in the making (select kernel still running)
+            int ok = 1;
+            if (lane == 0) {
+                unsigned spins = 0;
+                int f;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(ready + v) : "memory");
+                    if (f == epoch) break;
+                    __nanosleep(256);
+                    if (++spins > (1u << 22)) { ok = 0; atomicExch(error_flag, 1); break; }  // never hang the GPU
+                }
+            }
+            ok = __shfl_sync(FULL, ok, 0);
+            if (!ok) break;
+        }
         if (wi < pairs) {
-            const int v = __ldg(new_ids + wi / (unsigned)g.stride0);
             const int n = __ldcg(g.adj0 + (size_t)v * g.stride0 + wi % (unsigned)g.stride0);
             if (n >= 0) link_one(v, n, 0);
         } else {
-            const int v = __ldg(new_ids + (wi - pairs));
             const int level = __ldg(levels + v);
             for (int layer = min(level, g.top_layer); layer >= 1; --layer) {
                 int vstride;
@@ -241,12 +276,13 @@ static int gvis_slots_per_warp(const uint32_t* d_gvis, size_t gvis_words, size_t
     return slots >= 1024 ? slots : 0;
 }
 
-// d_work_counter: three consecutive words -- [0] select work, [1] link work, [2] error flag
+// d_work_counter: [0] select work, [1] link work, [2] error flag, [9] select work of every other batch (tail fill)
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, const int* d_new_ids, int count, int efc, unsigned* d_work_counter,
                         u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream,
-                        cudaStream_t link_stream, cudaEvent_t select_done) {
+                        cudaStream_t link_stream, cudaEvent_t select_done, int* d_ready, int epoch) {
     if (count <= 0) return;
     if (link_stream == nullptr) link_stream = stream;
+    if (link_stream != stream || t.build_tail_fill == 0) d_ready = nullptr;  // tail fill: both kernels in one stream
     const int maxE0 = 2 * g.max_edges;
     const int list_cap_sel = std::max(efc, 1);
     const int list_cap_link = maxE0 + 1;
@@ -261,7 +297,10 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
     const bool vis16 = (long long)g.count <= ((long long)vis << 16);
     const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap);   // per warp
     const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap);  // per warp
-    HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
+    // Tail fill: a batch's link kernel can end while the last select warps are still on their way out (one more fetch from the
+    // work counter each), so consecutive batches take their select work from alternating words
+    unsigned* sel_counter = (d_ready != nullptr && (epoch & 1)) ? d_work_counter + 9 : d_work_counter;
+    HNSW_CUDA_CHECK(cudaMemsetAsync(sel_counter, 0, sizeof(unsigned), stream));
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter + 1, 0, sizeof(unsigned), link_stream));
     int* err = reinterpret_cast<int*>(d_work_counter + 2);
 #define HNSW_LAUNCH_BUILD(M)                                                                                                    \
@@ -283,31 +322,46 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
             if (per3 * 3 > per4 * 4 && t.blocks_per_sm <= 0) {                                                                  \
                 const int g3 = std::max(1, std::min((count + 2) / 3, device_sm_count() * per3));                                \
                 build_select_kernel<M, S, 3><<<g3, 96, smem_sel * 3, stream>>>(                                                 \
-                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, nullptr, 0, t.build_flags); \
+                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, nullptr, 0, t.build_flags, d_ready, epoch); \
             } else {                                                                                                             \
                 const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                \
                 build_select_kernel<M, S><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                             \
-                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots, t.build_flags); \
+                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, d_gvis, gslots, t.build_flags, d_ready, epoch); \
             }                                                                                                                    \
         } else if (vis16) {                                                                                                     \
             const int g1 = persistent_grid(build_select_kernel<M, kSpecVis16>, smem_sel, t, count, w1);                        \
             const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
             build_select_kernel<M, kSpecVis16><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                        \
-                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots, t.build_flags); \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, d_gvis, gslots, t.build_flags, d_ready, epoch); \
         } else {                                                                                                                \
             const int g1 = persistent_grid(build_select_kernel<M, 0>, smem_sel, t, count, w1);                                 \
             const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
             build_select_kernel<M, 0><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                 \
-                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, d_work_counter, d_build_prof, d_gvis, gslots, t.build_flags); \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, d_gvis, gslots, t.build_flags, d_ready, epoch); \
         }                                                                                                                       \
         if (link_stream != stream) { /* the links of this batch follow its select kernel, on their own stream */             \
             HNSW_CUDA_CHECK(cudaEventRecord(select_done, stream));                                                             \
             HNSW_CUDA_CHECK(cudaStreamWaitEvent(link_stream, select_done, 0));                                                 \
         }                                                                                                                       \
-        const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, (int)std::min<long long>((long long)count * (g.stride0 + 1), 1 << 30), w2);                                         \
-        build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, link_stream>>>(g, d_levels, d_new_ids, count, list_cap_link,      \
-                                                                           cand_cap, sel_cap, d_work_counter + 1, err,        \
-                                                                           d_build_prof);                                      \
+        const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, (int)std::min<long long>((long long)count * (g.stride0 + 1), 1 << 30), w2); \
+        if (d_ready != nullptr) {                                                                                               \
+            /* programmatic dependent launch: resident as soon as all select blocks have started and SM slots are free */      \
+            cudaLaunchConfig_t cfg = {};                                                                                        \
+            cfg.gridDim = dim3((unsigned)g2);                                                                                   \
+            cfg.blockDim = dim3(32u * (unsigned)w2);                                                                            \
+            cfg.dynamicSmemBytes = smem_link * w2;                                                                              \
+            cfg.stream = stream;                                                                                                \
+            cudaLaunchAttribute attr[1];                                                                                        \
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                    \
+            attr[0].val.programmaticStreamSerializationAllowed = 1;                                                             \
+            cfg.attrs = attr;                                                                                                   \
+            cfg.numAttrs = 1;                                                                                                   \
+            HNSW_CUDA_CHECK(cudaLaunchKernelEx(&cfg, build_link_kernel<M>, g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
+                                               d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch));            \
+        } else {                                                                                                                \
+            build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, link_stream>>>(g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
+                                                                               d_work_counter + 1, err, d_build_prof, nullptr, 0); \
+        }                                                                                                                       \
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_BUILD(SQ_EUCLID) break;

@@ -103,7 +103,7 @@ Index::~Index() {
     cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
     cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_); cudaFree(d_gvis_search_);
     cudaFree(rq_keys_); cudaFree(rq_hash_); cudaFree(rq_small_); cudaFree(rq_dense_);
-    cudaFree(rm_small_); cudaFree(rm_aff_); cudaFree(d_rm_index_); cudaFree(d_new_ids_);
+    cudaFree(rm_small_); cudaFree(rm_aff_); cudaFree(d_rm_index_); cudaFree(d_new_ids_); cudaFree(d_ready_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
     for (QueryCtx& c : qctx_) {
         cudaFree(c.d_q); cudaFree(c.d_ids); cudaFree(c.d_dists); cudaFree(c.d_stats); cudaFree(c.d_counters);
@@ -140,6 +140,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "build_specialized") tuning_.build_specialized = value;
     else if (key == "build_warps3") tuning_.build_warps3 = value;
     else if (key == "build_flags") tuning_.build_flags = value;
+    else if (key == "build_tail_fill") tuning_.build_tail_fill = value;
     else if (key == "exact_tcgen05") tuning_.exact_tcgen05 = value;
     else if (key == "wl_min_ef") tuning_.wl_min_ef = value;
     else if (key == "wide_min_ef") tuning_.wide_min_ef = value;
@@ -347,6 +348,12 @@ void Index::add_committed(const float* vectors, int count, int dim, const std::v
         new_ids_cap_ = nnew;
     }
     HNSW_CUDA_CHECK(cudaMemcpyAsync(d_new_ids_, ids_new.data(), (size_t)nnew * 4, cudaMemcpyHostToDevice, stream_));
+    if (ready_cap_ < dev_capacity_) {  // one word per node: the epoch of the batch that wrote its rows (tail fill); epochs start at 1
+        cudaFree(d_ready_); d_ready_ = nullptr; ready_cap_ = 0;
+        HNSW_CUDA_CHECK(cudaMalloc(&d_ready_, (size_t)dev_capacity_ * sizeof(int)));
+        HNSW_CUDA_CHECK(cudaMemsetAsync(d_ready_, 0, (size_t)dev_capacity_ * sizeof(int), stream_));
+        ready_cap_ = dev_capacity_;
+    }
     if (nreused == 0 && nnew == count) {
         HNSW_CUDA_CHECK(cudaMemcpyAsync(d_levels_ + first, levels_.data() + first, (size_t)nfresh * 4, cudaMemcpyHostToDevice, stream_));
         HNSW_CUDA_CHECK(cudaMemcpyAsync(d_upper_off_ + first, upper_off_.data() + first, (size_t)nfresh * 4, cudaMemcpyHostToDevice, stream_));
@@ -422,7 +429,7 @@ void Index::add_committed(const float* vectors, int count, int dim, const std::v
             links_on_aux = false;
         }
         launch_build_batch((int)metric_, view(), d_levels_, d_new_ids_ + done, batch, params_.MaxCandidates, d_counters_, d_build_prof_, d_gvis_,
-                           gvis_words_, tuning_, stream_, overlap ? aux_stream_ : stream_, ev_fork_);
+                           gvis_words_, tuning_, stream_, overlap ? aux_stream_ : stream_, ev_fork_, d_ready_, ++build_epoch_);
         links_on_aux = links_on_aux || overlap;
         stats_.build_launches += 2;
         if (new_top) {  // GraphConnector.cs:36-41

@@ -166,6 +166,9 @@ private:
     int* d_rm_index_ = nullptr;   // [capacity] see GraphView::rm_index
     int* d_new_ids_ = nullptr;    // ids of the nodes of the running add()
     size_t new_ids_cap_ = 0;
+    int* d_ready_ = nullptr;      // per node: the epoch of the insertion batch that wrote its rows (tail fill, build_kernels.cu)
+    int ready_cap_ = 0;
+    int build_epoch_ = 0;
     int upper_rows_ = 0, upper_rows_cap_ = 0;
 
     float* d_vectors_ = nullptr;
@@ -175,7 +178,7 @@ private:
     int* d_adjU_ = nullptr;
     int* d_locks_ = nullptr;
     int* d_levels_ = nullptr;
-    unsigned* d_counters_ = nullptr;  // [0..2] build, [3] search
+    unsigned* d_counters_ = nullptr;  // [0..2] build (+ [9]), [3] search, [4..5] remove, [6..7] scatter, [8] second query stream
     u64* d_build_prof_ = nullptr;     // [16]
     uint32_t* d_gvis_ = nullptr;      // per-warp visited sets of the build search (allocated by the first add)
     size_t gvis_words_ = 0;

@@ -17,6 +17,10 @@ struct Tuning {
     int build_overlap = 0;    // large insertion batches: run the link kernel on a second stream so that the next batch's select
                               // kernel fills the SM slots freed in the tails.  Off: -4.5 % build time, but the next batch
                               // then sees the previous batch's reverse links only partly and recall@10 drops 0.2 pt
+    int build_tail_fill = 1;  // the link kernel of a batch is a programmatic dependent launch that moves into the SM slots the
+                              // select kernel's first finishing blocks leave and waits for each node's ready flag, instead of
+                              // starting when the last insertion of the batch has ended (a batch is ~6 insertions deep per warp, so
+                              // the select kernel's tail is ~8 % of it)
     int build_flags = 2;        // beam-search flags of the construction search (bit 0: L2-prefetch rows of accepted candidates, bit 1: guess-row load)
     int build_warps3 = 1;       // select kernel as 6 blocks of 3 warps per SM instead of 4 of 4 when registers and shared memory allow
     int build_specialized = 1;  // the C5-shaped select kernel instantiation (short rows, MaxCandidates <= 1024, 16-bit tags)
@@ -82,9 +86,11 @@ void launch_scatter_new_items(const float* d_src, const int* d_src_row, const in
 // graph as it stands, relative-neighbour selection, write the node's own rows.
 // K6: reverse links with per-node locks and overflow pruning.
 // d_build_prof: 16 u64 cycle / work counters accumulated by the kernels (build_kernels.cu BuildProf).
+// d_ready / epoch (tail fill, Tuning::build_tail_fill): one word per node id, set to `epoch` by the select kernel
+// when the node's rows are written; the link kernel then starts under the select kernel's tail and waits per node.
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, const int* d_new_ids, int count, int ef_construction,
                         unsigned* d_work_counter, u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream,
-                        cudaStream_t link_stream = nullptr, cudaEvent_t select_done = nullptr);
+                        cudaStream_t link_stream = nullptr, cudaEvent_t select_done = nullptr, int* d_ready = nullptr, int epoch = 0);
 
 // RangeQuery (HNSWIndex.cs:144-168): traversal of all in-range nodes reachable from the layer-0 entry.  Work item w handles
 // query qmap[w] (or w when qmap is null); out_keys [nwork][cap] unsorted (distance|id) keys, out_count[w] = result size or -1
