@@ -41,6 +41,8 @@ struct WarpScratch {
     uint32_t* gvis;    // optional exact visited set of this warp in GLOBAL memory (open addressing, ids + 1), or null
     int gvis_size;     // slots, power of two
     int gvis_shift;    // 32 - log2(gvis_size)
+    uint32_t* vbm;     // optional EXACT visited bitmap of this warp in global memory (one bit per node; long-row searches), or null
+    int vbm_words;     // its size in 32-bit words (multiple of 4)
 };
 
 constexpr int kPrefetchRows = 1;  // flags bit 0: L2-prefetch the adjacency rows of accepted candidates
@@ -78,6 +80,8 @@ __device__ __forceinline__ WarpScratch carve_scratch(unsigned char* base, int pi
     s.gvis = nullptr;
     s.gvis_size = 0;
     s.gvis_shift = 0;
+    s.vbm = nullptr;
+    s.vbm_words = 0;
     return s;
 }
 
@@ -118,6 +122,20 @@ __device__ __forceinline__ void stage_issue(const GraphView& g, Stager& stg, con
     }
 #endif
 }
+// the same for a subset of the rows: bit 2r of `keep` set = row r is still wanted (lane-pair ballot form)
+__device__ __forceinline__ void stage_issue_kept(const GraphView& g, Stager& stg, const int* ids, int base, int nrows, int f0, int nfl, int lane,
+                                                 unsigned keep) {
+    const int myid = lane < nrows ? ids[base + lane] : 0;
+    const char* src0 = reinterpret_cast<const char*>(g.vectors) + (size_t)(f0 + lane * 4) * 4;
+    const uint32_t dst0 = stg.buf_s + lane * 16;
+    const unsigned pitch_bytes = (unsigned)g.pitch * 4u;
+    if (lane * 4 >= nfl) keep = 0u;  // lanes beyond the row length copy nothing
+#pragma unroll
+    for (int r = 0; r < kStageRows; ++r) {
+        const unsigned id = (unsigned)__shfl_sync(FULL, myid, r);
+        if ((keep >> (2 * r)) & 1u) cp_async_16s(dst0 + r * (kSegPitch * 4), src0 + (size_t)id * pitch_bytes);
+    }
+}
 // wait until the copies started by stage_issue have landed and are visible to the whole warp
 __device__ __forceinline__ void stage_complete(Stager& stg) {
 #ifdef HNSW_STAGE_BULK
@@ -151,7 +169,8 @@ __device__ __forceinline__ void compute_staged(const GraphView& g, Stager& stg, 
 //   bit 0: rows fit one staging segment (pitch <= kSegFloats);  bit 1: the list never exceeds 64 entries (ef <= 64)
 //   bit 2: the visited table holds 16-bit tags (vis16_test_and_set): every id of the index is below vis_size * 65536
 //   bit 3: the list never exceeds 1024 entries (ef <= 1024): the binary-search insertion path is dead code
-//   bit 5: the search kernel attaches an exact per-warp visited set in global memory behind the shared-memory table
+//   bit 5: the search kernel attaches an exact per-warp visited bitmap in global memory behind the shared-memory table
+//          (long rows: WarpScratch::vbm, batch_dist_probe; the CTA-per-query kernel has its own use of the bit)
 //   bit 6: the list is wide.cuh's non-shifting WideList (sorted main array + 32 pending keys in registers), layer 0 only
 constexpr int kSpecShortRows = 1, kSpecSmallList = 2, kSpecVis16 = 4, kSpecMidList = 8, kSpecGvis = 32, kSpecWideList = 64;
 
@@ -193,6 +212,101 @@ __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, c
         if (active && h == 0) out[base + grp] = metric_finish<METRIC>(r, an, q_norm_sqrt);
     }
     __syncwarp();
+}
+// Long rows with the warp's exact visited bitmap (kSpecGvis searches): the filter in front of this call is the forgetful
+// shared-memory table, so some of ids[0..m) have been evaluated before -- on 1M x 960 that is 9 % of all evaluations, each
+// 3.8 KB of DRAM traffic.  An exact test costs a round trip to L2 / DRAM, which this kernel cannot afford once per expansion,
+// so it travels under work that is needed anyway: the bitmap words of ALL candidates are requested up front; the first pass
+// (16 rows) starts at once and drops the candidates found visited after the first segment of their rows (1/8 of a 960-float
+// row read instead of all of it: ids[j] = -1, no distance); by then every word has arrived, and the remaining candidates are
+// compacted (stable: stored order is kept) before their passes are formed, so those passes are full and fewer.
+// Fresh candidates are marked.  m is updated; returns the number of dropped candidates.
+template <int METRIC, int SPEC>
+__device__ __forceinline__ int batch_dist_probe(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, int* ids, float* out, int& m,
+                                                uint32_t* vbm, int lane) {
+    constexpr bool SQ = metric_is_sq(METRIC);
+    const int h = lane & 1, grp = lane >> 1;
+    const int nfull = g.dim >> 3;
+    const int ntail = g.dim - (nfull << 3);
+    int dropped = 0;
+    // requests: pass 0's rows by lane pair, the rest one candidate per lane (two chunks in registers; more are tested later)
+    const int nrows = min(kStageRows, m);
+    const bool mine = grp < nrows;
+    const int id = mine ? ids[grp] : 0;
+    uint32_t word = 0u;
+    if (mine && h == 0) word = __ldcg(vbm + (id >> 5));
+    const int j0 = kStageRows + lane, j1 = kStageRows + 32 + lane;
+    const int id0 = j0 < m ? ids[j0] : -1, id1 = j1 < m ? ids[j1] : -1;
+    uint32_t w0 = 0u, w1 = 0u;
+    if (id0 >= 0) w0 = __ldcg(vbm + (id0 >> 5));
+    if (id1 >= 0) w1 = __ldcg(vbm + (id1 >> 5));
+    {   // pass 0
+        bool active = mine;
+        unsigned keep = __ballot_sync(FULL, mine && h == 0);
+        double an = 0.0;
+        if (METRIC == COSINE && active) an = __ldg(g.norm_sqrt + id);
+        PairAcc acc = {0.f, 0.f, 0.f, 0.f};
+        float r = 0.f;
+        for (int f0 = 0; f0 < g.pitch; f0 += kSegFloats) {
+            const int nfl = min(kSegFloats, g.pitch - f0);
+            stage_issue_kept(g, stg, ids, 0, nrows, f0, nfl, lane, keep);
+            stage_complete(stg);
+            const float* row = stg.buf + grp * kSegPitch;
+            const int nch = min(nfull - (f0 >> 3), kSegFloats >> 3);
+            if (active && nch > 0) pair_accumulate<SQ>(acc, row, q + f0, nch, h);
+            if (f0 == 0) {
+                const bool seen = mine && h == 0 && ((word >> (id & 31)) & 1u);
+                if (mine && h == 0 && !seen) atomicOr(vbm + (id >> 5), 1u << (id & 31));  // result unused: a reduction
+                keep = __ballot_sync(FULL, mine && h == 0 && !seen);
+                active = mine && ((keep >> (lane & ~1)) & 1u);
+                dropped += nrows - __popc(keep);
+            }
+            if (f0 + kSegFloats >= g.pitch) {
+                r = pair_hsum<SQ>(acc);
+                if (active && ntail > 0) r = pair_tail<SQ>(r, row + ((nfull << 3) - f0), q + (nfull << 3), ntail);
+            }
+            __syncwarp();
+        }
+        if (mine && h == 0) {
+            if (active) out[grp] = metric_finish<METRIC>(r, an, q_norm_sqrt);
+            else ids[grp] = -1;
+        }
+    }
+    if (m <= kStageRows) {
+        __syncwarp();
+        return dropped;
+    }
+    // compact the rest: stable, fresh ones marked
+    int mnew = kStageRows;
+    {
+        const bool f0 = id0 >= 0 && !((w0 >> (id0 & 31)) & 1u);
+        const bool f1 = id1 >= 0 && !((w1 >> (id1 & 31)) & 1u);
+        if (f0) atomicOr(vbm + (id0 >> 5), 1u << (id0 & 31));
+        if (f1) atomicOr(vbm + (id1 >> 5), 1u << (id1 & 31));
+        const unsigned m0 = __ballot_sync(FULL, f0), m1 = __ballot_sync(FULL, f1);
+        __syncwarp();  // every lane has read its ids before they are overwritten
+        if (f0) ids[mnew + __popc(m0 & ((1u << lane) - 1u))] = id0;
+        mnew += __popc(m0);
+        if (f1) ids[mnew + __popc(m1 & ((1u << lane) - 1u))] = id1;
+        mnew += __popc(m1);
+        __syncwarp();
+    }
+    for (int jb = kStageRows + 64; jb < m; jb += 32) {  // rows longer than 80 neighbours: tested chunk by chunk (one round trip each)
+        const int j = jb + lane;
+        const int idj = j < m ? ids[j] : -1;
+        bool fr = false;
+        if (idj >= 0) fr = !((atomicOr(vbm + (idj >> 5), 1u << (idj & 31)) >> (idj & 31)) & 1u);
+        const unsigned mk = __ballot_sync(FULL, fr);
+        __syncwarp();
+        if (fr) ids[mnew + __popc(mk & ((1u << lane) - 1u))] = idj;
+        mnew += __popc(mk);
+        __syncwarp();
+    }
+    dropped += m - mnew;
+    m = mnew;
+    if (m > kStageRows) batch_dist_to<METRIC, SPEC>(g, stg, q, q_norm_sqrt, ids + kStageRows, out + kStageRows, m - kStageRows, lane);
+    __syncwarp();
+    return dropped;
 }
 template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void batch_dist(const GraphView& g, WarpScratch& s, double q_norm_sqrt, int m, int lane) {
@@ -437,7 +551,7 @@ template <int SPEC = 0>
 __device__ __forceinline__ void insert_candidates(const GraphView& g, WarpScratch& s, BeamState& st, int lo, int hi, int layer, int lane, int flags) {
     for (int jb = lo; jb < hi; jb += 32) {
         const int j = jb + lane;
-        const bool have = j < hi;
+        const bool have = j < hi && (!(SPEC & kSpecGvis) || s.cand_id[j] >= 0);  // kSpecGvis: batch_dist_probe drops visited candidates
         const u64 mykey = have ? make_key(s.cand_dist[j], s.cand_id[j]) : ~0ull;
         bool pending = have;
         for (;;) {
@@ -470,12 +584,18 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
     st.cursor = 0;
     vis_clear(s, lane);
     if (s.gvis != nullptr) gvis_clear(s, lane);
+    if ((SPEC & kSpecGvis) && s.vbm != nullptr) {
+        uint4* t = reinterpret_cast<uint4*>(s.vbm);
+        for (int i = lane; i < (s.vbm_words >> 2); i += 32) __stcg(t + i, make_uint4(0u, 0u, 0u, 0u));
+        __syncwarp();
+    }
     // compile-time choice: two inlined variants under a run-time branch cost this loop a factor of two on sm_100a
     constexpr bool vis16 = (SPEC & kSpecVis16) != 0;
     list_insert<SPEC>(s.list, st, make_key(entry_d, entry), lane);
     if (lane == 0) {
         if (vis16) vis16_test_and_set(s, entry); else vis_test_and_set(s, entry);
         if (s.gvis != nullptr) gvis_test_and_set(s, entry);
+        if ((SPEC & kSpecGvis) && s.vbm != nullptr) atomicOr(s.vbm + (entry >> 5), 1u << (entry & 31));
     }
     __syncwarp();
     int guess_id = -1, guess_nb = -1;  // adjacency word [lane] of the candidate expected to be expanded next
@@ -546,7 +666,8 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
                 insert_candidates<SPEC>(g, s, st, base, base + nrows, layer, lane, flags);
             }
         } else if (!(SPEC & kSpecShortRows)) {
-            batch_dist<METRIC, SPEC>(g, s, qn, m, lane);
+            if ((SPEC & kSpecGvis) && s.vbm != nullptr) wc.ndist -= batch_dist_probe<METRIC, SPEC>(g, s.stg, s.q, qn, s.cand_id, s.cand_dist, m, s.vbm, lane);
+            else batch_dist<METRIC, SPEC>(g, s, qn, m, lane);
             insert_candidates<SPEC>(g, s, st, 0, m, layer, lane, flags);
         }
     }

@@ -101,7 +101,7 @@ Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), par
 Index::~Index() {
     cudaSetDevice(device_);
     cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
-    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_); cudaFree(d_gvis_search_);
+    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_);
     cudaFree(rq_keys_); cudaFree(rq_hash_); cudaFree(rq_small_); cudaFree(rq_dense_);
     cudaFree(rm_small_); cudaFree(rm_aff_); cudaFree(d_rm_index_); cudaFree(d_new_ids_); cudaFree(d_ready_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
@@ -236,18 +236,6 @@ void Index::ensure_stats(int count) {
         HNSW_CUDA_CHECK(cudaMalloc(&d_stats_, (size_t)count * sizeof(QueryStats)));
         stats_cap_ = count;
     }
-}
-
-// Room for the per-warp exact visited sets of long-row searches: 16 warps per SM x min(vis_global_search, 64 ef) slots.
-void Index::ensure_search_gvis(int ef) {
-    if (pitch_ <= 128 || tuning_.vis_global_search <= 0 || ef > 1024) return;
-    int slots = 1024;
-    while (slots < tuning_.vis_global_search && slots < 64 * ef) slots <<= 1;
-    const size_t words = (size_t)device_sm_count() * 16 * slots;
-    if (words <= gvis_search_words_) return;
-    cudaFree(d_gvis_search_); d_gvis_search_ = nullptr; gvis_search_words_ = 0;
-    HNSW_CUDA_CHECK(cudaMalloc(&d_gvis_search_, words * sizeof(uint32_t)));
-    gvis_search_words_ = words;
 }
 
 void Index::set_stream(cudaStream_t s) {
@@ -685,10 +673,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
         Exclusive ex(mu_);
         join_aux_locked(true);
     }
-    // the optional global visited sets of long-row searches are one allocation per index: such calls stay exclusive
-    std::shared_lock<std::shared_mutex> shared(mu_, std::defer_lock);
-    Exclusive exclusive(mu_, std::defer_lock);
-    if (tuning_.vis_global_search > 0) exclusive.lock(); else shared.lock();
+    std::shared_lock<std::shared_mutex> shared(mu_);
     check_usable();
     if (count <= 0 || k < 1) return;
     if (this->count() <= 0) {  // HNSWIndex.cs:109
@@ -715,7 +700,6 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
     const bool direct_out = ids_dst != nullptr && d_dst != nullptr;
     int* ids_out = direct_out ? ids_dst : c.d_ids;
     float* d_out = direct_out ? d_dst : c.d_dists;
-    if (exclusive.owns_lock()) ensure_search_gvis(ef);
     // Pageable queries (what numpy hands over through the reference's own bindings.py) are staged by the driver, and the
     // host thread is held while that happens: a large batch is therefore uploaded in four pieces, each piece's search
     // launched as soon as it is on the device and alternating between the two streams, so the upload of piece i+1 runs
@@ -723,7 +707,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
     // Page-locked batches need no upload, but the same split pays there too: a persistent launch ends with a tail in which
     // its last queries keep only part of the SM slots busy, and the next piece's blocks (other stream) move in as they free up.
     int pieces = 1;
-    if (!want_stats && layer == 0 && count >= 4096 && tuning_.async_overlap != 0 && tuning_.vis_global_search <= 0)
+    if (!want_stats && layer == 0 && count >= 4096 && tuning_.async_overlap != 0)
         pieces = tuning_.sync_pieces > 0 ? tuning_.sync_pieces : (q_src ? 2 : 4);
     pieces = std::max(1, std::min(pieces, 16));
     HNSW_CUDA_CHECK(cudaEventRecord(c.ev0, st0));
@@ -733,7 +717,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
             q_src = c.d_q;
         }
         launch_knn_search((int)metric_, view(), q_src, count, k, ef, layer, ids_out, d_out, c.d_counters + 3, want_stats ? c.d_stats : nullptr,
-                          exclusive.owns_lock() ? d_gvis_search_ : nullptr, exclusive.owns_lock() ? gvis_search_words_ : 0, tuning_, st0);
+                          tuning_, st0);
     } else {
         HNSW_CUDA_CHECK(cudaEventRecord(c.ev_fork, st0));
         HNSW_CUDA_CHECK(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
@@ -745,7 +729,7 @@ void Index::knn_query(const float* queries, int count, int dim, int k, int* out_
             if (!q_src)
                 HNSW_CUDA_CHECK(cudaMemcpyAsync(c.d_q + (size_t)q0 * dim, queries + (size_t)q0 * dim, (size_t)(q1 - q0) * dim * 4, cudaMemcpyHostToDevice, st));
             launch_knn_search((int)metric_, g, qp, q1 - q0, k, ef, 0, ids_out + (size_t)q0 * k, d_out + (size_t)q0 * k,
-                              c.d_counters + ((p & 1) ? 8 : 3), nullptr, nullptr, 0, tuning_, st);
+                              c.d_counters + ((p & 1) ? 8 : 3), nullptr, tuning_, st);
         }
         HNSW_CUDA_CHECK(cudaEventRecord(c.ev_join, c.aux));
         HNSW_CUDA_CHECK(cudaStreamWaitEvent(st0, c.ev_join, 0));
@@ -785,9 +769,8 @@ void Index::knn_query_device(const float* d_queries, int count, int dim, int k, 
     if (collect_stats_) ensure_stats(count);
     const int ef = std::max(params_.MinNN, k);
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
-    ensure_search_gvis(ef);
     launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, collect_stats_ ? d_stats_ : nullptr,
-                      d_gvis_search_, gvis_search_words_, tuning_, stream_);
+                      tuning_, stream_);
     HNSW_CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     stats_.search_launches += 1;
     HNSW_CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -832,7 +815,7 @@ void Index::knn_query_device_async(const float* d_queries, int count, int dim, i
     HNSW_CUDA_CHECK(cudaSetDevice(device_));
     ensure_dim(dim);
     const int ef = std::max(params_.MinNN, k);
-    const bool overlap = tuning_.vis_global_search <= 0 && tuning_.async_overlap != 0;
+    const bool overlap = tuning_.async_overlap != 0;
     if (overlap && !aux_dirty_) {  // first batch of a sequence: the auxiliary stream starts behind what the primary holds NOW
         HNSW_CUDA_CHECK(cudaEventRecord(ev_fork_, stream_));
         HNSW_CUDA_CHECK(cudaStreamWaitEvent(aux_stream_, ev_fork_, 0));
@@ -841,12 +824,9 @@ void Index::knn_query_device_async(const float* d_queries, int count, int dim, i
     }
     const bool use_aux = overlap && (async_seq_++ & 1u) != 0;
     if (!use_aux) {
-        ensure_search_gvis(ef);
-        launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, nullptr, d_gvis_search_,
-                          gvis_search_words_, tuning_, stream_);
+        launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 3, nullptr, tuning_, stream_);
     } else {
-        launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 8, nullptr, nullptr, 0, tuning_,
-                          aux_stream_);
+        launch_knn_search((int)metric_, view(), d_queries, count, k, ef, 0, d_ids, d_dists, d_counters_ + 8, nullptr, tuning_, aux_stream_);
     }
     stats_.search_launches += 1;
 }

@@ -132,7 +132,6 @@ private:
     void upload_graph(const HostGraph& g);
     GraphView view() const;
     void fetch_query_stats(int count);
-    void ensure_search_gvis(int ef);
     void active_add(int id);
     void active_remove(int id);
     void remove_chunk(const int* ids, int n);
@@ -187,8 +186,6 @@ private:
     // range_query scratch (grow-only): per-query key slices, visited tables, small arrays, packed results
     void *rq_keys_ = nullptr, *rq_hash_ = nullptr, *rq_small_ = nullptr, *rq_dense_ = nullptr;
     size_t rq_keys_bytes_ = 0, rq_hash_bytes_ = 0, rq_small_bytes_ = 0, rq_dense_bytes_ = 0;
-    uint32_t* d_gvis_search_ = nullptr;  // per-warp visited sets of long-row searches
-    size_t gvis_search_words_ = 0;
 
     float* d_q_ = nullptr;
     int* d_ids_ = nullptr;

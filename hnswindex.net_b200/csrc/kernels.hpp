@@ -12,8 +12,12 @@ struct Tuning {
     int vis_size_build = 0;
     int vis_global_build = 0;     // slots per warp of an exact global-memory visited set for the build search (0 = off;
                                   // -23 % evaluations but one more L2 round trip per expansion: no net gain at 1M x 128)
-    int vis_global_search = 0;  // slots per warp of an exact global visited set for long-row (dim > 128) searches (0 = off:
-                                // at C3 it removes 8.7 % of the evaluations, but its L2 round trip per expansion costs as much)
+    int vis_global_search = 0;  // 1: long-row (dim > 128) one-warp searches keep an EXACT visited bitmap per resident warp in global memory
+                                // behind the shared-memory table; the look-ups travel with the first 128 floats of the first 16 rows
+                                // (beam.cuh batch_dist_probe), the rest of the candidates is compacted before its passes are formed.
+                                // 1M x 960, k = 100, ef 192: evaluations 11 288 -> 10 210 per query (the oracle's 10 211), but the
+                                // bitmaps of ~1 800 resident warps (222 MB) do not stay in L2 and their 32-byte DRAM accesses cost
+                                // what the saved rows gave: 72.2 vs 68.6-69.7 ms, 68.8 with a 256-word table -- off
     int build_overlap = 0;    // large insertion batches: run the link kernel on a second stream so that the next batch's select
                               // kernel fills the SM slots freed in the tails.  Off: -4.5 % build time, but the next batch
                               // then sees the previous batch's reverse links only partly and recall@10 drops 0.2 pt
@@ -58,10 +62,10 @@ int device_sm_count();
 // K2: batched KnnQuery (HNSWIndex.cs:107-137).  queries: device [nq][dim] dense fp32;
 // out_ids/out_dists: device [nq][k], rows ascending, padded with -1 / NaN.
 // `layer`: the layer searched (HNSWIndex.cs:107 `layer` argument; 0 = base layer), descent stops above it.
-// d_gvis / gvis_words: optional room for per-warp exact visited sets (used by long-row searches, see search_kernels.cu)
 void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
-                       unsigned* d_work_counter, QueryStats* d_stats, uint32_t* d_gvis, size_t gvis_words, const Tuning& t,
-                       cudaStream_t stream);
+                       unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream);
+// lets the device's default memory pool keep freed scratch (the per-launch visited bitmaps) instead of releasing it at every sync
+void retain_freed_scratch();
 
 // K2w: the same search with one CTA per query and a list that does not shift per insertion (wide_kernels.cu); layer 0 only.
 // launch_knn_search routes to it when wide_search_applies().

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <set>
 
 #include "wide.cuh"
 #include "kernels.hpp"
@@ -30,7 +31,10 @@ knn_search_kernel(GraphView g, const float* __restrict__ queries, int nq, int k,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis_size, cand_cap);
     WarpScratch s = carve_scratch(smem + warp * per_warp, g.pitch, ef, vis_size, cand_cap, lane);
-    if (SPEC & kSpecGvis) gvis_attach(s, gvis + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * gvis_slots, gvis_slots);
+    if (SPEC & kSpecGvis) {  // exact visited bitmap of this warp (long rows): gvis_slots words per warp
+        s.vbm = gvis + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * gvis_slots;
+        s.vbm_words = gvis_slots;
+    }
 
     for (;;) {
         unsigned qi = 0;
@@ -205,9 +209,25 @@ static int configure_persistent(Kern kern, size_t smem_per_warp, const Tuning& t
     return persistent_launch(kern, smem_per_warp, t.blocks_per_sm, work_items, warps);
 }
 
+// The visited bitmaps of the wide-beam and long-row searches are stream-ordered allocations of a few hundred MB per launch:
+// let the device's default pool keep up to 1 GiB of freed memory instead of returning it at every synchronisation.
+void retain_freed_scratch() {
+    static std::mutex mu;
+    static std::set<int> done;
+    int dev = 0;
+    HNSW_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (!done.insert(dev).second) return;
+    cudaMemPool_t pool;
+    HNSW_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t have = 0;
+    HNSW_CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &have));
+    uint64_t want = 1ull << 30;
+    if (have < want) HNSW_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want));
+}
+
 void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
-                       unsigned* d_work_counter, QueryStats* d_stats, uint32_t* d_gvis, size_t gvis_words, const Tuning& t,
-                       cudaStream_t stream) {
+                       unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream) {
     if (nq <= 0) return;
     if (wide_search_applies(g, nq, ef, layer, t)) {
         launch_knn_wide(metric, g, d_queries, nq, k, ef, d_ids, d_dists, d_work_counter, d_stats, t, stream);
@@ -219,6 +239,9 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
     const int cand_cap = ((std::max(g.stride0, g.strideU) + 31) / 32) * 32;
     const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis, cand_cap);
     const size_t per_warp_mid = warp_scratch_bytes(g.pitch, ef, vis_mid, cand_cap);
+    // exact visited bitmap for long-row searches: one bit per node per resident warp (1M nodes: 125 KB x ~1 800 warps)
+    const int bitmap_words = (t.vis_global_search != 0 && g.count <= t.wide_bitmap_max_nodes) ? ((g.count + 127) / 128) * 4 : 0;
+    retain_freed_scratch();
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
 #define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
     {                                                                                                                           \
@@ -235,7 +258,7 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
             const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);                 \
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                                \
                 g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);              \
-        } else if (layer == 0 && t.wl_min_ef > 0 && ef >= t.wl_min_ef && g.pitch > kSegFloats && t.vis_global_search <= 0 &&    \
+        } else if (layer == 0 && t.wl_min_ef > 0 && ef >= t.wl_min_ef && g.pitch > kSegFloats && bitmap_words == 0 &&          \
                    (long long)g.count <= ((long long)vis << 16)) {                                                              \
             constexpr int S = kSpecWideList | kSpecVis16;                                                                       \
             const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                     \
@@ -247,23 +270,21 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                                \
                 g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);              \
         } else if (layer == 0 && g.pitch > kSegFloats && ef <= 1024 && (long long)g.count <= ((long long)vis << 16)) {          \
-            /* long rows are DRAM-bound and every re-evaluation is real traffic (C3: 440 GB read for 393 GB of algorithmic     \
-               bytes): 16-bit tags (same words, twice the entries) and, when the engine provides room, an exact per-warp set    \
-               in global memory behind them -- one 8-byte L2 access per candidate against 4 x dim bytes per evaluation */      \
+            /* long rows are DRAM-bound and every re-evaluation is real traffic (C3: 429 GB read for 393 GB of algorithmic      \
+               bytes): 16-bit tags (same words, twice the entries) and behind them an exact per-warp visited bitmap in global  \
+               memory whose look-up travels with the first segment of the row (beam.cuh batch_dist_probe) */                   \
             constexpr int S = kSpecMidList | kSpecVis16;                                                                        \
-            int grid = configure_persistent(knn_search_kernel<M, false, S | kSpecGvis>, per_warp, t, nq, warps);               \
-            int gslots = 0;                                                                                                     \
-            if (d_gvis != nullptr && t.vis_global_search > 0) {                                                                 \
-                gslots = 1024;                                                                                                  \
-                while (gslots < t.vis_global_search && gslots < 64 * ef) gslots <<= 1;                                          \
-                while (gslots >= 1024 && (size_t)gslots * grid * warps > gvis_words) gslots >>= 1;                              \
-                if (gslots < 1024) gslots = 0;                                                                                  \
-            }                                                                                                                   \
-            if (gslots > 0) {                                                                                                   \
+            if (bitmap_words > 0) {                                                                                             \
+                const int grid = configure_persistent(knn_search_kernel<M, false, S | kSpecGvis>, per_warp, t, nq, warps);     \
+                uint32_t* d_bitmap = nullptr;                                                                                   \
+                HNSW_CUDA_CHECK(cudaMallocAsync(&d_bitmap, (size_t)grid * warps * bitmap_words * sizeof(uint32_t), stream));    \
                 knn_search_kernel<M, false, S | kSpecGvis><<<grid, 32 * warps, per_warp * warps, stream>>>(                    \
-                    g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, d_gvis, gslots); \
+                    g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, d_bitmap, bitmap_words); \
+                const cudaError_t launch_err = cudaGetLastError(); /* back to the pool whether or not the launch took */        \
+                HNSW_CUDA_CHECK(cudaFreeAsync(d_bitmap, stream));                                                               \
+                HNSW_CUDA_CHECK(launch_err);                                                                                    \
             } else {                                                                                                            \
-                grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                           \
+                const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp, t, nq, warps);                 \
                 knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                \
                     g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);  \
             }                                                                                                                   \

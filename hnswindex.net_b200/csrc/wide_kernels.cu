@@ -129,6 +129,8 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
     s.gvis = nullptr;
     s.gvis_size = 0;
     s.gvis_shift = 0;
+    s.vbm = nullptr;
+    s.vbm_words = 0;
 
     for (;;) {
         __syncthreads();  // the previous query is finished by every warp

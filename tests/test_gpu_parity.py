@@ -740,3 +740,27 @@ def test_readd_into_removed_slots_in_one_call(hnswindex, oracle):
     assert (rows0[new_ids] >= 0).sum(axis=1).min() >= 1          # every re-added node is linked
     ref_levels = oracle.draw_levels(31337, 1.0 / np.log(16.0), 9500)
     assert levels[new_ids].tolist() == list(ref_levels[6000:9500])  # the level stream continues where the first Add stopped
+
+
+@pytest.mark.gpu
+def test_long_row_search_with_exact_visited_bitmap(hnswindex, oracle, tmp_path):
+    # Tuning vis_global_search = 1 (beam.cuh batch_dist_probe): identical answers, and the number of distance evaluations drops to
+    # (at most a handful above) the oracle's exact-visited-set count; rows of 64 and of 100 neighbours cover the compaction paths
+    rng = np.random.default_rng(23)
+    for max_edges, n, dim in ((32, 6000, 200), (50, 4000, 136)):
+        data = rng.standard_normal((n, dim)).astype(np.float32)
+        q = rng.standard_normal((300, dim)).astype(np.float32)
+        ref, path = _oracle_graph(oracle, tmp_path, "cosine", data, f"vbm{max_edges}", max_edges=max_edges, collection_size=n)
+        ix = hnswindex.Index.deserialize("cosine", str(path))
+        ix.set_min_nn(150)
+        ids0, d0 = ix.knn_query(q, 20)
+        ix.enable_stats(True); ix.knn_query(q, 20); base = ix.stats()["ndist"]; ix.enable_stats(False)
+        ix.set_tuning("vis_global_search", 1)
+        ids1, d1 = ix.knn_query(q, 20)
+        ix.enable_stats(True); ix.knn_query(q, 20); exact = ix.stats()["ndist"]; ix.enable_stats(False)
+        assert np.array_equal(ids0, ids1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+        ref.set_min_nn(150)
+        oids, od, oc = ref.knn_query(q, 20, threads=8, counters=True)
+        _assert_identical(ids1, d1, oids, od, explain=(oracle, "cosine", data, q))
+        # the oracle counts an exact visited set; the descent is counted a little differently (test_gpu_wide.py)
+        assert exact <= base and 0 <= exact - int(oc[0]) <= 8 * len(q), (exact, int(oc[0]), base)

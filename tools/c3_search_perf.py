@@ -1,4 +1,4 @@
-"""Exploration: C3 at full size (1M x 960 cosine, M=32): search kernel time with / without the global visited set."""
+"""Exploration: C3 at full size (1M x 960 cosine, M=32): search kernel time with / without the exact visited bitmap."""
 import sys, time, json
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -15,10 +15,8 @@ ix.set_min_nn(192)
 qd = [torch.from_numpy(q[i * 10000:(i + 1) * 10000]).cuda() for i in range(2)]
 ids = torch.empty((10000, 100), dtype=torch.int32, device="cuda"); dd = torch.empty((10000, 100), dtype=torch.float32, device="cuda")
 base = None
-cfgs = [{"vis_size_search": 0}, {"vis_size_search": 2048}, {"vis_size_search": 4096}, {"vis_size_search": 8192},
-        {"vis_size_search": 0, "wl_min_ef": 1}, {"vis_size_search": 4096, "wl_min_ef": 1},
-        {"vis_size_search": 0, "wl_min_ef": 256, "wide_min_ef": 1, "wide_warps": 3}, {"wide_min_ef": 1, "wide_warps": 4},
-        {"wide_min_ef": 1, "wide_warps": 4, "vis_size_search": 4096}, {"wide_min_ef": 1024, "wide_warps": 0, "vis_size_search": 0}]
+cfgs = [{"vis_global_search": 0}, {"vis_global_search": 1}, {"vis_global_search": 0}, {"vis_global_search": 1},
+        {"vis_global_search": 1, "vis_size_search": 256}, {"vis_global_search": 1, "vis_size_search": 128}, {"vis_global_search": 1, "vis_size_search": 1024}]
 for cfg in cfgs:
     for k, v in cfg.items(): ix.set_tuning(k, v)
     ix.enable_stats(True); ix.knn_query_device(qd[0].data_ptr(), 10000, 100, ids.data_ptr(), dd.data_ptr()); st = ix.stats(); ix.enable_stats(False)
