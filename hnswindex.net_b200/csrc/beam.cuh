@@ -38,11 +38,9 @@ struct WarpScratch {
     int vis_size;      // power of two >= 64
     int vis_shift;     // 32 - log2(vis_size / 2)
     int cap;           // list capacity (>= ef)
-    uint32_t* gvis;    // optional exact visited set of this warp in GLOBAL memory (open addressing, ids + 1), or null
-    int gvis_size;     // slots, power of two
-    int gvis_shift;    // 32 - log2(gvis_size)
     uint32_t* vbm;     // optional EXACT visited bitmap of this warp in global memory (one bit per node; long-row searches), or null
     int vbm_words;     // its size in 32-bit words (multiple of 4)
+    // (keep this struct small: two more words and ptxas compiles the 96-register construction kernel in a mode that runs 2.4x slower)
 };
 
 constexpr int kPrefetchRows = 1;  // flags bit 0: L2-prefetch the adjacency rows of accepted candidates
@@ -77,9 +75,6 @@ __device__ __forceinline__ WarpScratch carve_scratch(unsigned char* base, int pi
     s.vis_size = vis_size;
     s.vis_shift = 32 - (31 - __clz(vis_size >> 1));
     s.cap = cap;
-    s.gvis = nullptr;
-    s.gvis_size = 0;
-    s.gvis_shift = 0;
     s.vbm = nullptr;
     s.vbm_words = 0;
     return s;
@@ -146,13 +141,24 @@ __device__ __forceinline__ void stage_complete(Stager& stg) {
 #endif
 }
 
+// SPEC (compile-time knowledge that lets the hot kernels drop dead code; 0 = generic):
+//   bit 0: rows fit one staging segment (pitch <= kSegFloats);  bit 1: the list never exceeds 64 entries (ef <= 64)
+//   bit 2: the visited table holds 16-bit tags (vis16_test_and_set): every id of the index is below vis_size * 65536
+//   bit 3: the list never exceeds 1024 entries (ef <= 1024): the binary-search insertion path is dead code
+//   bit 5: the search kernel attaches an exact per-warp visited bitmap in global memory behind the shared-memory table
+//          (long rows: WarpScratch::vbm, batch_dist_probe; the CTA-per-query kernel has its own use of the bit)
+//   bit 6: the list is wide.cuh's non-shifting WideList (sorted main array + 32 pending keys in registers), layer 0 only
+//   bit 7: vectors of exactly 128 floats (dim == pitch == 128): constant trip counts in the distance loops (construction)
+constexpr int kSpecShortRows = 1, kSpecSmallList = 2, kSpecVis16 = 4, kSpecMidList = 8, kSpecGvis = 32, kSpecWideList = 64, kSpecDim128 = 128;
+
 // rows of at most kSegFloats floats (one segment), already staged: distances of ids[base .. base+nrows) -> out
-template <int METRIC>
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void compute_staged(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, const int* ids, float* out,
                                                int base, int nrows, int lane) {
     constexpr bool SQ = metric_is_sq(METRIC);
     const int h = lane & 1, grp = lane >> 1;
-    const int nfull = g.dim >> 3, ntail = g.dim - (nfull << 3);
+    // kSpecDim128: the chunk loop has a compile-time trip count (the construction kernel is issue-bound: its loop control counts)
+    const int nfull = (SPEC & kSpecDim128) ? 16 : g.dim >> 3, ntail = (SPEC & kSpecDim128) ? 0 : g.dim - (nfull << 3);
     const bool active = grp < nrows;
     double an = 0.0;
     if (METRIC == COSINE && active) an = __ldg(g.norm_sqrt + ids[base + grp]);
@@ -165,14 +171,6 @@ __device__ __forceinline__ void compute_staged(const GraphView& g, Stager& stg, 
     __syncwarp();  // staged rows are free again, distances are visible
 }
 
-// SPEC (compile-time knowledge that lets the hot kernels drop dead code; 0 = generic):
-//   bit 0: rows fit one staging segment (pitch <= kSegFloats);  bit 1: the list never exceeds 64 entries (ef <= 64)
-//   bit 2: the visited table holds 16-bit tags (vis16_test_and_set): every id of the index is below vis_size * 65536
-//   bit 3: the list never exceeds 1024 entries (ef <= 1024): the binary-search insertion path is dead code
-//   bit 5: the search kernel attaches an exact per-warp visited bitmap in global memory behind the shared-memory table
-//          (long rows: WarpScratch::vbm, batch_dist_probe; the CTA-per-query kernel has its own use of the bit)
-//   bit 6: the list is wide.cuh's non-shifting WideList (sorted main array + 32 pending keys in registers), layer 0 only
-constexpr int kSpecShortRows = 1, kSpecSmallList = 2, kSpecVis16 = 4, kSpecMidList = 8, kSpecGvis = 32, kSpecWideList = 64;
 
 template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, const float* q, double q_norm_sqrt, const int* ids, float* out,
@@ -186,7 +184,7 @@ __device__ __forceinline__ void batch_dist_to(const GraphView& g, Stager& stg, c
         if ((SPEC & kSpecShortRows) || g.pitch <= kSegFloats) {
             stage_issue(g, stg, ids, base, nrows, 0, g.pitch, lane);
             stage_complete(stg);
-            compute_staged<METRIC>(g, stg, q, q_norm_sqrt, ids, out, base, nrows, lane);
+            compute_staged<METRIC, SPEC>(g, stg, q, q_norm_sqrt, ids, out, base, nrows, lane);
             continue;
         }
         if (SPEC & kSpecShortRows) continue;  // (unreachable; lets the compiler drop the long-row code)
@@ -468,34 +466,6 @@ __device__ __forceinline__ bool vis16_test_and_set(const WarpScratch& s, int id)
     return true;
 }
 
-// Exact second level behind the shared-memory table (construction, where a search touches thousands of nodes and a
-// forgetful table re-evaluates ~60 % of them): a per-warp open-addressing set in global memory (L2 atomics).  Still
-// "never invents": when 16 probes find neither the id nor a free slot the node is simply evaluated again.
-__device__ __forceinline__ void gvis_attach(WarpScratch& s, uint32_t* table, int slots) {
-    s.gvis = table;
-    s.gvis_size = slots;
-    s.gvis_shift = 32 - (31 - __clz(slots));
-}
-__device__ __forceinline__ void gvis_clear(const WarpScratch& s, int lane) {
-    uint4* t = reinterpret_cast<uint4*>(s.gvis);
-    for (int i = lane; i < (s.gvis_size >> 2); i += 32) t[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncwarp();
-}
-__device__ __forceinline__ bool gvis_test_and_set(const WarpScratch& s, int id) {
-    // 2-way buckets read with ONE 64-bit load that bypasses L1 (the table lives in L2), updated with a plain store:
-    // only this warp touches its table, and two lanes of one instruction landing in the same bucket merely lose one
-    // of the two records (that node may be evaluated again later -- harmless)
-    const uint32_t tag = (uint32_t)id + 1u;
-    const uint32_t b = (tag * 0x9E3779B1u) >> (s.gvis_shift + 1);
-    uint2* bucket = reinterpret_cast<uint2*>(s.gvis) + b;
-    const uint2 v = __ldcg(bucket);
-    if (v.x == tag || v.y == tag) return false;
-    if (v.x == 0u) __stcg(&bucket->x, tag);
-    else if (v.y == 0u) __stcg(&bucket->y, tag);
-    else __stcg(bucket, make_uint2(tag, v.x));  // full bucket: the older record is dropped
-    return true;
-}
-
 // ----------------------------------------------------------------------------
 // Greedy descent on one upper layer (GraphNavigator.cs:51-82): scan the whole
 // row of the current node in stored order, move to the strict minimum (first
@@ -583,7 +553,6 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
     st.far_ord = 0xFFFFFFFFu;
     st.cursor = 0;
     vis_clear(s, lane);
-    if (s.gvis != nullptr) gvis_clear(s, lane);
     if ((SPEC & kSpecGvis) && s.vbm != nullptr) {
         uint4* t = reinterpret_cast<uint4*>(s.vbm);
         for (int i = lane; i < (s.vbm_words >> 2); i += 32) __stcg(t + i, make_uint4(0u, 0u, 0u, 0u));
@@ -594,7 +563,6 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
     list_insert<SPEC>(s.list, st, make_key(entry_d, entry), lane);
     if (lane == 0) {
         if (vis16) vis16_test_and_set(s, entry); else vis_test_and_set(s, entry);
-        if (s.gvis != nullptr) gvis_test_and_set(s, entry);
         if ((SPEC & kSpecGvis) && s.vbm != nullptr) atomicOr(s.vbm + (entry >> 5), 1u << (entry & 31));
     }
     __syncwarp();
@@ -629,7 +597,6 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
             deg += __popc(__ballot_sync(FULL, nb >= 0));
             bool fresh = false;
             if (nb >= 0) fresh = vis16 ? vis16_test_and_set(s, nb) : vis_test_and_set(s, nb);
-            if (s.gvis != nullptr && fresh) fresh = gvis_test_and_set(s, nb);
             const unsigned mk = __ballot_sync(FULL, fresh);
             if (fresh) s.cand_id[m + __popc(mk & ((1u << lane) - 1u))] = nb;
             m += __popc(mk);
@@ -647,7 +614,7 @@ __device__ __forceinline__ void beam_search(const GraphView& g, WarpScratch& s, 
             for (int base = 0; base < m; base += kStageRows) {
                 const int nrows = min(kStageRows, m - base);
                 stage_complete(s.stg);
-                compute_staged<METRIC>(g, s.stg, s.q, qn, s.cand_id, s.cand_dist, base, nrows, lane);
+                compute_staged<METRIC, SPEC>(g, s.stg, s.q, qn, s.cand_id, s.cand_dist, base, nrows, lane);
                 const int nbase = base + kStageRows;
                 if (nbase < m) {
                     stage_issue(g, s.stg, s.cand_id, nbase, min(kStageRows, m - nbase), 0, g.pitch, lane);

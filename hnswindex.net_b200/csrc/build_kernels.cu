@@ -33,11 +33,10 @@ enum BuildProf : int {
     BP_CYC_LINK, BP_CYC_PRUNE, BP_PRUNES, BP_NDIST_PRUNE, BP_CYC_LOCK, BP_CYC_SELECT_KERNEL, BP_LINKS, BP_WORDS
 };
 
-// WARPS = warps per block: 4, or 3 with six blocks per SM (18 instead of 16 resident warps; needs <= 112 registers)
-template <int METRIC, int SPEC, int WARPS = 4>
-__global__ void __launch_bounds__(32 * WARPS, WARPS == 3 ? 6 : 4)
-build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int efc, int list_cap, int vis_size, int cand_cap,
-                    int sel_cap, unsigned* work_counter, u64* prof, uint32_t* gvis, int gvis_slots, int flags, int* ready, int epoch) {
+template <int METRIC, int SPEC>
+__device__ __forceinline__ void build_select_body(const GraphView& g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int efc,
+                                                  int list_cap, int vis_size, int cand_cap, int sel_cap, unsigned* work_counter, u64* prof, int flags,
+                                                  int* ready, int epoch) {
     extern __shared__ __align__(128) unsigned char smem[];
     // Tail fill (ready != null): the link kernel that follows in the stream is a programmatic dependent launch.  Its blocks
     // may become resident as soon as every block of THIS grid has started, i.e. into the slots the first finishing select
@@ -47,10 +46,8 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, vis_size, cand_cap, sel_cap);
     BuildScratch b = carve_build(smem + warp * per_warp, g.pitch, list_cap, vis_size, cand_cap, sel_cap, lane);
     WarpScratch& s = b.s;
-    if (gvis_slots > 0) gvis_attach(s, gvis + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * gvis_slots, gvis_slots);
-    long long cyc_descent = 0, cyc_search = 0, cyc_select = 0;
-    unsigned n_items = 0, nd_search = 0, nd_select = 0;
-    const long long t_begin = clock64();
+    // Profile counters go to global memory as they arise (a few atomics per 1.7 ms insertion): nothing of them is carried
+    // across the searches of this issue- and register-bound kernel.
 
     for (;;) {
         unsigned wi = 0;
@@ -59,8 +56,6 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
         if (wi >= (unsigned)count) break;
         const int v = __ldg(new_ids + wi);
         const int level = __ldg(levels + v);
-        ++n_items;
-
         long long t0 = clock64();
         load_vector(g, v, s.q, lane);
         double qn = 0.0;
@@ -71,14 +66,22 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
         float cur_d = single_dist<METRIC, SPEC>(g, s, qn, cur, lane);
         for (int layer = g.top_layer; layer > level; --layer) greedy_layer<METRIC, SPEC>(g, s, qn, layer, cur, cur_d, lane, wc);
         long long t1 = clock64();
-        cyc_descent += t1 - t0;
+        if (lane == 0) {
+            atomicAdd(prof + BP_INSERTS, (u64)1);
+            atomicAdd(prof + BP_CYC_DESCENT, (u64)(t1 - t0));
+            atomicAdd(prof + BP_CYC_SELECT_KERNEL, (u64)(t1 - t0));  // busy cycles of the warp: descent + searches + heuristic
+        }
 
         for (int layer = min(level, g.top_layer); layer >= 0; --layer) {
             BeamState st;
             t0 = clock64();
             beam_search<METRIC, SPEC>(g, s, qn, layer, cur, cur_d, efc, st, lane, wc, flags);
             t1 = clock64();
-            cyc_search += t1 - t0;
+            if (lane == 0) {
+                atomicAdd(prof + BP_CYC_SEARCH, (u64)(t1 - t0));
+                atomicAdd(prof + BP_CYC_SELECT_KERNEL, (u64)(t1 - t0));
+            }
+            unsigned nd_select = 0;
             const int maxE = layer == 0 ? 2 * g.max_edges : g.max_edges;
             int nsel;
             int next;
@@ -96,7 +99,12 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
                 next = key_id(s.list[0]);  // the closest candidate is always selected first
                 next_d = key_dist(s.list[0]);
             }
-            cyc_select += clock64() - t1;
+            if (lane == 0) {
+                const u64 dt = (u64)(clock64() - t1);
+                atomicAdd(prof + BP_CYC_SELECT, dt);
+                atomicAdd(prof + BP_CYC_SELECT_KERNEL, dt);
+                atomicAdd(prof + BP_NDIST_SELECT, (u64)nd_select);
+            }
             int stride;
             int* row = row_ptr_mut(g, v, layer, stride);
             for (int j = lane; j < stride; j += 32) row[j] = j < nsel ? b.sel[j] : -1;
@@ -104,25 +112,28 @@ build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __re
             cur = next;
             cur_d = next_d;
         }
-        nd_search += wc.ndist;
+        if (lane == 0) atomicAdd(prof + BP_NDIST_SEARCH, (u64)wc.ndist);
         if (ready != nullptr) {
-            // every lane's row stores, then the flag (release).  Indexed by node id, not by batch position: `v` is live here
-            // anyway, while a position kept across the searches costs the 96-register build of this kernel a factor 2.4
+            // every lane's row stores, then the flag (release).  Indexed by node id, not by batch position: `v` is live here anyway
             __threadfence();
             __syncwarp();
             if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready + v), "r"(epoch) : "memory");
         }
         __syncwarp();
     }
-    if (lane == 0 && n_items > 0) {
-        atomicAdd(prof + BP_INSERTS, (u64)n_items);
-        atomicAdd(prof + BP_CYC_DESCENT, (u64)cyc_descent);
-        atomicAdd(prof + BP_CYC_SEARCH, (u64)cyc_search);
-        atomicAdd(prof + BP_CYC_SELECT, (u64)cyc_select);
-        atomicAdd(prof + BP_NDIST_SEARCH, (u64)nd_search);
-        atomicAdd(prof + BP_NDIST_SELECT, (u64)nd_select);
-        atomicAdd(prof + BP_CYC_SELECT_KERNEL, (u64)(clock64() - t_begin));
-    }
+}
+
+// Four blocks of four warps per SM.  (A shape of six three-warp blocks -- 18 instead of 16 resident warps -- was the default for
+// a while: under __launch_bounds__(96, 6) ptxas settled on 96 registers, and on that edge the compile was bimodal: one mode
+// moved the loop control of the distance loops to the uniform datapath and ran 4 % faster than this shape, the other -- reached
+// through unrelated edits such as two more words in WarpScratch or one more value live across the searches -- reported no spills
+// either and ran 2.4x slower.  With a stated budget of 112 registers the shape equals this one; the constant trip counts of
+// kSpecDim128 give what the lucky mode gave, reliably.  Removed.)
+template <int METRIC, int SPEC>
+__global__ void __launch_bounds__(kThreads, 4)
+build_select_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int efc, int list_cap, int vis_size, int cand_cap,
+                    int sel_cap, unsigned* work_counter, u64* prof, int flags, int* ready, int epoch) {
+    build_select_body<METRIC, SPEC>(g, levels, new_ids, count, efc, list_cap, vis_size, cand_cap, sel_cap, work_counter, prof, flags, ready, epoch);
 }
 
 __device__ __forceinline__ bool lock_node(int* locks, int n, int lane, int* error_flag) {
@@ -268,17 +279,9 @@ static int persistent_grid(Kern kern, size_t smem_per_warp, const Tuning& t, int
     return persistent_launch(kern, smem_per_warp, t.blocks_per_sm, work_items, warps);
 }
 
-// slots of the global visited set each warp of the select kernel gets (0 = not used)
-static int gvis_slots_per_warp(const uint32_t* d_gvis, size_t gvis_words, size_t warps, const Tuning& t) {
-    if (d_gvis == nullptr || t.vis_global_build <= 0 || warps == 0) return 0;
-    int slots = pow2_ge(t.vis_global_build);
-    while (slots >= 1024 && (size_t)slots * warps > gvis_words) slots >>= 1;
-    return slots >= 1024 ? slots : 0;
-}
-
 // d_work_counter: [0] select work, [1] link work, [2] error flag, [9] select work of every other batch (tail fill)
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, const int* d_new_ids, int count, int efc, unsigned* d_work_counter,
-                        u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream,
+                        u64* d_build_prof, const Tuning& t, cudaStream_t stream,
                         cudaStream_t link_stream, cudaEvent_t select_done, int* d_ready, int epoch) {
     if (count <= 0) return;
     if (link_stream == nullptr) link_stream = stream;
@@ -290,7 +293,6 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
     const int sel_cap = std::max(maxE0, list_cap_sel < maxE0 ? list_cap_sel : maxE0);
     // small table: shared memory per warp decides the occupancy of this latency-bound kernel (see search_kernels.cu)
     int vis = t.vis_size_build > 0 ? std::max(64, pow2_ge(t.vis_size_build)) : std::min(2048, std::max(256, pow2_ge(2 * efc)));
-    if (t.vis_size_build <= 0 && d_gvis != nullptr && t.vis_global_build > 0) vis = 256;  // first-level filter only
     // 16-bit tags (beam.cuh vis16_test_and_set) hold two entries per word: half the words keep the same filter and let a
     // fourth block fit on the SM
     if (t.vis_size_build <= 0 && vis > 256 && (long long)g.count <= ((long long)(vis / 2) << 16)) vis /= 2;
@@ -303,41 +305,31 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
     HNSW_CUDA_CHECK(cudaMemsetAsync(sel_counter, 0, sizeof(unsigned), stream));
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter + 1, 0, sizeof(unsigned), link_stream));
     int* err = reinterpret_cast<int*>(d_work_counter + 2);
+#define HNSW_LAUNCH_SELECT_C5(M, SPECV)                                                                                        \
+    {                                                                                                                           \
+        constexpr int S = SPECV;                                                                                                \
+        const int g1 = persistent_grid(build_select_kernel<M, S>, smem_sel, t, count, w1);                                     \
+        build_select_kernel<M, S><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                      \
+            g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, t.build_flags, d_ready, epoch); \
+    }
 #define HNSW_LAUNCH_BUILD(M)                                                                                                    \
     {                                                                                                                           \
         int w1 = 0, w2 = 0;                                                                                                     \
         if (vis16 && g.pitch <= kSegFloats && list_cap_sel <= 1024 && t.build_specialized != 0) {                                \
-            /* the C5 shape: rows of one staging segment, MaxCandidates <= 1024, 16-bit tags -- no long-row / large-list code */ \
-            constexpr int S = kSpecVis16 | kSpecShortRows | kSpecMidList;                                                       \
-            const int g1 = persistent_grid(build_select_kernel<M, S>, smem_sel, t, count, w1);                                 \
-            /* three-warp blocks when six of them fit where four four-warp blocks do */                                         \
-            int per3 = 0;                                                                                                        \
-            if (w1 == 4 && t.build_warps3 != 0 && smem_sel * 3 <= (size_t)48 * 1024 * 4) {                                      \
-                if (smem_sel * 3 > (size_t)48 * 1024) /* per device, per launch: cheap next to a batch */                       \
-                    HNSW_CUDA_CHECK(cudaFuncSetAttribute(build_select_kernel<M, S, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_sel * 3))); \
-                HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, build_select_kernel<M, S, 3>, 96, smem_sel * 3)); \
-            }                                                                                                                    \
-            int per4 = 0;                                                                                                        \
-            HNSW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per4, build_select_kernel<M, S>, 128, smem_sel * 4)); \
-            if (per3 * 3 > per4 * 4 && t.blocks_per_sm <= 0) {                                                                  \
-                const int g3 = std::max(1, std::min((count + 2) / 3, device_sm_count() * per3));                                \
-                build_select_kernel<M, S, 3><<<g3, 96, smem_sel * 3, stream>>>(                                                 \
-                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, nullptr, 0, t.build_flags, d_ready, epoch); \
-            } else {                                                                                                             \
-                const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                \
-                build_select_kernel<M, S><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                             \
-                    g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, d_gvis, gslots, t.build_flags, d_ready, epoch); \
-            }                                                                                                                    \
+            /* the C5 shape: rows of one staging segment, MaxCandidates <= 1024, 16-bit tags -- no long-row / large-list code; \
+               and for vectors of exactly 128 floats the distance loops have compile-time trip counts */                       \
+            if (g.dim == 128 && g.pitch == 128 && t.build_dim128 != 0)                                                          \
+                HNSW_LAUNCH_SELECT_C5(M, (kSpecVis16 | kSpecShortRows | kSpecMidList | kSpecDim128))                            \
+            else                                                                                                                \
+                HNSW_LAUNCH_SELECT_C5(M, (kSpecVis16 | kSpecShortRows | kSpecMidList))                                          \
         } else if (vis16) {                                                                                                     \
             const int g1 = persistent_grid(build_select_kernel<M, kSpecVis16>, smem_sel, t, count, w1);                        \
-            const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
             build_select_kernel<M, kSpecVis16><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                        \
-                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, d_gvis, gslots, t.build_flags, d_ready, epoch); \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, t.build_flags, d_ready, epoch); \
         } else {                                                                                                                \
             const int g1 = persistent_grid(build_select_kernel<M, 0>, smem_sel, t, count, w1);                                 \
-            const int gslots = gvis_slots_per_warp(d_gvis, gvis_words, (size_t)g1 * w1, t);                                    \
             build_select_kernel<M, 0><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                 \
-                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, d_gvis, gslots, t.build_flags, d_ready, epoch); \
+                g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, t.build_flags, d_ready, epoch); \
         }                                                                                                                       \
         if (link_stream != stream) { /* the links of this batch follow its select kernel, on their own stream */             \
             HNSW_CUDA_CHECK(cudaEventRecord(select_done, stream));                                                             \
@@ -370,6 +362,7 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
         default: HNSW_LAUNCH_BUILD(UCOSINE) break;
     }
 #undef HNSW_LAUNCH_BUILD
+#undef HNSW_LAUNCH_SELECT_C5
     HNSW_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -79,10 +79,10 @@ __device__ __forceinline__ int select_neighbors_long(const GraphView& g, BuildSc
 }
 
 // distance between one staged row (this lane pair's) and a vector in shared memory; both lanes of the pair get it
-template <int METRIC>
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ float staged_row_dist(const GraphView& g, const float* row, const float* q, double an, double qn, bool active, int h) {
     constexpr bool SQ = metric_is_sq(METRIC);
-    const int nfull = g.dim >> 3, ntail = g.dim - (nfull << 3);
+    const int nfull = (SPEC & kSpecDim128) ? 16 : g.dim >> 3, ntail = (SPEC & kSpecDim128) ? 0 : g.dim - (nfull << 3);
     PairAcc acc = {0.f, 0.f, 0.f, 0.f};
     if (active) pair_accumulate<SQ>(acc, row, q, nfull, h);
     float r = pair_hsum<SQ>(acc);
@@ -96,7 +96,7 @@ __device__ __forceinline__ float staged_row_dist(const GraphView& g, const float
 // then the window is resolved in order, a newly selected candidate being tested against the later ones straight out
 // of the staging buffer.  A candidate is dropped at the first selected neighbour that is strictly closer to it than
 // the base vector is (Heuristic.cs:31-35), so it is evaluated against exactly the neighbours the reference tries.
-template <int METRIC>
+template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ int select_neighbors_windowed(const GraphView& g, BuildScratch& b, const u64* list, int n, int maxE, int lane,
                                                          unsigned& ndist) {
     WarpScratch& s = b.s;
@@ -136,7 +136,7 @@ __device__ __forceinline__ int select_neighbors_windowed(const GraphView& g, Bui
             if (METRIC == COSINE) qn = __ldg(g.norm_sqrt + b.sel[j]);
             const bool act = !rej;
             ndist += __popc(__ballot_sync(FULL, act && h == 0));
-            const float d = staged_row_dist<METRIC>(g, row, qv, an, qn, act, h);
+            const float d = staged_row_dist<METRIC, SPEC>(g, row, qv, an, qn, act, h);
             if (act && d < cd) rej = true;  // strict, Heuristic.cs:34
             __syncwarp();                   // the slot of j is free for the copy issued two iterations later
         }
@@ -154,7 +154,7 @@ __device__ __forceinline__ int select_neighbors_windowed(const GraphView& g, Bui
             ndist += __popc(later);
             double qn = 0.0;
             if (METRIC == COSINE) qn = __ldg(g.norm_sqrt + s.cand_id[gi]);
-            const float d = staged_row_dist<METRIC>(g, row, s.stg.buf + gi * kSegPitch, an, qn, act, h);
+            const float d = staged_row_dist<METRIC, SPEC>(g, row, s.stg.buf + gi * kSegPitch, an, qn, act, h);
             if (act && d < cd) rej = true;
         }
         __syncwarp();  // staged rows, cand_id and sel are consistent before the next window overwrites them
@@ -166,7 +166,7 @@ __device__ __forceinline__ int select_neighbors_windowed(const GraphView& g, Bui
 template <int METRIC, int SPEC = 0>
 __device__ __forceinline__ int select_neighbors(const GraphView& g, BuildScratch& b, const u64* list, int n, int maxE, int lane, unsigned& ndist) {
 #ifndef HNSW_STAGE_BULK
-    if ((SPEC & kSpecShortRows) || g.pitch <= kSegFloats) return select_neighbors_windowed<METRIC>(g, b, list, n, maxE, lane, ndist);
+    if ((SPEC & kSpecShortRows) || g.pitch <= kSegFloats) return select_neighbors_windowed<METRIC, SPEC>(g, b, list, n, maxE, lane, ndist);
 #endif
     if (SPEC & kSpecShortRows) return 0;  // (unreachable)
     return select_neighbors_long<METRIC>(g, b, list, n, maxE, lane, ndist);

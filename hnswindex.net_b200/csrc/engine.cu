@@ -101,7 +101,7 @@ Index::Index(MetricKind metric, const Parameters& params) : metric_(metric), par
 Index::~Index() {
     cudaSetDevice(device_);
     cudaFree(d_vectors_); cudaFree(d_norms_); cudaFree(d_adj0_); cudaFree(d_upper_off_); cudaFree(d_adjU_);
-    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_); cudaFree(d_gvis_);
+    cudaFree(d_locks_); cudaFree(d_levels_); cudaFree(d_counters_); cudaFree(d_build_prof_);
     cudaFree(rq_keys_); cudaFree(rq_hash_); cudaFree(rq_small_); cudaFree(rq_dense_);
     cudaFree(rm_small_); cudaFree(rm_aff_); cudaFree(d_rm_index_); cudaFree(d_new_ids_); cudaFree(d_ready_);
     cudaFree(d_q_); cudaFree(d_ids_); cudaFree(d_dists_); cudaFree(d_stats_);
@@ -125,7 +125,6 @@ Index::~Index() {
 void Index::set_tuning(const std::string& key, int value) {
     if (key == "vis_size_search") tuning_.vis_size_search = value;
     else if (key == "vis_size_build") tuning_.vis_size_build = value;
-    else if (key == "vis_global_build") tuning_.vis_global_build = value;
     else if (key == "vis_global_search") tuning_.vis_global_search = value;
     else if (key == "blocks_per_sm") tuning_.blocks_per_sm = value;
     else if (key == "flags") tuning_.flags = value;
@@ -138,7 +137,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "sync_pieces") tuning_.sync_pieces = value;
     else if (key == "build_overlap") tuning_.build_overlap = value;
     else if (key == "build_specialized") tuning_.build_specialized = value;
-    else if (key == "build_warps3") tuning_.build_warps3 = value;
+    else if (key == "build_dim128") tuning_.build_dim128 = value;
     else if (key == "build_flags") tuning_.build_flags = value;
     else if (key == "build_tail_fill") tuning_.build_tail_fill = value;
     else if (key == "exact_tcgen05") tuning_.exact_tcgen05 = value;
@@ -373,16 +372,6 @@ void Index::add_committed(const float* vectors, int count, int dim, const std::v
     }
     length_ = first + nfresh;
 
-    if (tuning_.vis_global_build > 0) {  // room for 16 warps per SM
-        int slots = 1024;
-        while (slots < tuning_.vis_global_build) slots <<= 1;
-        const size_t words = (size_t)device_sm_count() * 16 * slots;
-        if (words > gvis_words_) {
-            cudaFree(d_gvis_); d_gvis_ = nullptr; gvis_words_ = 0;
-            HNSW_CUDA_CHECK(cudaMalloc(&d_gvis_, words * sizeof(uint32_t)));
-            gvis_words_ = words;
-        }
-    }
     HNSW_CUDA_CHECK(cudaEventRecord(ev0_, stream_));
     int done = 0;
     bool links_on_aux = false;
@@ -416,8 +405,8 @@ void Index::add_committed(const float* vectors, int count, int dim, const std::v
             HNSW_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join_, 0));
             links_on_aux = false;
         }
-        launch_build_batch((int)metric_, view(), d_levels_, d_new_ids_ + done, batch, params_.MaxCandidates, d_counters_, d_build_prof_, d_gvis_,
-                           gvis_words_, tuning_, stream_, overlap ? aux_stream_ : stream_, ev_fork_, d_ready_, ++build_epoch_);
+        launch_build_batch((int)metric_, view(), d_levels_, d_new_ids_ + done, batch, params_.MaxCandidates, d_counters_, d_build_prof_,
+                           tuning_, stream_, overlap ? aux_stream_ : stream_, ev_fork_, d_ready_, ++build_epoch_);
         links_on_aux = links_on_aux || overlap;
         stats_.build_launches += 2;
         if (new_top) {  // GraphConnector.cs:36-41

@@ -179,8 +179,6 @@ private:
     int* d_levels_ = nullptr;
     unsigned* d_counters_ = nullptr;  // [0..2] build (+ [9]), [3] search, [4..5] remove, [6..7] scatter, [8] second query stream
     u64* d_build_prof_ = nullptr;     // [16]
-    uint32_t* d_gvis_ = nullptr;      // per-warp visited sets of the build search (allocated by the first add)
-    size_t gvis_words_ = 0;
     void *rm_small_ = nullptr, *rm_aff_ = nullptr;   // remove() scratch (grow-only)
     size_t rm_small_bytes_ = 0, rm_aff_bytes_ = 0;
     // range_query scratch (grow-only): per-query key slices, visited tables, small arrays, packed results

@@ -10,8 +10,6 @@ namespace hnsw {
 struct Tuning {
     int vis_size_search = 0;  // 0 = derive from ef
     int vis_size_build = 0;
-    int vis_global_build = 0;     // slots per warp of an exact global-memory visited set for the build search (0 = off;
-                                  // -23 % evaluations but one more L2 round trip per expansion: no net gain at 1M x 128)
     int vis_global_search = 0;  // 1: long-row (dim > 128) one-warp searches keep an EXACT visited bitmap per resident warp in global memory
                                 // behind the shared-memory table; the look-ups travel with the first 128 floats of the first 16 rows
                                 // (beam.cuh batch_dist_probe), the rest of the candidates is compacted before its passes are formed.
@@ -26,8 +24,8 @@ struct Tuning {
                               // starting when the last insertion of the batch has ended (a batch is ~6 insertions deep per warp, so
                               // the select kernel's tail is ~8 % of it)
     int build_flags = 2;        // beam-search flags of the construction search (bit 0: L2-prefetch rows of accepted candidates, bit 1: guess-row load)
-    int build_warps3 = 1;       // select kernel as 6 blocks of 3 warps per SM instead of 4 of 4 when registers and shared memory allow
     int build_specialized = 1;  // the C5-shaped select kernel instantiation (short rows, MaxCandidates <= 1024, 16-bit tags)
+    int build_dim128 = 1;       // ... and, for vectors of exactly 128 floats, the instantiation whose distance loops have constant trip counts
     int sync_pieces = 0;      // hnsw_knn_query: pieces a large batch is split into, alternating two streams (0 = 2 for page-locked, 4 for pageable buffers)
     int async_overlap = 1;    // hnsw_knn_query_device_async alternates two streams (consecutive batches overlap in their tails)
     int blocks_per_sm = 0;    // 0 = occupancy query
@@ -93,7 +91,7 @@ void launch_scatter_new_items(const float* d_src, const int* d_src_row, const in
 // d_ready / epoch (tail fill, Tuning::build_tail_fill): one word per node id, set to `epoch` by the select kernel
 // when the node's rows are written; the link kernel then starts under the select kernel's tail and waits per node.
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, const int* d_new_ids, int count, int ef_construction,
-                        unsigned* d_work_counter, u64* d_build_prof, uint32_t* d_gvis, size_t gvis_words, const Tuning& t, cudaStream_t stream,
+                        unsigned* d_work_counter, u64* d_build_prof, const Tuning& t, cudaStream_t stream,
                         cudaStream_t link_stream = nullptr, cudaEvent_t select_done = nullptr, int* d_ready = nullptr, int epoch = 0);
 
 // RangeQuery (HNSWIndex.cs:144-168): traversal of all in-range nodes reachable from the layer-0 entry.  Work item w handles

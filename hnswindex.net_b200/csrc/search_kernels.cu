@@ -229,6 +229,7 @@ void retain_freed_scratch() {
 void launch_knn_search(int metric, const GraphView& g, const float* d_queries, int nq, int k, int ef, int layer, int* d_ids, float* d_dists,
                        unsigned* d_work_counter, QueryStats* d_stats, const Tuning& t, cudaStream_t stream) {
     if (nq <= 0) return;
+    retain_freed_scratch();
     if (wide_search_applies(g, nq, ef, layer, t)) {
         launch_knn_wide(metric, g, d_queries, nq, k, ef, d_ids, d_dists, d_work_counter, d_stats, t, stream);
         return;
@@ -241,7 +242,6 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
     const size_t per_warp_mid = warp_scratch_bytes(g.pitch, ef, vis_mid, cand_cap);
     // exact visited bitmap for long-row searches: one bit per node per resident warp (1M nodes: 125 KB x ~1 800 warps)
     const int bitmap_words = (t.vis_global_search != 0 && g.count <= t.wide_bitmap_max_nodes) ? ((g.count + 127) / 128) * 4 : 0;
-    retain_freed_scratch();
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
 #define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
     {                                                                                                                           \

@@ -126,9 +126,6 @@ knn_wide_kernel(GraphView g, const float* __restrict__ queries, int nq, int k, i
     s.vis_size = vis_size;
     s.vis_shift = vis_shift;
     s.cap = ef;
-    s.gvis = nullptr;
-    s.gvis_size = 0;
-    s.gvis_shift = 0;
     s.vbm = nullptr;
     s.vbm_words = 0;
 

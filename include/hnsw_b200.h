@@ -236,7 +236,10 @@ HNSW_API int hnsw_get_wide_profile(hnsw_handle handle, unsigned long long* out16
 /* tuning knobs: "vis_size_search", "vis_size_build", "blocks_per_sm", "build_batch_max", "build_batch_ratio",
  * "flags", "zero_copy" (1 = page-locked caller buffers of hnsw_knn_query are accessed in place by the kernel),
  * "wl_min_ef" / "wide_min_ef" (search width from which the non-shifting list / the CTA-per-query kernel are used),
- * "wide_warps", "wide_prefetch", "wide_max_small_batch", "peer_timeout_ms" */
+ * "wide_warps", "wide_prefetch", "wide_max_small_batch", "wide_bitmap_min_ef", "wide_bitmap_max_nodes", "peer_timeout_ms",
+ * "build_tail_fill" (1 = the link kernel of an insertion batch starts under the tail of its select kernel),
+ * "vis_global_search" (1 = exact visited bitmap for searches over rows longer than 128 floats); the full list with
+ * defaults and measurements is struct Tuning in csrc/kernels.hpp.  Unknown keys return -1. */
 HNSW_API int hnsw_set_tuning(hnsw_handle handle, const char* key, int value);
 
 /* Copy the graph to host memory (tests / inspection).  levels[count]; rows0[count][stride0] (-1 padded).

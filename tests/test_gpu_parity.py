@@ -762,5 +762,5 @@ def test_long_row_search_with_exact_visited_bitmap(hnswindex, oracle, tmp_path):
         ref.set_min_nn(150)
         oids, od, oc = ref.knn_query(q, 20, threads=8, counters=True)
         _assert_identical(ids1, d1, oids, od, explain=(oracle, "cosine", data, q))
-        # the oracle counts an exact visited set; the descent is counted a little differently (test_gpu_wide.py)
-        assert exact <= base and 0 <= exact - int(oc[0]) <= 8 * len(q), (exact, int(oc[0]), base)
+        # the oracle counts an exact visited set; it counts a few evaluations of the descent that the GPU does not (test_gpu_wide.py)
+        assert exact <= base and 0 <= int(oc[0]) - exact <= 8 * len(q), (exact, int(oc[0]), base)
