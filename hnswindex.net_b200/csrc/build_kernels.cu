@@ -155,7 +155,7 @@ __device__ __forceinline__ void unlock_node(int* locks, int n, int lane) {
     if (lane == 0) atomicExch(locks + n, 0);
 }
 
-template <int METRIC>
+template <int METRIC, int SPEC = 0>
 __global__ void __launch_bounds__(kThreads, 4)
 build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int list_cap, int cand_cap, int sel_cap,
                   unsigned* work_counter, int* error_flag, u64* prof, const int* ready, int epoch) {
@@ -202,12 +202,12 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __rest
             load_vector(g, n, s.q, lane);
             double nn = 0.0;
             if (METRIC == COSINE) nn = __ldg(g.norm_sqrt + n);
-            batch_dist<METRIC>(g, s, nn, m, lane);
+            batch_dist<METRIC, SPEC>(g, s, nn, m, lane);
             nd_prune += m;
             BeamState st;
             st.n = 0; st.ef = list_cap; st.far_ord = 0xFFFFFFFFu; st.cursor = 0;
             for (int j = 0; j < m; ++j) list_insert(s.list, st, make_key(s.cand_dist[j], s.cand_id[j]), lane);
-            const int nsel = select_neighbors<METRIC>(g, b, s.list, st.n, maxE, lane, nd_prune);
+            const int nsel = select_neighbors<METRIC, SPEC>(g, b, s.list, st.n, maxE, lane, nd_prune);
             for (int j = lane; j < stride; j += 32) row[j] = j < nsel ? b.sel[j] : -1;
             cyc_prune += clock64() - tp;
         }
@@ -305,6 +305,29 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
     HNSW_CUDA_CHECK(cudaMemsetAsync(sel_counter, 0, sizeof(unsigned), stream));
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter + 1, 0, sizeof(unsigned), link_stream));
     int* err = reinterpret_cast<int*>(d_work_counter + 2);
+#define HNSW_LAUNCH_LINK(M, SPECV)                                                                                             \
+    {                                                                                                                           \
+        constexpr int SL = SPECV;                                                                                               \
+        const int g2 = persistent_grid(build_link_kernel<M, SL>, smem_link, t, (int)std::min<long long>((long long)count * (g.stride0 + 1), 1 << 30), w2); \
+        if (d_ready != nullptr) {                                                                                               \
+            /* programmatic dependent launch: resident as soon as all select blocks have started and SM slots are free */      \
+            cudaLaunchConfig_t cfg = {};                                                                                        \
+            cfg.gridDim = dim3((unsigned)g2);                                                                                   \
+            cfg.blockDim = dim3(32u * (unsigned)w2);                                                                            \
+            cfg.dynamicSmemBytes = smem_link * w2;                                                                              \
+            cfg.stream = stream;                                                                                                \
+            cudaLaunchAttribute attr[1];                                                                                        \
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                    \
+            attr[0].val.programmaticStreamSerializationAllowed = 1;                                                             \
+            cfg.attrs = attr;                                                                                                   \
+            cfg.numAttrs = 1;                                                                                                   \
+            HNSW_CUDA_CHECK(cudaLaunchKernelEx(&cfg, build_link_kernel<M, SL>, g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
+                                               d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch));            \
+        } else {                                                                                                                \
+            build_link_kernel<M, SL><<<g2, 32 * w2, smem_link * w2, link_stream>>>(g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
+                                                                               d_work_counter + 1, err, d_build_prof, nullptr, 0); \
+        }                                                                                                                       \
+    }
 #define HNSW_LAUNCH_SELECT_C5(M, SPECV)                                                                                        \
     {                                                                                                                           \
         constexpr int S = SPECV;                                                                                                \
@@ -318,7 +341,7 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
         if (vis16 && g.pitch <= kSegFloats && list_cap_sel <= 1024 && t.build_specialized != 0) {                                \
             /* the C5 shape: rows of one staging segment, MaxCandidates <= 1024, 16-bit tags -- no long-row / large-list code; \
                and for vectors of exactly 128 floats the distance loops have compile-time trip counts */                       \
-            if (g.dim == 128 && g.pitch == 128 && t.build_dim128 != 0)                                                          \
+            if (g.dim == 128 && g.pitch == 128 && t.dim128 != 0)                                                          \
                 HNSW_LAUNCH_SELECT_C5(M, (kSpecVis16 | kSpecShortRows | kSpecMidList | kSpecDim128))                            \
             else                                                                                                                \
                 HNSW_LAUNCH_SELECT_C5(M, (kSpecVis16 | kSpecShortRows | kSpecMidList))                                          \
@@ -335,25 +358,8 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
             HNSW_CUDA_CHECK(cudaEventRecord(select_done, stream));                                                             \
             HNSW_CUDA_CHECK(cudaStreamWaitEvent(link_stream, select_done, 0));                                                 \
         }                                                                                                                       \
-        const int g2 = persistent_grid(build_link_kernel<M>, smem_link, t, (int)std::min<long long>((long long)count * (g.stride0 + 1), 1 << 30), w2); \
-        if (d_ready != nullptr) {                                                                                               \
-            /* programmatic dependent launch: resident as soon as all select blocks have started and SM slots are free */      \
-            cudaLaunchConfig_t cfg = {};                                                                                        \
-            cfg.gridDim = dim3((unsigned)g2);                                                                                   \
-            cfg.blockDim = dim3(32u * (unsigned)w2);                                                                            \
-            cfg.dynamicSmemBytes = smem_link * w2;                                                                              \
-            cfg.stream = stream;                                                                                                \
-            cudaLaunchAttribute attr[1];                                                                                        \
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                    \
-            attr[0].val.programmaticStreamSerializationAllowed = 1;                                                             \
-            cfg.attrs = attr;                                                                                                   \
-            cfg.numAttrs = 1;                                                                                                   \
-            HNSW_CUDA_CHECK(cudaLaunchKernelEx(&cfg, build_link_kernel<M>, g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
-                                               d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch));            \
-        } else {                                                                                                                \
-            build_link_kernel<M><<<g2, 32 * w2, smem_link * w2, link_stream>>>(g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
-                                                                               d_work_counter + 1, err, d_build_prof, nullptr, 0); \
-        }                                                                                                                       \
+        if (g.dim == 128 && g.pitch == 128 && t.dim128 != 0) HNSW_LAUNCH_LINK(M, (kSpecShortRows | kSpecDim128))                 \
+        else HNSW_LAUNCH_LINK(M, 0)                                                                                             \
     }
     switch (metric) {
         case SQ_EUCLID: HNSW_LAUNCH_BUILD(SQ_EUCLID) break;
@@ -363,6 +369,7 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
     }
 #undef HNSW_LAUNCH_BUILD
 #undef HNSW_LAUNCH_SELECT_C5
+#undef HNSW_LAUNCH_LINK
     HNSW_CUDA_CHECK(cudaGetLastError());
 }
 

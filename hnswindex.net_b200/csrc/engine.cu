@@ -137,7 +137,7 @@ void Index::set_tuning(const std::string& key, int value) {
     else if (key == "sync_pieces") tuning_.sync_pieces = value;
     else if (key == "build_overlap") tuning_.build_overlap = value;
     else if (key == "build_specialized") tuning_.build_specialized = value;
-    else if (key == "build_dim128") tuning_.build_dim128 = value;
+    else if (key == "dim128") tuning_.dim128 = value;
     else if (key == "build_flags") tuning_.build_flags = value;
     else if (key == "build_tail_fill") tuning_.build_tail_fill = value;
     else if (key == "exact_tcgen05") tuning_.exact_tcgen05 = value;

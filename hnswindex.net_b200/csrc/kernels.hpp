@@ -25,7 +25,8 @@ struct Tuning {
                               // the select kernel's tail is ~8 % of it)
     int build_flags = 2;        // beam-search flags of the construction search (bit 0: L2-prefetch rows of accepted candidates, bit 1: guess-row load)
     int build_specialized = 1;  // the C5-shaped select kernel instantiation (short rows, MaxCandidates <= 1024, 16-bit tags)
-    int build_dim128 = 1;       // ... and, for vectors of exactly 128 floats, the instantiation whose distance loops have constant trip counts
+    int dim128 = 1;             // vectors of exactly 128 floats: kernel instantiations whose distance loops have compile-time trip counts
+                                // (construction, reverse links, searches with ef > 64; the issue-bound kernels feel their loop control)
     int sync_pieces = 0;      // hnsw_knn_query: pieces a large batch is split into, alternating two streams (0 = 2 for page-locked, 4 for pageable buffers)
     int async_overlap = 1;    // hnsw_knn_query_device_async alternates two streams (consecutive batches overlap in their tails)
     int blocks_per_sm = 0;    // 0 = occupancy query

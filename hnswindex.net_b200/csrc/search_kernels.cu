@@ -241,6 +241,9 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
     const size_t per_warp = warp_scratch_bytes(g.pitch, ef, vis, cand_cap);
     const size_t per_warp_mid = warp_scratch_bytes(g.pitch, ef, vis_mid, cand_cap);
     // exact visited bitmap for long-row searches: one bit per node per resident warp (1M nodes: 125 KB x ~1 800 warps)
+    // vectors of exactly 128 floats: instantiations whose distance loops have compile-time trip counts (beam.cuh kSpecDim128);
+    // not for the ef <= 64 kernel, which runs at the HBM roofline as it is
+    const bool dim128 = t.dim128 != 0 && g.dim == 128 && g.pitch == 128;
     const int bitmap_words = (t.vis_global_search != 0 && g.count <= t.wide_bitmap_max_nodes) ? ((g.count + 127) / 128) * 4 : 0;
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter, 0, sizeof(unsigned), stream));
 #define HNSW_LAUNCH_SEARCH(M)                                                                                                   \
@@ -254,10 +257,17 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
         } else if (layer == 0 && t.wl_min_ef > 0 && ef >= t.wl_min_ef && g.pitch <= kSegFloats &&                               \
                    (long long)g.count <= ((long long)vis_mid << 16)) {                                                          \
             /* wide.cuh: sorted main array + 32 pending keys in registers, merged in one pass: no per-insertion shifting */    \
-            constexpr int S = kSpecShortRows | kSpecWideList | kSpecVis16;                                                      \
-            const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);                 \
-            knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                                \
-                g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);              \
+            if (dim128) {                                                                                                       \
+                constexpr int S = kSpecShortRows | kSpecWideList | kSpecVis16 | kSpecDim128;                                    \
+                const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);             \
+                knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                            \
+                    g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0); \
+            } else {                                                                                                            \
+                constexpr int S = kSpecShortRows | kSpecWideList | kSpecVis16;                                                  \
+                const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);             \
+                knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                            \
+                    g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0); \
+            }                                                                                                                   \
         } else if (layer == 0 && t.wl_min_ef > 0 && ef >= t.wl_min_ef && g.pitch > kSegFloats && bitmap_words == 0 &&          \
                    (long long)g.count <= ((long long)vis << 16)) {                                                              \
             constexpr int S = kSpecWideList | kSpecVis16;                                                                       \
@@ -265,10 +275,17 @@ void launch_knn_search(int metric, const GraphView& g, const float* d_queries, i
             knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp * warps, stream>>>(                                    \
                 g, d_queries, nq, k, ef, 0, vis, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);                  \
         } else if (layer == 0 && g.pitch <= kSegFloats && ef <= 1024 && (long long)g.count <= ((long long)vis_mid << 16)) {     \
-            constexpr int S = kSpecShortRows | kSpecMidList | kSpecVis16;                                                       \
-            const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);                 \
-            knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                                \
-                g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0);              \
+            if (dim128) {                                                                                                       \
+                constexpr int S = kSpecShortRows | kSpecMidList | kSpecVis16 | kSpecDim128;                                     \
+                const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);             \
+                knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                            \
+                    g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0); \
+            } else {                                                                                                            \
+                constexpr int S = kSpecShortRows | kSpecMidList | kSpecVis16;                                                   \
+                const int grid = configure_persistent(knn_search_kernel<M, false, S>, per_warp_mid, t, nq, warps);             \
+                knn_search_kernel<M, false, S><<<grid, 32 * warps, per_warp_mid * warps, stream>>>(                            \
+                    g, d_queries, nq, k, ef, 0, vis_mid, cand_cap, t.flags, d_ids, d_dists, d_work_counter, d_stats, nullptr, 0); \
+            }                                                                                                                   \
         } else if (layer == 0 && g.pitch > kSegFloats && ef <= 1024 && (long long)g.count <= ((long long)vis << 16)) {          \
             /* long rows are DRAM-bound and every re-evaluation is real traffic (C3: 429 GB read for 393 GB of algorithmic      \
                bytes): 16-bit tags (same words, twice the entries) and behind them an exact per-warp visited bitmap in global  \

@@ -314,7 +314,7 @@ __device__ __forceinline__ void beam_search_wl(const GraphView& g, WarpScratch& 
             for (int base = 0; base < m; base += kStageRows) {
                 const int nrows = min(kStageRows, m - base);
                 stage_complete(s.stg);
-                compute_staged<METRIC>(g, s.stg, s.q, qn, s.cand_id, s.cand_dist, base, nrows, lane);
+                compute_staged<METRIC, SPEC>(g, s.stg, s.q, qn, s.cand_id, s.cand_dist, base, nrows, lane);
                 const int nbase = base + kStageRows;
                 if (nbase < m) {
                     stage_issue(g, s.stg, s.cand_id, nbase, min(kStageRows, m - nbase), 0, g.pitch, lane);

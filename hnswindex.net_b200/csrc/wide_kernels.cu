@@ -434,6 +434,7 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
                                  " B, the SM offers " + std::to_string(max_optin));
     const bool v16 = (long long)g.count <= ((long long)vis << 16);
     const bool shortrows = g.pitch <= kSegFloats;
+    const bool dim128 = t.dim128 != 0 && g.dim == 128 && g.pitch == 128;  // constant trip counts in the distance loops (kSpecDim128)
     const bool prefetch = t.wide_prefetch != 0;  // speculative evaluation of the next expansion
     // exact bitmap in global memory instead of the shared-memory table (speculating kernels, wide beams)
     const bool use_bitmap = bitmap_range;
@@ -460,10 +461,10 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     }
     if (use_bitmap) {
         switch (metric) {
-            case SQ_EUCLID: if (shortrows) HNSW_WIDE_BM(SQ_EUCLID, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(SQ_EUCLID, kSpecGvis) break;
-            case EUCLID: if (shortrows) HNSW_WIDE_BM(EUCLID, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(EUCLID, kSpecGvis) break;
-            case COSINE: if (shortrows) HNSW_WIDE_BM(COSINE, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(COSINE, kSpecGvis) break;
-            default: if (shortrows) HNSW_WIDE_BM(UCOSINE, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(UCOSINE, kSpecGvis) break;
+            case SQ_EUCLID: if (shortrows && dim128) HNSW_WIDE_BM(SQ_EUCLID, kSpecShortRows | kSpecGvis | kSpecDim128) else if (shortrows) HNSW_WIDE_BM(SQ_EUCLID, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(SQ_EUCLID, kSpecGvis) break;
+            case EUCLID: if (shortrows && dim128) HNSW_WIDE_BM(EUCLID, kSpecShortRows | kSpecGvis | kSpecDim128) else if (shortrows) HNSW_WIDE_BM(EUCLID, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(EUCLID, kSpecGvis) break;
+            case COSINE: if (shortrows && dim128) HNSW_WIDE_BM(COSINE, kSpecShortRows | kSpecGvis | kSpecDim128) else if (shortrows) HNSW_WIDE_BM(COSINE, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(COSINE, kSpecGvis) break;
+            default: if (shortrows && dim128) HNSW_WIDE_BM(UCOSINE, kSpecShortRows | kSpecGvis | kSpecDim128) else if (shortrows) HNSW_WIDE_BM(UCOSINE, kSpecShortRows | kSpecGvis) else HNSW_WIDE_BM(UCOSINE, kSpecGvis) break;
         }
         return;
     }
@@ -479,7 +480,8 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     }
 #define HNSW_WIDE_SPEC(M)                                                                                                          \
     {                                                                                                                              \
-        if (shortrows && v16) { if (prefetch) HNSW_WIDE_GO(M, kSpecShortRows | kSpecVis16, true) else HNSW_WIDE_GO(M, kSpecShortRows | kSpecVis16, false) } \
+        if (shortrows && v16 && prefetch && dim128) HNSW_WIDE_GO(M, kSpecShortRows | kSpecVis16 | kSpecDim128, true)                  \
+        else if (shortrows && v16) { if (prefetch) HNSW_WIDE_GO(M, kSpecShortRows | kSpecVis16, true) else HNSW_WIDE_GO(M, kSpecShortRows | kSpecVis16, false) } \
         else if (shortrows) { if (prefetch) HNSW_WIDE_GO(M, kSpecShortRows, true) else HNSW_WIDE_GO(M, kSpecShortRows, false) }     \
         else if (v16) { if (prefetch) HNSW_WIDE_GO(M, kSpecVis16, true) else HNSW_WIDE_GO(M, kSpecVis16, false) }                   \
         else { if (prefetch) HNSW_WIDE_GO(M, 0, true) else HNSW_WIDE_GO(M, 0, false) }                                              \

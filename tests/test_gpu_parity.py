@@ -198,13 +198,17 @@ def _rows_as_sets(rows):
     return [frozenset(int(x) for x in r if x >= 0) for r in rows]
 
 
-@pytest.mark.parametrize("metric,dim", [("sq_euclid", 32), ("cosine", 32), ("euclid", 32), ("cosine", 200), ("sq_euclid", 131)])
+@pytest.mark.parametrize("metric,dim", [("sq_euclid", 32), ("cosine", 32), ("euclid", 32), ("cosine", 200), ("sq_euclid", 131),
+                                        ("sq_euclid", 128), ("cosine", 128), ("ucosine", 128)])
 def test_one_by_one_insertion_builds_the_oracle_graph(hnswindex, oracle, metric, dim):
     # Adding items one call at a time is the reference's serial Add: the GPU must produce the same
     # levels, entry point and link sets (row order is free only where the reference's is: the
     # unsorted early return of Heuristic.cs:13-18).
-    # dims above 128 take the long-row (segmented) staging path and the candidate-by-candidate heuristic
+    # dims above 128 take the long-row (segmented) staging path and the candidate-by-candidate heuristic; exactly 128 floats take
+    # the instantiations with compile-time trip counts (kSpecDim128: select and link kernels of the C5 shape)
     v = oracle.random_vectors(dim, 700)
+    if metric == "ucosine":
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
     ref = oracle.OracleIndex(metric, max_edges=8, max_candidates=40, collection_size=64, allow_removals=False)
     ref.add(v)
     gpu = hnswindex.Index(dim, metric)
@@ -764,3 +768,29 @@ def test_long_row_search_with_exact_visited_bitmap(hnswindex, oracle, tmp_path):
         _assert_identical(ids1, d1, oids, od, explain=(oracle, "cosine", data, q))
         # the oracle counts an exact visited set; it counts a few evaluations of the descent that the GPU does not (test_gpu_wide.py)
         assert exact <= base and 0 <= int(oc[0]) - exact <= 8 * len(q), (exact, int(oc[0]), base)
+
+
+@pytest.mark.gpu
+def test_constant_trip_count_instantiations_change_nothing(hnswindex):
+    # Tuning dim128 (beam.cuh kSpecDim128): for 128-float vectors the searches with ef > 64 and the construction kernels run
+    # instantiations whose distance loops have compile-time trip counts -- same bits, same graph
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal((20000, 128)).astype(np.float32)
+    q = rng.standard_normal((500, 128)).astype(np.float32)
+    for metric in ("sq_euclid", "cosine"):
+        built = []
+        for flag in (1, 0):
+            ix = hnswindex.Index(128, metric)
+            ix.set_collection_size(len(data)); ix.set_allow_removals(False); ix._create()
+            ix.set_tuning("dim128", flag)
+            for i in range(0, 3000, 1):      # one by one: deterministic graph
+                ix.add(data[i])
+            built.append((ix, ix.export_layer0()))
+        (a, (la, ra, ea)), (b, (lb, rb, eb)) = built
+        assert np.array_equal(la, lb) and np.array_equal(ra, rb) and ea == eb
+        a.add(data[3000:])                   # batched from here on; searched with both settings on the same graph
+        for ef in (65, 100, 255, 256, 383, 384, 700, 1024, 1500):
+            a.set_min_nn(ef)
+            a.set_tuning("dim128", 1); i1, d1 = a.knn_query(q, 10)
+            a.set_tuning("dim128", 0); i0, d0 = a.knn_query(q, 10)
+            assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32)), (metric, ef)

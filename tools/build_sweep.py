@@ -14,7 +14,7 @@ import hnswindex  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 data, q = bench.make_data(N, 2000)
 truth = None
-cfgs = [dict(), dict(build_dim128=0), dict(build_tail_fill=0), dict()]
+cfgs = [dict(), dict(dim128=0), dict(build_tail_fill=0), dict()]
 for cfg in cfgs:
     ix = hnswindex.Index(128, "sq_euclid")
     ix.set_collection_size(N); ix.set_max_edges(16); ix.set_max_candidates(200); ix.set_allow_removals(False)
