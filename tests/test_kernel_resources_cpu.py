@@ -57,10 +57,12 @@ def test_construction_kernels_have_register_headroom_and_no_spills(needle, max_r
     assert r["regs"] <= max_regs and r["stack"] == 0 and r["spill_st"] == 0 and r["spill_ld"] == 0, r
 
 
-def test_no_kernel_of_the_search_and_build_units_spills_more_than_a_word_or_two():
-    # (a few cosine / unit-cosine instantiations at the 96-register bound of 5 blocks per SM spill one or two 4-byte values; the optional bitmap variant of the long-row kernel three)
-    for unit in ("search_kernels.cu", "build_kernels.cu", "wide_kernels.cu"):
-        bad = {k: v for k, v in _ptxas_report(unit).items() if v["spill_st"] > 32 or v["spill_ld"] > 32}
+def test_no_kernel_of_the_search_and_build_units_spills_more_than_a_few_words():
+    # a few cosine / unit-cosine instantiations at the 96-register bound of 5 blocks per SM spill one to three 4-byte values;
+    # the CTA-per-query kernels run at 64 registers with up to 68 bytes spilled outside their hot loops (measured against
+    # larger budgets, wide_kernels.cu) -- anything beyond that is a change worth looking at
+    for unit, bound in (("search_kernels.cu", 32), ("build_kernels.cu", 0), ("wide_kernels.cu", 96)):
+        bad = {k: v for k, v in _ptxas_report(unit).items() if v["spill_st"] > bound or v["spill_ld"] > bound}
         assert not bad, bad
 
 
