@@ -321,8 +321,16 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
             attr[0].val.programmaticStreamSerializationAllowed = 1;                                                             \
             cfg.attrs = attr;                                                                                                   \
             cfg.numAttrs = 1;                                                                                                   \
-            HNSW_CUDA_CHECK(cudaLaunchKernelEx(&cfg, build_link_kernel<M, SL>, g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
-                                               d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch));            \
+            cudaError_t pe = cudaLaunchKernelEx(&cfg, build_link_kernel<M, SL>, g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
+                                                d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch);            \
+            if (pe == cudaErrorNotSupported || pe == cudaErrorInvalidValue) {                                                   \
+                /* a driver without programmatic stream serialization: plain launch, the ready flags are then always set */    \
+                (void)cudaGetLastError();                                                                                       \
+                cfg.numAttrs = 0;                                                                                               \
+                pe = cudaLaunchKernelEx(&cfg, build_link_kernel<M, SL>, g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
+                                        d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch);                    \
+            }                                                                                                                   \
+            HNSW_CUDA_CHECK(pe);                                                                                                \
         } else {                                                                                                                \
             build_link_kernel<M, SL><<<g2, 32 * w2, smem_link * w2, link_stream>>>(g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
                                                                                d_work_counter + 1, err, d_build_prof, nullptr, 0); \
