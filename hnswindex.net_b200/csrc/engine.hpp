@@ -210,10 +210,13 @@ private:
         float* d_dists = nullptr;
         QueryStats* d_stats = nullptr;
         unsigned* d_counters = nullptr;  // [16]
+        unsigned char* h_stage = nullptr;  // page-locked, device-mapped scratch for small calls (kSmallCallBytes): no copy commands at all
+        unsigned char* d_stage = nullptr;  // ... its device alias
         size_t q_cap = 0, out_cap = 0, stats_cap = 0;
         bool busy = false, created = false;
     };
     static constexpr int kQueryContexts = 4;
+    static constexpr size_t kSmallCallBytes = 64 * 1024;  // queries + results of a call that goes through the mapped scratch
     QueryCtx qctx_[kQueryContexts];  // [0] runs on stream_ (set_stream applies), the others on their own streams
     std::mutex ctx_mu_, stats_mu_;
     std::condition_variable ctx_cv_;

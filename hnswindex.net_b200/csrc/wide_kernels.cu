@@ -424,8 +424,12 @@ void launch_knn_wide(int metric, const GraphView& g, const float* d_queries, int
     // exact visited bitmap in global memory instead of the shared-memory table: one bit per node per resident query must stay
     // L2-resident, so only up to wide_bitmap_max_nodes (2M nodes = 256 KB per query); larger indexes keep the table
     const bool bitmap_range = t.wide_prefetch != 0 && t.wide_bitmap_min_ef > 0 && ef >= t.wide_bitmap_min_ef && g.count <= t.wide_bitmap_max_nodes;
-    int warps = t.wide_warps > 0 ? t.wide_warps : (g.stride0 > 32 ? 3 : 2);
+    // ... but a call with fewer queries than SMs leaves room for a second helper on every SM: a single query at ef 48 is answered in
+    // 191 instead of 238 us of kernel time with it (a third helper adds nothing)
+    int warps = t.wide_warps > 0 ? t.wide_warps : ((g.stride0 > 32 || nq <= device_sm_count()) ? 3 : 2);
     warps = std::max(2, std::min(kWarpsPerBlock, warps));
+    // (the second helper's staging buffer must not be what pushes a very wide list out of shared memory)
+    if (t.wide_warps <= 0 && warps == 3 && g.stride0 <= 32 && wide_smem_bytes(3, g.pitch, ef, bitmap_range ? 0 : 64, cand_cap) > (size_t)max_optin) warps = 2;
     // visited table: 4 ef entries when they fit (the setting of the one-warp kernel), else what the shared memory leaves
     int vis = t.vis_size_search > 0 ? std::max(64, pow2_floor((size_t)t.vis_size_search)) : std::max(256, pow2_floor((size_t)2 * ef));
     const bool can16 = (long long)g.count <= (64ll << 16);
