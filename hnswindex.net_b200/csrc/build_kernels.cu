@@ -229,13 +229,14 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __rest
         if (ready != nullptr) {  // tail fill: this node's rows may still be in the making (select kernel still running)
             int ok = 1;
             if (lane == 0) {
-                unsigned spins = 0;
+                unsigned spins = 0, nap = 256;
                 int f;
                 for (;;) {
                     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(ready + v) : "memory");
                     if (f == epoch) break;
-                    __nanosleep(256);
-                    if (++spins > (1u << 22)) { ok = 0; atomicExch(error_flag, 1); break; }  // never hang the GPU
+                    __nanosleep(nap);
+                    if (nap < 4096) nap <<= 1;
+                    if (++spins > (1u << 20)) { ok = 0; atomicExch(error_flag, 1); break; }  // ~4 s: never hang the GPU
                 }
             }
             ok = __shfl_sync(FULL, ok, 0);
@@ -285,7 +286,9 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
                         cudaStream_t link_stream, cudaEvent_t select_done, int* d_ready, int epoch) {
     if (count <= 0) return;
     if (link_stream == nullptr) link_stream = stream;
-    if (link_stream != stream || t.build_tail_fill == 0) d_ready = nullptr;  // tail fill: both kernels in one stream
+    // tail fill: both kernels in one stream; not for a handful of nodes (one Add per call: nothing to fill, and the waiting link
+    // blocks cost the lone select warp 70 us)
+    if (link_stream != stream || t.build_tail_fill == 0 || count < 64) d_ready = nullptr;
     const int maxE0 = 2 * g.max_edges;
     const int list_cap_sel = std::max(efc, 1);
     const int list_cap_link = maxE0 + 1;
