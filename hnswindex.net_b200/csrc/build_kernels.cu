@@ -158,7 +158,8 @@ __device__ __forceinline__ void unlock_node(int* locks, int n, int lane) {
 template <int METRIC, int SPEC = 0>
 __global__ void __launch_bounds__(kThreads, 4)
 build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __restrict__ new_ids, int count, int list_cap, int cand_cap, int sel_cap,
-                  unsigned* work_counter, int* error_flag, u64* prof, const int* ready, int epoch) {
+                  unsigned* work_counter, int* error_flag, u64* prof, const int* ready, int epoch, const unsigned* sel_counter,
+                  unsigned sel_fetches) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = build_scratch_bytes(g.pitch, list_cap, 64, cand_cap, sel_cap);
@@ -224,7 +225,22 @@ build_link_kernel(GraphView g, const int* __restrict__ levels, const int* __rest
         unsigned wi = 0;
         if (lane == 0) wi = atomicAdd(work_counter, 1u);
         wi = __shfl_sync(FULL, wi, 0);
-        if (wi >= pairs + (unsigned)count) break;
+        if (wi >= pairs + (unsigned)count) {
+            // Tail fill: this kernel must not end before every select warp has done its last (empty) fetch from the select work
+            // counter -- the next batch resets that word.  The one warp that draws the first empty index of THIS queue waits
+            // until the select counter shows all of them: count real fetches + one empty fetch per select warp.
+            if (ready != nullptr && wi == pairs + (unsigned)count && lane == 0) {
+                unsigned spins = 0, nap = 64, seen;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sel_counter) : "memory");
+                    if (seen >= sel_fetches) break;
+                    __nanosleep(nap);
+                    if (nap < 4096) nap <<= 1;
+                    if (++spins > (1u << 20)) { atomicExch(error_flag, 1); break; }
+                }
+            }
+            break;
+        }
         const int v = __ldg(new_ids + (wi < pairs ? wi / (unsigned)g.stride0 : wi - pairs));
         if (ready != nullptr) {  // tail fill: this node's rows may still be in the making (select kernel still running)
             int ok = 1;
@@ -280,7 +296,7 @@ static int persistent_grid(Kern kern, size_t smem_per_warp, const Tuning& t, int
     return persistent_launch(kern, smem_per_warp, t.blocks_per_sm, work_items, warps);
 }
 
-// d_work_counter: [0] select work, [1] link work, [2] error flag, [9] select work of every other batch (tail fill)
+// d_work_counter: [0] select work, [1] link work, [2] error flag
 void launch_build_batch(int metric, const GraphView& g, const int* d_levels, const int* d_new_ids, int count, int efc, unsigned* d_work_counter,
                         u64* d_build_prof, const Tuning& t, cudaStream_t stream,
                         cudaStream_t link_stream, cudaEvent_t select_done, int* d_ready, int epoch) {
@@ -302,9 +318,8 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
     const bool vis16 = (long long)g.count <= ((long long)vis << 16);
     const size_t smem_sel = build_scratch_bytes(g.pitch, list_cap_sel, vis, cand_cap, sel_cap);   // per warp
     const size_t smem_link = build_scratch_bytes(g.pitch, list_cap_link, 64, cand_cap, sel_cap);  // per warp
-    // Tail fill: a batch's link kernel can end while the last select warps are still on their way out (one more fetch from the
-    // work counter each), so consecutive batches take their select work from alternating words
-    unsigned* sel_counter = (d_ready != nullptr && (epoch & 1)) ? d_work_counter + 9 : d_work_counter;
+    unsigned* sel_counter = d_work_counter;
+    int sel_warps = 0;  // warps of the select launch (the link kernel waits for the last fetch of every one of them, see there)
     HNSW_CUDA_CHECK(cudaMemsetAsync(sel_counter, 0, sizeof(unsigned), stream));
     HNSW_CUDA_CHECK(cudaMemsetAsync(d_work_counter + 1, 0, sizeof(unsigned), link_stream));
     int* err = reinterpret_cast<int*>(d_work_counter + 2);
@@ -325,24 +340,27 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
             cfg.attrs = attr;                                                                                                   \
             cfg.numAttrs = 1;                                                                                                   \
             cudaError_t pe = cudaLaunchKernelEx(&cfg, build_link_kernel<M, SL>, g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
-                                                d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch);            \
+                                                d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch, (const unsigned*)sel_counter, \
+                                                (unsigned)(count + sel_warps));            \
             if (pe == cudaErrorNotSupported || pe == cudaErrorInvalidValue) {                                                   \
                 /* a driver without programmatic stream serialization: plain launch, the ready flags are then always set */    \
                 (void)cudaGetLastError();                                                                                       \
                 cfg.numAttrs = 0;                                                                                               \
                 pe = cudaLaunchKernelEx(&cfg, build_link_kernel<M, SL>, g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
-                                        d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch);                    \
+                                        d_work_counter + 1, err, d_build_prof, (const int*)d_ready, epoch, (const unsigned*)sel_counter, \
+                                                (unsigned)(count + sel_warps));                    \
             }                                                                                                                   \
             HNSW_CUDA_CHECK(pe);                                                                                                \
         } else {                                                                                                                \
             build_link_kernel<M, SL><<<g2, 32 * w2, smem_link * w2, link_stream>>>(g, d_levels, d_new_ids, count, list_cap_link, cand_cap, sel_cap, \
-                                                                               d_work_counter + 1, err, d_build_prof, nullptr, 0); \
+                                                                               d_work_counter + 1, err, d_build_prof, nullptr, 0, nullptr, 0u); \
         }                                                                                                                       \
     }
 #define HNSW_LAUNCH_SELECT_C5(M, SPECV)                                                                                        \
     {                                                                                                                           \
         constexpr int S = SPECV;                                                                                                \
         const int g1 = persistent_grid(build_select_kernel<M, S>, smem_sel, t, count, w1);                                     \
+        sel_warps = g1 * w1;                                                                                                    \
         build_select_kernel<M, S><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                      \
             g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, t.build_flags, d_ready, epoch); \
     }
@@ -358,10 +376,12 @@ void launch_build_batch(int metric, const GraphView& g, const int* d_levels, con
                 HNSW_LAUNCH_SELECT_C5(M, (kSpecVis16 | kSpecShortRows | kSpecMidList))                                          \
         } else if (vis16) {                                                                                                     \
             const int g1 = persistent_grid(build_select_kernel<M, kSpecVis16>, smem_sel, t, count, w1);                        \
+            sel_warps = g1 * w1;                                                                                                \
             build_select_kernel<M, kSpecVis16><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                        \
                 g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, t.build_flags, d_ready, epoch); \
         } else {                                                                                                                \
             const int g1 = persistent_grid(build_select_kernel<M, 0>, smem_sel, t, count, w1);                                 \
+            sel_warps = g1 * w1;                                                                                                \
             build_select_kernel<M, 0><<<g1, 32 * w1, smem_sel * w1, stream>>>(                                                 \
                 g, d_levels, d_new_ids, count, efc, list_cap_sel, vis, cand_cap, sel_cap, sel_counter, d_build_prof, t.build_flags, d_ready, epoch); \
         }                                                                                                                       \
