@@ -177,7 +177,7 @@ private:
     int* d_adjU_ = nullptr;
     int* d_locks_ = nullptr;
     int* d_levels_ = nullptr;
-    unsigned* d_counters_ = nullptr;  // [0..2] build (+ [9]), [3] search, [4..5] remove, [6..7] scatter, [8] second query stream
+    unsigned* d_counters_ = nullptr;  // [0..2] build, [3] search, [4..5] remove, [6..7] scatter, [8] second query stream
     u64* d_build_prof_ = nullptr;     // [16]
     void *rm_small_ = nullptr, *rm_aff_ = nullptr;   // remove() scratch (grow-only)
     size_t rm_small_bytes_ = 0, rm_aff_bytes_ = 0;
